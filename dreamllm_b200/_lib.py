@@ -1,0 +1,102 @@
+"""ctypes loader (and in-tree builder) for libdreamllm_sm100.so — the C-ABI boundary (include/dreamllm_sm100.h).
+
+There is NO fallback: if the shared library is missing or a call returns non-zero, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libdreamllm_sm100.so")
+SOURCES = ["capi.cu", "gemm_sm100.cu", "elementwise.cu", "attn_sm100.cu"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
+]
+
+
+def _needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(_CSRC, f) for f in os.listdir(_CSRC)] + [os.path.join(_HERE, "..", "include", "dreamllm_sm100.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc-compile every .cu for sm_100a into dreamllm_b200/libdreamllm_sm100.so (in-tree, travels with gpurun)."""
+    if not force and not _needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    objs = []
+    procs = []
+    os.makedirs(os.path.join(_HERE, "build"), exist_ok=True)
+    for src in SOURCES:
+        obj = os.path.join(_HERE, "build", src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(_CSRC, src), "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{out}")
+        if verbose and out:
+            print(out)
+    cmd = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise RuntimeError(f"link failed:\n{out.stdout}")
+    return LIB_PATH
+
+
+_vp, _i, _l, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/dreamllm_sm100.h one-to-one
+SIGNATURES = {
+    "dllm_version": (_i, []),
+    "dllm_error_string": (ctypes.c_char_p, [_i]),
+    "dllm_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _i, _i, _i, _i, _vp]),
+    "dllm_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "dllm_rmsnorm_bwd_workspace_bytes": (_sz, [_i, _i]),
+    "dllm_rmsnorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _vp, _sz, _i, _i, _vp]),
+    "dllm_rope_inplace": (_i, [_vp, _vp, _vp, _vp, _l, _i, _i, _i, _i, _vp]),
+    "dllm_swiglu_fwd": (_i, [_vp, _vp, _l, _i, _i, _vp]),
+    "dllm_swiglu_bwd": (_i, [_vp, _vp, _vp, _l, _i, _i, _vp]),
+    "dllm_add_bf16": (_i, [_vp, _vp, _vp, _l, _vp]),
+    "dllm_cross_entropy": (_i, [_vp, _vp, _vp, _f, _vp, _l, _i, _i, _i, _vp]),
+    "dllm_embedding_fwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "dllm_embedding_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dllm_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _l, _l, _i, _f, _vp]),
+    "dllm_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
+    "dllm_attn_bwd": (_i, [_vp] * 11 + [_sz, _i, _i, _i, _i, _l, _l, _l, _i, _f, _vp]),
+}
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                "dreamllm_b200 has no CPU / eager fallback by design."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)  # AttributeError if the ABI is incomplete
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().dllm_error_string(rc).decode()
+        raise RuntimeError(f"{what} failed: {msg} (code {rc})")

@@ -1,0 +1,366 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a (bf16 x bf16 -> fp32 in TMEM -> bf16|fp32).
+//
+//   C[M,N] = op(A) * op(B)      A "K-major":  memory [M, K] row-major        (x, dY)
+//                               A "MN-major": memory [K, M] row-major        (dY^T for wgrad)
+//                               B "K-major":  memory [N, K] row-major        (nn.Linear weight, fwd)
+//                               B "MN-major": memory [K, N] row-major        (weight for dgrad, x for wgrad)
+//
+// This single kernel serves every dense contraction on the DreamLLM hot path (reference call sites:
+// modeling_dreamllm.py:336-338, :395 (q/k/v/o_proj), :237 (gate/up/down_proj), :1452 (lm_head), and their
+// autograd dgrad/wgrad), replacing the cuBLAS calls torch makes for nn.Linear.
+//
+// Structure (one CTA per SM, or one CTA *pair* per two SMs with cta_group::2):
+//   warp 0    TMA producer: global -> 128B-swizzled smem stages, mbarrier complete_tx
+//   warp 1    MMA issuer (one elected thread): tcgen05.mma, accumulators in TMEM, double-buffered (2 x 256 cols)
+//   warp 2    TMEM allocator
+//   warps 4-7 epilogue: tcgen05.ld -> convert -> swizzled smem -> per-warp TMA store (overlaps next tile's MMAs)
+#include "common.cuh"
+#include "gemm_sm100.h"
+
+namespace dllm {
+
+constexpr int BM = 128;  // A rows per CTA == TMEM lanes
+constexpr int BN = 256;  // UMMA N
+constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle line
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 256;
+constexpr int kEpiWarp0 = 4;
+
+template <int kCta>
+struct GemmCfg {
+  static constexpr int kBRows = BN / kCta;  // rows of B each CTA loads
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = kBRows * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (kCta == 1) ? 4 : 6;
+  static constexpr int kEpiBufBytes = 32 * 128;                // 32 rows x 128 B per warp-store
+  static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;       // 4 warps x double buffer
+  static constexpr int kBarBytes = 1024;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024 /*align slack*/;
+};
+
+template <int kCta, bool kAMN, bool kBMN, typename OutT>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m) {
+  using Cfg = GemmCfg<kCta>;
+  constexpr int kStages = Cfg::kStages;
+  constexpr bool kOutF32 = sizeof(OutT) == 4;
+  constexpr int CH = kOutF32 ? 32 : 64;  // output columns per 128-byte store line
+  constexpr int kChunks = BN / CH;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* epi_smem = smem + kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_smem + Cfg::kEpiBytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp_idx = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = (kCta == 2) ? cluster_ctarank() : 0u;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tma_a);
+    tma_prefetch_desc(&tma_b);
+    tma_prefetch_desc(&tma_c);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 4 * kCta);  // one arrive per epilogue warp of every CTA in the pair
+    }
+    fence_mbar_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc<kCta>(tmem_ptr_smem, 512);
+    tmem_relinquish<kCta>();
+  }
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  // ---- persistent tile schedule (identical sequence in every role) ----
+  const int tile_m = BM * kCta;
+  const int num_m_tiles = (M + tile_m - 1) / tile_m;
+  const int num_n_tiles = (N + BN - 1) / BN;
+  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_kb = (K + BK - 1) / BK;
+  const int cluster_id = blockIdx.x / kCta;
+  const int num_clusters = gridDim.x / kCta;
+  const int tiles_per_group = group_m * num_n_tiles;
+
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int g = tile / tiles_per_group;
+    const int first_m = g * group_m;
+    const int gsize = min(group_m, num_m_tiles - first_m);
+    const int r = tile - g * tiles_per_group;
+    m_blk = first_m + r % gsize;
+    n_blk = r / gsize;
+  };
+
+  if (warp_idx == 0 && lane == 0) {
+    // ======================= TMA producer =======================
+    int stage = 0;
+    uint32_t phase = 0;
+    const uint32_t full0_cluster = (kCta == 2) ? mapa_shared(smem_u32(&full_bar[0]), 0) : 0u;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blk, n_blk);
+      const int m0 = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
+      const int n0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+        uint8_t* a_s = smem + stage * Cfg::kStageBytes;
+        uint8_t* b_s = a_s + Cfg::kABytes;
+        const int k0 = kb * BK;
+        if constexpr (kCta == 1) {
+          mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if constexpr (!kAMN) {
+            tma_load_2d(a_s, &tma_a, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(a_s + i * 8192, &tma_a, &full_bar[stage], m0 + i * 64, k0);
+          }
+          if constexpr (!kBMN) {
+            tma_load_2d(b_s, &tma_b, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < Cfg::kBRows / 64; ++i)
+              tma_load_2d(b_s + i * 8192, &tma_b, &full_bar[stage], n0 + i * 64, k0);
+          }
+        } else {
+          // both CTAs' bytes are counted on the leader's barrier
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+          const uint32_t fb = full0_cluster + stage * 8;
+          if constexpr (!kAMN) {
+            tma_load_2d_2cta(a_s, &tma_a, fb, k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d_2cta(a_s + i * 8192, &tma_a, fb, m0 + i * 64, k0);
+          }
+          if constexpr (!kBMN) {
+            tma_load_2d_2cta(b_s, &tma_b, fb, k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < Cfg::kBRows / 64; ++i) tma_load_2d_2cta(b_s + i * 8192, &tma_b, fb, n0 + i * 64, k0);
+          }
+        }
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp_idx == 1 && lane == 0 && cta_rank == 0) {
+    // ======================= MMA issuer (leader CTA only) =======================
+    constexpr uint32_t idesc = make_idesc_bf16(BM * kCta, BN, kAMN, kBMN);
+    constexpr uint32_t a_adv = kAMN ? 2048u : 32u;  // bytes per UMMA_K step
+    constexpr uint32_t b_adv = kBMN ? 2048u : 32u;
+    constexpr uint32_t a_lbo = kAMN ? 8192u : 16u;
+    constexpr uint32_t b_lbo = kBMN ? 8192u : 16u;
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 2);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + as * BN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase, 3);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t b_base = a_base + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t adesc = make_smem_desc(a_base + k * a_adv, a_lbo, 1024);
+          const uint64_t bdesc = make_smem_desc(b_base + k * b_adv, b_lbo, 1024);
+          umma_ss<kCta>(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        if constexpr (kCta == 1) umma_commit(&empty_bar[stage]); else umma_commit_2cta(&empty_bar[stage], 0b11);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if constexpr (kCta == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_2cta(&tmem_full_bar[as], 0b11);
+    }
+  } else if (warp_idx >= kEpiWarp0) {
+    // ======================= epilogue warps =======================
+    const int wq = warp_idx - kEpiWarp0;  // TMEM lane quarter: this warp may touch lanes [32*wq, 32*wq+32)
+    uint8_t* my_epi = epi_smem + wq * 2 * Cfg::kEpiBufBytes;
+    const uint32_t tmem_empty0_cluster = (kCta == 2) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
+    int it = 0;
+    int buf = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blk, n_blk);
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int row0 = m_blk * tile_m + static_cast<int>(cta_rank) * BM + wq * 32;
+      const int col0 = n_blk * BN;
+      mbar_wait(&tmem_full_bar[as], aphase, 4);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * BN;
+#pragma unroll 1
+      for (int c = 0; c < kChunks; ++c) {
+        uint32_t v[kOutF32 ? 32 : 64];
+        tmem_ld32(taddr0 + c * CH, v);
+        if constexpr (!kOutF32) tmem_ld32(taddr0 + c * CH + 32, v + 32);
+        tmem_ld_wait();
+        // the staging buffer we are about to overwrite was handed to TMA two stores ago
+        if (lane == 0) tma_store_wait_read<1>();
+        __syncwarp();
+        uint8_t* dst = my_epi + buf * Cfg::kEpiBufBytes + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          uint4 q;
+          if constexpr (kOutF32) {
+            q = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+            q.x = pack_bf16(__uint_as_float(v[8 * j + 0]), __uint_as_float(v[8 * j + 1]));
+            q.y = pack_bf16(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+            q.z = pack_bf16(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]));
+            q.w = pack_bf16(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+          }
+          *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = q;  // 128B swizzle: chunk ^= row % 8
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          if (row0 < M && col0 + c * CH < N)
+            tma_store_2d(&tma_c, my_epi + buf * Cfg::kEpiBufBytes, col0 + c * CH, row0);
+          tma_store_commit();
+        }
+        buf ^= 1;
+      }
+      // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if constexpr (kCta == 1) mbar_arrive(&tmem_empty_bar[as]); else mbar_arrive_cluster(tmem_empty0_cluster + as * 8);
+      }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  // ---- teardown ----
+  tc_fence_before();
+  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if (warp_idx == 2) tmem_dealloc<kCta>(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2D row-major tensor [rows, cols] with row stride `ld` elements; box = [box_rows, box_cols]; 128B swizzle.
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return DLLM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * elem_bytes) & 15)) return DLLM_ERR_ALIGN;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstr[1] = {ld * elem_bytes};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : DLLM_ERR_TMAP;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return n;
+}
+
+template <int kCta, bool kAMN, bool kBMN, typename OutT>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<kCta>;
+  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
+      return DLLM_ERR_LAUNCH;
+    attr_set = true;
+  }
+  const int tile_m = BM * kCta;
+  const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+  const int max_clusters = num_sms() / kCta;
+  const int clusters = num_tiles < max_clusters ? num_tiles : max_clusters;
+  const int group_m = (kCta == 2) ? 8 : 16;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(clusters * kCta);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCta;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m);
+  return e == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
+              int b_mn, int out_fp32, int cta_pair, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return DLLM_ERR_SHAPE;
+  const int kcta = (cta_pair < 0) ? (M > BM ? 2 : 1) : (cta_pair ? 2 : 1);
+  CUtensorMap ta, tb, tc;
+  int rc;
+  // A
+  if (!a_mn) rc = make_tmap_2d(&ta, A, 2, M, K, lda, BM, BK);
+  else rc = make_tmap_2d(&ta, A, 2, K, M, lda, BK, 64);
+  if (rc) return rc;
+  // B
+  if (!b_mn) rc = make_tmap_2d(&tb, B, 2, N, K, ldb, BN / kcta, BK);
+  else rc = make_tmap_2d(&tb, B, 2, K, N, ldb, BK, 64);
+  if (rc) return rc;
+  // C: per-warp store boxes of 32 rows x 128 bytes
+  rc = make_tmap_2d(&tc, C, out_fp32 ? 4 : 2, M, N, ldc, 32, out_fp32 ? 32 : 64);
+  if (rc) return rc;
+
+#define DLLM_GEMM_CASE(CTA, AMN, BMN)                                                                 \
+  if (kcta == CTA && (a_mn != 0) == AMN && (b_mn != 0) == BMN) {                                      \
+    return out_fp32 ? launch_gemm<CTA, AMN, BMN, float>(ta, tb, tc, M, N, K, stream)                  \
+                    : launch_gemm<CTA, AMN, BMN, bf16>(ta, tb, tc, M, N, K, stream);                  \
+  }
+  DLLM_GEMM_CASE(1, false, false)
+  DLLM_GEMM_CASE(1, false, true)
+  DLLM_GEMM_CASE(1, true, true)
+  DLLM_GEMM_CASE(1, true, false)
+  DLLM_GEMM_CASE(2, false, false)
+  DLLM_GEMM_CASE(2, false, true)
+  DLLM_GEMM_CASE(2, true, true)
+  DLLM_GEMM_CASE(2, true, false)
+#undef DLLM_GEMM_CASE
+  return DLLM_ERR_SHAPE;
+}
+
+}  // namespace dllm

@@ -1,0 +1,25 @@
+// Internal (C++) declarations shared between the kernels and the C-ABI layer.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define DLLM_OK 0
+#define DLLM_ERR_SHAPE (-1)
+#define DLLM_ERR_ALIGN (-2)
+#define DLLM_ERR_DRIVER (-3)
+#define DLLM_ERR_TMAP (-4)
+#define DLLM_ERR_LAUNCH (-5)
+#define DLLM_ERR_UNSUPPORTED (-6)
+
+namespace dllm {
+
+int num_sms();
+int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
+                 uint32_t box_rows, uint32_t box_cols);
+
+// C[M,N] = op(A) op(B); see gemm_sm100.cu for the operand conventions. ld* are row strides in elements.
+int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
+              int b_mn, int out_fp32, int cta_pair, cudaStream_t stream);
+
+}  // namespace dllm

@@ -1,0 +1,28 @@
+// Internal C++ declarations of the non-GEMM ops (definitions: elementwise.cu, attn_sm100.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+namespace dllm {
+int rmsnorm_fwd(const void* x, const void* add, const void* w, void* x_out, void* y, float* rstd, int T, int H, float eps,
+                cudaStream_t s);
+size_t rmsnorm_bwd_workspace(int T, int H);
+int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx, void* dw,
+                int dw_accumulate, void* workspace, size_t workspace_bytes, int T, int H, cudaStream_t s);
+int rope_inplace(void* buf, const void* cos_t, const void* sin_t, const int* pos, long ld, int T, int heads_total,
+                 int head_dim, int mode, cudaStream_t s);
+int swiglu_fwd(const void* gu, void* act, long ld_gu, int T, int I, cudaStream_t s);
+int swiglu_bwd(const void* dact, const void* gu, void* dgu, long ld_gu, int T, int I, cudaStream_t s);
+int add_bf16(const void* a, const void* b, void* o, long n, cudaStream_t s);
+int cross_entropy(void* logits, const long long* labels, float* loss, float dloss, void* workspace, long ld, int T, int V,
+                  int write_grad, cudaStream_t s);
+int embedding_fwd(const long long* ids, const void* W, void* out, int T, int H, cudaStream_t s);
+int embedding_bwd(const long long* sorted_ids, const long long* order, const void* dy, void* dW, int T, int H,
+                  int accumulate, cudaStream_t s);
+int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int nh,
+             int d, long ld_qkv, long ld_o, int causal, float scale, cudaStream_t s);
+size_t attn_bwd_workspace(int B, int S, int nh, int d);
+int attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
+             void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int S, int nh, int d,
+             long ld_qkv, long ld_o, long ld_dqkv, int causal, float scale, cudaStream_t s);
+}  // namespace dllm

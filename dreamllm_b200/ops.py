@@ -1,0 +1,205 @@
+"""Thin torch-tensor wrappers over the C ABI (include/dreamllm_sm100.h).
+
+torch is used here only for device memory and the current stream; every function hands raw device pointers to
+libdreamllm_sm100.so and raises RuntimeError on a non-zero return code.  No function here has a torch / CPU
+fallback: a CPU tensor is an error.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import check, lib
+
+BF16 = torch.bfloat16
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _chk_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dreamllm_b200 ops need CUDA tensors (there is no CPU fallback)")
+
+
+# ----------------------------------------------------------------------------------------------- GEMM
+def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out: torch.Tensor | None = None,
+         out_dtype=BF16, cta_pair: int = -1) -> torch.Tensor:
+    """C[M,N] = op(A) @ op(B) on tcgen05.
+
+    a_mn=False: a is [M,K];  a_mn=True: a is [K,M] (uses a^T)
+    b_mn=False: b is [N,K] (nn.Linear weight layout, C = A @ B^T);  b_mn=True: b is [K,N] (C = A @ B)
+    Inputs are 2-D bf16 with unit inner stride (row stride may exceed the width: column-slice views are fine).
+    """
+    _chk_cuda(a, b, out)
+    assert a.dtype == BF16 and b.dtype == BF16 and a.dim() == 2 and b.dim() == 2
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    if a_mn:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    assert K == Kb, f"contraction mismatch {K} vs {Kb}"
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+    assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (BF16, torch.float32)
+    rc = lib().dllm_gemm_bf16(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
+                              int(b_mn), int(out.dtype == torch.float32), cta_pair, _stream())
+    check(rc, "dllm_gemm_bf16")
+    return out
+
+
+def linear(x2d: torch.Tensor, weight: torch.Tensor, out=None, out_dtype=BF16) -> torch.Tensor:
+    """y = x @ W^T (nn.Linear forward)."""
+    return gemm(x2d, weight, out=out, out_dtype=out_dtype)
+
+
+def linear_dgrad(dy2d: torch.Tensor, weight: torch.Tensor, out=None) -> torch.Tensor:
+    """dx = dy @ W."""
+    return gemm(dy2d, weight, b_mn=True, out=out)
+
+
+def linear_wgrad(dy2d: torch.Tensor, x2d: torch.Tensor, out=None, out_dtype=BF16) -> torch.Tensor:
+    """dW = dy^T @ x."""
+    return gemm(dy2d, x2d, a_mn=True, b_mn=True, out=out, out_dtype=out_dtype)
+
+
+# ----------------------------------------------------------------------------------------------- norms
+def rmsnorm_fwd(x2d, weight, eps, add=None, want_sum=True):
+    """returns (y, rstd, x_sum) — x_sum = bf16(x + add) when `add` is given else x itself."""
+    _chk_cuda(x2d, weight, add)
+    T, H = x2d.shape
+    assert x2d.is_contiguous() and x2d.dtype == BF16 and weight.dtype == BF16
+    y = torch.empty_like(x2d)
+    rstd = torch.empty(T, device=x2d.device, dtype=torch.float32)
+    x_out = torch.empty_like(x2d) if add is not None else None
+    if add is not None:
+        assert add.is_contiguous() and add.shape == x2d.shape
+    check(lib().dllm_rmsnorm_fwd(_p(x2d), _p(add), _p(weight), _p(x_out), _p(y), _p(rstd), T, H, float(eps), _stream()),
+          "dllm_rmsnorm_fwd")
+    return y, rstd, (x_out if add is not None else x2d)
+
+
+def rmsnorm_bwd(dy2d, x2d, weight, rstd, dres=None, need_dw=True):
+    """returns (dx, dweight|None); dx includes `dres` (the residual-branch gradient) when given."""
+    _chk_cuda(dy2d, x2d, weight, rstd, dres)
+    T, H = x2d.shape
+    assert dy2d.is_contiguous() and x2d.is_contiguous()
+    dx = torch.empty_like(x2d)
+    dw = torch.empty_like(weight) if need_dw else None
+    wsb = lib().dllm_rmsnorm_bwd_workspace_bytes(T, H) if need_dw else 0
+    ws = torch.empty(max(wsb, 4), device=x2d.device, dtype=torch.uint8)
+    check(lib().dllm_rmsnorm_bwd(_p(dy2d), _p(x2d), _p(weight), _p(rstd), _p(dres), _p(dx), _p(dw), 0, _p(ws), wsb, T, H,
+                                 _stream()), "dllm_rmsnorm_bwd")
+    return dx, dw
+
+
+# ----------------------------------------------------------------------------------------------- rope / swiglu / add
+def rope_(buf2d, cos_t, sin_t, pos_i32, heads_total, head_dim, backward=False):
+    """In place on the first heads_total*head_dim columns of buf2d ([T, ld])."""
+    _chk_cuda(buf2d, cos_t, sin_t, pos_i32)
+    T = buf2d.shape[0]
+    assert buf2d.stride(1) == 1 and pos_i32.dtype == torch.int32 and pos_i32.numel() == T
+    assert cos_t.dtype == BF16 and cos_t.is_contiguous() and cos_t.shape[1] == head_dim
+    check(lib().dllm_rope_inplace(_p(buf2d), _p(cos_t), _p(sin_t), _p(pos_i32), buf2d.stride(0), T, heads_total, head_dim,
+                                  -1 if backward else 1, _stream()), "dllm_rope_inplace")
+    return buf2d
+
+
+def swiglu_fwd(gu2d, inter):
+    _chk_cuda(gu2d)
+    T = gu2d.shape[0]
+    assert gu2d.shape[1] == 2 * inter and gu2d.stride(1) == 1
+    act = torch.empty((T, inter), device=gu2d.device, dtype=BF16)
+    check(lib().dllm_swiglu_fwd(_p(gu2d), _p(act), gu2d.stride(0), T, inter, _stream()), "dllm_swiglu_fwd")
+    return act
+
+
+def swiglu_bwd(dact2d, gu2d, inter, out=None):
+    _chk_cuda(dact2d, gu2d)
+    T = gu2d.shape[0]
+    assert dact2d.is_contiguous() and gu2d.is_contiguous()
+    dgu = torch.empty_like(gu2d) if out is None else out
+    check(lib().dllm_swiglu_bwd(_p(dact2d), _p(gu2d), _p(dgu), gu2d.stride(0), T, inter, _stream()), "dllm_swiglu_bwd")
+    return dgu
+
+
+def add(a, b, out=None):
+    _chk_cuda(a, b)
+    assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
+    out = torch.empty_like(a) if out is None else out
+    check(lib().dllm_add_bf16(_p(a), _p(b), _p(out), a.numel(), _stream()), "dllm_add_bf16")
+    return out
+
+
+# ----------------------------------------------------------------------------------------------- loss / embedding
+def cross_entropy_(logits2d, shifted_labels, dloss=1.0, write_grad=True):
+    """loss (fp32 scalar tensor); when write_grad, logits2d is overwritten with dloss * dloss/dlogits."""
+    _chk_cuda(logits2d, shifted_labels)
+    T, V = logits2d.shape
+    assert logits2d.dtype == BF16 and logits2d.stride(1) == 1 and shifted_labels.dtype == torch.int64
+    assert shifted_labels.is_contiguous() and shifted_labels.numel() == T
+    loss = torch.empty(1, device=logits2d.device, dtype=torch.float32)
+    ws = torch.empty(T + 2, device=logits2d.device, dtype=torch.float32)
+    check(lib().dllm_cross_entropy(_p(logits2d), _p(shifted_labels), _p(loss), float(dloss), _p(ws), logits2d.stride(0), T,
+                                   V, int(write_grad), _stream()), "dllm_cross_entropy")
+    return loss[0]
+
+
+def embedding_fwd(ids, weight):
+    _chk_cuda(ids, weight)
+    ids = ids.contiguous()
+    T = ids.numel()
+    H = weight.shape[1]
+    out = torch.empty((*ids.shape, H), device=weight.device, dtype=weight.dtype)
+    check(lib().dllm_embedding_fwd(_p(ids), _p(weight), _p(out), T, H, _stream()), "dllm_embedding_fwd")
+    return out
+
+
+def embedding_bwd(ids, dy2d, vocab):
+    _chk_cuda(ids, dy2d)
+    T, H = dy2d.shape
+    sorted_ids, order = torch.sort(ids.reshape(-1), stable=True)
+    dW = torch.zeros((vocab, H), device=dy2d.device, dtype=dy2d.dtype)
+    check(lib().dllm_embedding_bwd(_p(sorted_ids), _p(order), _p(dy2d), _p(dW), T, H, 0, _stream()), "dllm_embedding_bwd")
+    return dW
+
+
+# ----------------------------------------------------------------------------------------------- attention
+def attn_fwd(q, k, v, causal=True, seqlens=None, scale=None):
+    """q,k,v: [B, S, nh, d] views (last two dims dense, token stride shared) — e.g. slices of the fused qkv buffer.
+    returns (out [B,S,nh*d], lse [B,nh,S])."""
+    _chk_cuda(q, k, v, seqlens)
+    B, S, nh, d = q.shape
+    for t in (q, k, v):
+        assert t.dtype == BF16 and t.stride(3) == 1 and t.stride(2) == d and t.stride(0) == S * t.stride(1)
+    assert q.stride(1) == k.stride(1) == v.stride(1)
+    out = torch.empty((B, S, nh * d), device=q.device, dtype=BF16)
+    lse = torch.empty((B, nh, S), device=q.device, dtype=torch.float32)
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    check(lib().dllm_attn_fwd(_p(q), _p(k), _p(v), _p(out), _p(lse), _p(seqlens), B, S, nh, d, q.stride(1), nh * d,
+                              int(causal), scale, _stream()), "dllm_attn_fwd")
+    return out, lse
+
+
+def attn_bwd(dout, q, k, v, out, lse, dq, dk, dv, causal=True, seqlens=None, scale=None):
+    """dq/dk/dv: [B,S,nh,d] views to write into (e.g. slices of a fused dqkv buffer)."""
+    _chk_cuda(dout, q, k, v, out, lse, dq, dk, dv, seqlens)
+    B, S, nh, d = q.shape
+    assert dout.is_contiguous() and out.is_contiguous()
+    assert dq.stride(1) == dk.stride(1) == dv.stride(1)
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    wsb = lib().dllm_attn_bwd_workspace_bytes(B, S, nh, d)
+    ws = torch.empty(max(wsb, 4), device=q.device, dtype=torch.uint8)
+    check(lib().dllm_attn_bwd(_p(dout), _p(q), _p(k), _p(v), _p(out), _p(lse), _p(dq), _p(dk), _p(dv), _p(seqlens), _p(ws),
+                              wsb, B, S, nh, d, q.stride(1), nh * d, dq.stride(1), int(causal), scale, _stream()),
+          "dllm_attn_bwd")
+    return dq, dk, dv

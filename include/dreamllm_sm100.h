@@ -1,0 +1,89 @@
+/* libdreamllm_sm100.so — C ABI of the B200-native DreamLLM hot path.
+ *
+ * The reference (RunpeiDong/DreamLLM) is pure Python and has no FFI of its own; these entry points
+ * are what a ctypes / cffi binding inside `omni/models/dreamllm` calls in place of the torch ops the reference
+ * issues.  Each function cites the reference call site it replaces
+ * (paths relative to /root/reference/omni/models/dreamllm/).
+ *
+ * Conventions: plain device pointers + sizes, no torch types; bf16 unless noted; row-major; `ld*` = row stride in
+ * ELEMENTS; every call is asynchronous on `stream` (a cudaStream_t passed as void*), allocates nothing, never
+ * synchronises; returns 0 or a negative DLLM_ERR_* code.  Thread-safe for distinct streams.
+ */
+#ifndef DREAMLLM_SM100_H
+#define DREAMLLM_SM100_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLLM_OK 0
+#define DLLM_ERR_SHAPE (-1)
+#define DLLM_ERR_ALIGN (-2)
+#define DLLM_ERR_DRIVER (-3)
+#define DLLM_ERR_TMAP (-4)
+#define DLLM_ERR_LAUNCH (-5)
+#define DLLM_ERR_UNSUPPORTED (-6)
+
+int dllm_version(void);
+const char* dllm_error_string(int code);
+
+/* Dense contraction on tcgen05 tensor cores: C[M,N] = op(A) * op(B), fp32 accumulate in TMEM.
+ *   a_mn = 0: A is [M,K] row-major; a_mn = 1: A is stored [K,M] row-major (i.e. A^T, used for wgrad)
+ *   b_mn = 0: B is [N,K] row-major (an nn.Linear weight); b_mn = 1: B is stored [K,N] row-major
+ *   out_fp32: C dtype (0 = bf16, 1 = fp32).  cta_pair: -1 auto, 0 = one CTA per tile, 1 = cta_group::2 pairs.
+ * Replaces F.linear / nn.Linear and their autograd dgrad/wgrad:
+ *   modeling_dreamllm.py:336-338, :395 (q/k/v/o_proj), :237 (gate/up/down_proj), :1452 (lm_head),
+ *   omni/models/projector/mlp_projector.py:11-50 (projectors). */
+int dllm_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc,
+                   int a_mn, int b_mn, int out_fp32, int cta_pair, void* stream);
+
+/* DreamLLMRMSNorm.forward (modeling_dreamllm.py:86-91), optionally fused with the preceding residual add
+ * (:638, :644): if `add` != NULL, x_out = bf16(x + add) is written and normalised.  rstd[T] (fp32) is saved for bwd. */
+int dllm_rmsnorm_fwd(const void* x, const void* add, const void* weight, void* x_out, void* y, float* rstd, int T,
+                     int H, float eps, void* stream);
+size_t dllm_rmsnorm_bwd_workspace_bytes(int T, int H);
+/* dx = d(norm)/dx (+ dres if != NULL); dweight (=|+=) column sums (bf16). */
+int dllm_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const float* rstd, const void* dres, void* dx,
+                     void* dweight, int dweight_accumulate, void* workspace, size_t workspace_bytes, int T, int H,
+                     void* stream);
+
+/* apply_rotary_pos_emb (modeling_dreamllm.py:184-209) in place on `heads_total` heads laid side by side in a
+ * [T, ld] buffer (q and k blocks of the fused qkv projection); cos/sin tables [max_pos, head_dim] bf16 (:126-127),
+ * pos[T] int32.  mode = +1 forward, -1 backward. */
+int dllm_rope_inplace(void* buf, const void* cos_table, const void* sin_table, const int* pos, long ld, int T,
+                      int heads_total, int head_dim, int mode, void* stream);
+
+/* DreamLLMMLP activation (modeling_dreamllm.py:237): act = silu(gate) * up on the fused [T, 2I] gate|up buffer. */
+int dllm_swiglu_fwd(const void* gate_up, void* act, long ld_gate_up, int T, int I, void* stream);
+int dllm_swiglu_bwd(const void* dact, const void* gate_up, void* dgate_up, long ld_gate_up, int T, int I, void* stream);
+
+int dllm_add_bf16(const void* a, const void* b, void* out, long n, void* stream);
+
+/* Shifted masked-mean cross entropy (modeling_dreamllm.py:1453-1470). labels[T] int64, already shifted, -100 =
+ * ignore. loss[1] fp32.  If write_grad, logits are overwritten in place by dloss * d(loss)/d(logits) (bf16).
+ * workspace: (T + 2) floats. */
+int dllm_cross_entropy(void* logits, const long long* labels, float* loss, float dloss, void* workspace, long ld,
+                       int T, int V, int write_grad, void* stream);
+
+/* embed_tokens lookup (modeling_dreamllm.py:1066-1067) and its deterministic gradient (sorted segment sums). */
+int dllm_embedding_fwd(const long long* ids, const void* weight, void* out, int T, int H, void* stream);
+int dllm_embedding_bwd(const long long* sorted_ids, const long long* order, const void* dy, void* dweight, int T,
+                       int H, int accumulate, void* stream);
+
+/* Causal / full flash attention on tcgen05 (replaces flash_attn_func / flash_attn_varlen_func,
+ * modeling_dreamllm.py:500-551, and the eager path :357-379).
+ * q,k,v: [B, S, nh, d] views with row stride ld_qkv (elements) between consecutive tokens — the fused qkv GEMM
+ * output is consumed directly, no transposes.  out: [B, S, nh*d] (ld_o).  lse: [B, nh, S] fp32.
+ * seqlens: int32[B] valid (right-padded) lengths or NULL.  Rows >= seqlens[b] are written as zeros (pad_input). */
+int dllm_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B,
+                  int S, int nh, int d, long ld_qkv, long ld_o, int causal, float scale, void* stream);
+size_t dllm_attn_bwd_workspace_bytes(int B, int S, int nh, int d);
+int dllm_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse,
+                  void* dq, void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B,
+                  int S, int nh, int d, long ld_qkv, long ld_o, long ld_dqkv, int causal, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
