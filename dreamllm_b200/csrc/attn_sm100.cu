@@ -1,10 +1,738 @@
-// placeholder until the tcgen05 attention kernels land (next commit) — keeps the C ABI complete
+// tcgen05 flash attention for sm_100a: forward, and backward split in two deterministic kernels (dK/dV, dQ).
+//
+// Replaces flash_attn_func / flash_attn_varlen_func (reference modeling_dreamllm.py:500-551) and the eager
+// softmax(QK^T/sqrt(d) + mask)V path (:357-379).  q/k/v are read straight out of the fused qkv projection buffer
+// ([B, S, heads, d] views with a shared token stride) through 3-D TMA maps — no transposes, no .contiguous().
+//
+// Common structure of the three kernels (192 threads):
+//   warps 0-3  "row" warps: thread t of warp w owns TMEM lane 32w+t = one row of the 128-row MMA tile
+//              (softmax / dS math, P tile written to swizzled smem as the next MMA's A operand, epilogue)
+//   warp 4     TMA producer (one lane)
+//   warp 5     TMEM allocator + MMA issuer (one lane): tcgen05.mma, S/dP tiles double-buffered in TMEM
+// All inter-role hand-offs are mbarriers; tcgen05.commit signals MMA completion.
+#include "common.cuh"
 #include "gemm_sm100.h"
 #include "ops.h"
+
 namespace dllm {
-int attn_fwd(const void*, const void*, const void*, void*, float*, const int*, int, int, int, int, long, long, int, float,
-             cudaStream_t) { return DLLM_ERR_UNSUPPORTED; }
-size_t attn_bwd_workspace(int, int, int, int) { return 0; }
-int attn_bwd(const void*, const void*, const void*, const void*, const void*, const float*, void*, void*, void*, const int*,
-             void*, size_t, int, int, int, int, long, long, long, int, float, cudaStream_t) { return DLLM_ERR_UNSUPPORTED; }
+
+constexpr int kAttnThreads = 192;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+typedef CUresult (*PFN_encodeTiled3)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// [B, S, cols] bf16 view: token stride ld (elements), batch stride S*ld; box = [1, box_rows, 64 cols], 128B swizzle
+static int make_tmap_bsc(CUtensorMap* map, const void* ptr, int B, int S, int cols, long ld, int box_rows) {
+  static PFN_encodeTiled3 enc = nullptr;
+  if (!enc) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p)
+      return DLLM_ERR_DRIVER;
+    enc = reinterpret_cast<PFN_encodeTiled3>(p);
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || ((ld * 2) & 15)) return DLLM_ERR_ALIGN;
+  cuuint64_t gdim[3] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(S), static_cast<cuuint64_t>(B)};
+  cuuint64_t gstr[2] = {static_cast<cuuint64_t>(ld) * 2, static_cast<cuuint64_t>(S) * ld * 2};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : DLLM_ERR_TMAP;
 }
+
+// one full MMA tile: D[tmem] (+)= A * B over `ksteps` UMMA_K steps
+__device__ __forceinline__ void mma_tile(uint32_t tmem_d, uint32_t a_base, bool a_mn, uint32_t a_cs, uint32_t b_base,
+                                         bool b_mn, uint32_t b_cs, int ksteps, uint32_t idesc, bool accumulate) {
+  for (int ks = 0; ks < ksteps; ++ks)
+    umma_ss<1>(tmem_d, op_desc(a_base, a_mn, a_cs, ks), op_desc(b_base, b_mn, b_cs, ks), idesc,
+               (accumulate || ks > 0) ? 1u : 0u);
+}
+
+// write 64 bf16 (one 128-byte swizzled line) for tile row `row`; vals come 8 at a time
+__device__ __forceinline__ void store_row_chunk(uint8_t* tile, int row, int j, const float* f8) {
+  uint4 q;
+  q.x = pack_bf16(f8[0], f8[1]);
+  q.y = pack_bf16(f8[2], f8[3]);
+  q.z = pack_bf16(f8[4], f8[5]);
+  q.w = pack_bf16(f8[6], f8[7]);
+  *reinterpret_cast<uint4*>(tile + row * 128 + ((j ^ (row & 7)) << 4)) = q;
+}
+
+// TMEM accumulator (128 lanes x D fp32 cols) -> *scale -> bf16 -> swizzled staging [D/64][128 rows][128 B] -> per-warp
+// TMA store of [32 rows x 64 cols] boxes at (col0 + c*64, row0 + 32*warp, b).
+template <int D>
+__device__ __forceinline__ void store_acc_tile(uint32_t tmem_acc, uint8_t* stage, float mul, const CUtensorMap* tm,
+                                               int col0, int row0, int b, int warp, int lane) {
+  const int row = warp * 32 + lane;
+#pragma unroll 1
+  for (int c = 0; c < D / 32; ++c) {
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
+    tmem_ld_wait();
+    uint8_t* tile = stage + (c >> 1) * 16384;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[8 * j + e]) * mul;
+      store_row_chunk(tile, row, (c & 1) * 4 + j, f);
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+#pragma unroll
+    for (int c = 0; c < D / 64; ++c) tma_store_3d(tm, stage + c * 16384 + warp * 4096, col0 + c * 64, row0 + warp * 32, b);
+    tma_store_commit();
+    tma_store_wait_all<0>();
+  }
+}
+
+// ================================================================================================ forward
+template <int D>
+struct FwdSmem {
+  static constexpr int NCH = D / 64;
+  static constexpr int kQ = NCH * 16384;       // [NCH][128][128B]
+  static constexpr int kKV = NCH * 8192;       // [NCH][64][128B]
+  static constexpr int kP = 16384;             // [128][128B]
+  static constexpr int oQ = 0, oK = kQ, oV = oK + 2 * kKV, oP = oV + 2 * kKV, oBar = oP + kP;
+  static constexpr int kBytes = oBar + 256;
+};
+
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, float* __restrict__ lse,
+                const int* __restrict__ seqlens, int S, int nh, float scale_log2) {
+  using L = FwdSmem<D>;
+  constexpr int NCH = L::NCH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* k_full = bars + 1;   // [2]
+  uint64_t* k_empty = bars + 3;  // [2]
+  uint64_t* v_full = bars + 5;   // [2]
+  uint64_t* v_empty = bars + 7;  // [2]
+  uint64_t* s_full = bars + 9;   // [2]
+  uint64_t* p_full = bars + 11;
+  uint64_t* pv_done = bars + 12;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int kv_len = seqlens ? min(seqlens[b], S) : S;
+  const int kv_end = kCausal ? min(kv_len, q0 + 128) : kv_len;
+  const int n_kv = (kv_end + 63) / 64;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_fwd: smem misaligned\n"); __trap(); }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+    }
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc<1>(tmem_ptr, 256); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base;        // 2 x 64 columns
+  const uint32_t tmem_O = tmem_base + 128;  // D columns
+
+  if (warp == 4 && lane == 0 && n_kv > 0) {
+    // ---------------- TMA producer ----------------
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
+    mbar_arrive_expect_tx(q_full, 128 * D * 2);
+    for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oQ + c * 16384, &tq, q_full, h * D + c * 64, q0, b);
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const uint32_t ph = (j >> 1) & 1;
+      mbar_wait(&k_empty[st], ph ^ 1, 10);
+      mbar_arrive_expect_tx(&k_full[st], 64 * D * 2);
+      for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oK + st * L::kKV + c * 8192, &tk, &k_full[st], h * D + c * 64, j * 64, b);
+      mbar_wait(&v_empty[st], ph ^ 1, 11);
+      mbar_arrive_expect_tx(&v_full[st], 64 * D * 2);
+      for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &v_full[st], h * D + c * 64, j * 64, b);
+    }
+  } else if (warp == 5 && lane == 0 && n_kv > 0) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);
+    const uint32_t sQ = smem_u32(smem + L::oQ), sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV),
+                   sP = smem_u32(smem + L::oP);
+    auto issue_qk = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&k_full[st], (j >> 1) & 1, 12);
+      tc_fence_after();
+      mma_tile(tmem_S + (j & 1) * 64, sQ, false, 16384, sK + st * L::kKV, false, 8192, D / 16, idesc_qk, false);
+      umma_commit(&k_empty[st]);
+      umma_commit(&s_full[j & 1]);
+    };
+    mbar_wait(q_full, 0, 13);
+    issue_qk(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_qk(j + 1);
+      const int st = j & 1;
+      mbar_wait(&v_full[st], (j >> 1) & 1, 14);
+      mbar_wait(p_full, j & 1, 15);
+      tc_fence_after();
+      mma_tile(tmem_O, sP, false, 0, sV + st * L::kKV, true, 8192, 4, idesc_pv, j > 0);
+      umma_commit(&v_empty[st]);
+      umma_commit(pv_done);
+    }
+  } else if (warp < 4) {
+    // ---------------- softmax rows ----------------
+    const int row = warp * 32 + lane;
+    const int q_row = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1, 16);
+      tc_fence_after();
+      uint32_t sv[64];
+      tmem_ld32(tmem_S + lane_off + (j & 1) * 64, sv);
+      tmem_ld32(tmem_S + lane_off + (j & 1) * 64 + 32, sv + 32);
+      tmem_ld_wait();
+      const int kv0 = j * 64;
+      const bool need_mask = (kCausal && kv0 + 63 > q0 + warp * 32) || (kv0 + 64 > kv_len);
+      float mx = -INFINITY;
+      if (need_mask) {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          const int kvi = kv0 + c;
+          const bool ok = (kvi < kv_len) && (!kCausal || kvi <= q_row);
+          float s = ok ? __uint_as_float(sv[c]) : -INFINITY;
+          sv[c] = __float_as_uint(s);
+          mx = fmaxf(mx, s);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+      }
+      const float m_new = fmaxf(m_run, mx * scale_log2);
+      // lazy rescale: only move the reference max when it grew by more than 2^8 (keeps P <= 256, exact after 1/l)
+      const bool need = (m_new - m_run) > 8.0f;
+      const bool any = __any_sync(0xffffffffu, need);
+      if (j > 0) mbar_wait(pv_done, (j - 1) & 1, 17);  // P buffer free, O quiescent
+      if (any) {
+        const float m_tgt = (m_new == -INFINITY) ? m_run : m_new;
+        const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_tgt);
+        if (j > 0) {
+          tc_fence_after();
+#pragma unroll 1
+          for (int c = 0; c < D / 32; ++c) {
+            uint32_t o[32];
+            tmem_ld32(tmem_O + lane_off + c * 32, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+            tmem_st32(tmem_O + lane_off + c * 32, o);
+          }
+          tmem_st_wait();
+        }
+        l_run *= alpha;
+        m_run = m_tgt;
+      }
+      const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+      float lsum = 0.f;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float p[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          p[e] = exp2f(__uint_as_float(sv[jj * 8 + e]) * scale_log2 - m_use);
+          lsum += p[e];
+        }
+        store_row_chunk(smem + L::oP, row, jj, p);
+      }
+      l_run += lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    if (n_kv > 0) {
+      mbar_wait(pv_done, (n_kv - 1) & 1, 18);
+      tc_fence_after();
+    }
+    const bool valid_row = (q_row < kv_len) && n_kv > 0 && l_run > 0.f;
+    const float inv = valid_row ? 1.f / l_run : 0.f;
+    if (n_kv > 0) {
+      store_acc_tile<D>(tmem_O, smem + L::oQ, inv, &to, h * D, q0, b, warp, lane);
+    } else {
+      // no keys at all: write zeros
+      for (int c = 0; c < D / 64; ++c)
+        for (int jj = 0; jj < 8; ++jj) {
+          float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          store_row_chunk(smem + L::oQ + c * 16384, row, jj, z);
+        }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        for (int c = 0; c < D / 64; ++c) tma_store_3d(&to, smem + L::oQ + c * 16384 + warp * 4096, h * D + c * 64, q0 + warp * 32, b);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+    if (q_row < S)
+      lse[(static_cast<size_t>(b) * nh + h) * S + q_row] = valid_row ? (m_run + log2f(l_run)) * kLn2 : INFINITY;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<1>(tmem_base, 256);
+}
+
+// ================================================================================================ backward prep
+// delta[b,h,s] = sum_d dO*O ; lse2 = lse*log2(e).  One warp per (token, head).
+template <int D>
+__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, const float* __restrict__ lse,
+                                     float* __restrict__ delta, float* __restrict__ lse2, int B, int S, int nh, long ld_o) {
+  const long gw = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const long total = static_cast<long>(B) * S * nh;
+  if (gw >= total) return;
+  const int h = static_cast<int>(gw % nh);
+  const long tok = gw / nh;
+  const int s = static_cast<int>(tok % S);
+  const int b = static_cast<int>(tok / S);
+  const bf16* po = out + tok * ld_o + h * D;
+  const bf16* pd = dout + tok * ld_o + h * D;
+  float acc = 0.f;
+  constexpr int EPL = D / 32;  // elements per lane (4 or 2)
+#pragma unroll
+  for (int e = 0; e < EPL; e += 2) {
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(po + lane * EPL + e));
+    const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pd + lane * EPL + e));
+    acc += a.x * g.x + a.y * g.y;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    const size_t idx = (static_cast<size_t>(b) * nh + h) * S + s;
+    delta[idx] = acc;
+    lse2[idx] = lse[idx] * kLog2e;
+  }
+}
+
+// ================================================================================================ backward: dK, dV
+// CTA = one 128-row kv tile of one (b, h); loops over 64-row q tiles.  Row threads own kv rows, so everything the
+// MMAs consume as an A operand ([kv][q] tiles P^T and dS^T) is K-major as written.
+//   S^T  = K  Q_i^T      dP^T = V dO_i^T            (M = 128 kv, N = 64 q, K = d)
+//   dV  += P^T dO_i      dK  += dS^T Q_i            (M = 128 kv, N = d,    K = 64 q; B operands MN-major)
+template <int D>
+struct BwdKVSmem {
+  static constexpr int NCH = D / 64;
+  static constexpr int kKV = NCH * 16384;  // [NCH][128][128B]
+  static constexpr int kQ = NCH * 8192;    // [NCH][64][128B]
+  static constexpr int oK = 0, oV = kKV, oQ = 2 * kKV, oDO = oQ + 2 * kQ, oP = oDO + 2 * kQ, oDS = oP + 16384,
+                       oBar = oDS + 16384;
+  static constexpr int kBytes = oBar + 256;
+};
+
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                     const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                     const __grid_constant__ CUtensorMap tdk, const __grid_constant__ CUtensorMap tdv,
+                     const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ seqlens,
+                     int S, int nh, float scale, float scale_log2) {
+  using L = BwdKVSmem<D>;
+  constexpr int NCH = L::NCH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;   // [2]
+  uint64_t* pds_full = bars + 7;
+  uint64_t* acc_done = bars + 8;   // dV/dK MMAs of iteration i retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int len = seqlens ? min(seqlens[b], S) : S;
+  const int i_begin = kCausal ? (kv0 / 64) : 0;
+  const int i_end = (len + 63) / 64;  // q rows >= len carry no gradient
+  const int n_it = (kv0 < len) ? max(i_end - i_begin, 0) : 0;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_bwd_dkdv: smem misaligned\n"); __trap(); }
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&sdp_full[i], 1); }
+    mbar_init(pds_full, 128);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_St = tmem_base;         // 2 x 64
+  const uint32_t tmem_dPt = tmem_base + 128;  // 2 x 64
+  const uint32_t tmem_dV = tmem_base + 256;   // D
+  const uint32_t tmem_dK = tmem_base + 256 + D;
+
+  if (warp == 4 && lane == 0 && n_it > 0) {
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    mbar_arrive_expect_tx(kv_full, 2 * 128 * D * 2);
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem + L::oK + c * 16384, &tk, kv_full, h * D + c * 64, kv0, b);
+      tma_load_3d(smem + L::oV + c * 16384, &tv, kv_full, h * D + c * 64, kv0, b);
+    }
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const int qr0 = (i_begin + it) * 64;
+      mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1, 20);
+      mbar_arrive_expect_tx(&qdo_full[st], 2 * 64 * D * 2);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smem + L::oQ + st * L::kQ + c * 8192, &tq, &qdo_full[st], h * D + c * 64, qr0, b);
+        tma_load_3d(smem + L::oDO + st * L::kQ + c * 8192, &tdo, &qdo_full[st], h * D + c * 64, qr0, b);
+      }
+    }
+  } else if (warp == 5 && lane == 0 && n_it > 0) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+    const uint32_t sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV), sQ = smem_u32(smem + L::oQ),
+                   sDO = smem_u32(smem + L::oDO), sP = smem_u32(smem + L::oP), sDS = smem_u32(smem + L::oDS);
+    auto issue_s = [&](int it) {
+      const int st = it & 1;
+      mbar_wait(&qdo_full[st], (it >> 1) & 1, 21);
+      tc_fence_after();
+      mma_tile(tmem_St + st * 64, sK, false, 16384, sQ + st * L::kQ, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_dPt + st * 64, sV, false, 16384, sDO + st * L::kQ, false, 8192, D / 16, idesc_s, false);
+      umma_commit(&sdp_full[st]);
+    };
+    mbar_wait(kv_full, 0, 22);
+    issue_s(0);
+    for (int it = 0; it < n_it; ++it) {
+      if (it + 1 < n_it) issue_s(it + 1);
+      const int st = it & 1;
+      mbar_wait(pds_full, it & 1, 23);
+      tc_fence_after();
+      mma_tile(tmem_dV, sP, false, 0, sDO + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
+      mma_tile(tmem_dK, sDS, false, 0, sQ + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
+      umma_commit(&qdo_empty[st]);
+      umma_commit(acc_done);
+    }
+  } else if (warp < 4) {
+    const int row = warp * 32 + lane;  // kv row within tile
+    const int kv_row = kv0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const float* lse_bh = lse2 + (static_cast<size_t>(b) * nh + h) * S;
+    const float* del_bh = delta + (static_cast<size_t>(b) * nh + h) * S;
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const int qr0 = (i_begin + it) * 64;
+      mbar_wait(&sdp_full[st], (it >> 1) & 1, 24);
+      tc_fence_after();
+      if (it > 0) mbar_wait(acc_done, (it - 1) & 1, 25);  // previous dV/dK MMAs finished reading sP/sDS
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_St + lane_off + st * 64 + half * 32, sv);
+        tmem_ld32(tmem_dPt + lane_off + st * 64 + half * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float p[8], ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = half * 32 + jj * 8 + e;
+            const int qi = qr0 + c;
+            const bool ok = (qi < len) && (kv_row < len) && (!kCausal || kv_row <= qi);
+            const int qs = min(qi, S - 1);
+            const float pe = ok ? exp2f(__uint_as_float(sv[jj * 8 + e]) * scale_log2 - __ldg(lse_bh + qs)) : 0.f;
+            p[e] = pe;
+            ds[e] = pe * (__uint_as_float(dv[jj * 8 + e]) - __ldg(del_bh + qs)) * scale;
+          }
+          store_row_chunk(smem + L::oP, row, half * 4 + jj, p);
+          store_row_chunk(smem + L::oDS, row, half * 4 + jj, ds);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+    if (n_it > 0) {
+      mbar_wait(acc_done, (n_it - 1) & 1, 26);
+      tc_fence_after();
+      store_acc_tile<D>(tmem_dV, smem + L::oV, 1.f, &tdv, h * D, kv0, b, warp, lane);
+      store_acc_tile<D>(tmem_dK, smem + L::oK, 1.f, &tdk, h * D, kv0, b, warp, lane);
+    } else {
+      for (int c = 0; c < D / 64; ++c)
+        for (int jj = 0; jj < 8; ++jj) {
+          float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          store_row_chunk(smem + L::oK + c * 16384, row, jj, z);
+        }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        for (int c = 0; c < D / 64; ++c) {
+          tma_store_3d(&tdk, smem + L::oK + c * 16384 + warp * 4096, h * D + c * 64, kv0 + warp * 32, b);
+          tma_store_3d(&tdv, smem + L::oK + c * 16384 + warp * 4096, h * D + c * 64, kv0 + warp * 32, b);
+        }
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// ================================================================================================ backward: dQ
+// CTA = one 128-row q tile of one (b, h); loops over 64-row kv tiles.
+//   S = Q K_j^T    dP = dO V_j^T     (M = 128 q, N = 64 kv, K = d)       dQ += dS K_j   (M = 128 q, N = d, K = 64 kv)
+template <int D>
+struct BwdQSmem {
+  static constexpr int NCH = D / 64;
+  static constexpr int kQ = NCH * 16384;
+  static constexpr int kKV = NCH * 8192;
+  static constexpr int oQ = 0, oDO = kQ, oK = 2 * kQ, oV = oK + 2 * kKV, oDS = oV + 2 * kKV, oBar = oDS + 16384;
+  static constexpr int kBytes = oBar + 256;
+};
+
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kAttnThreads, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                   const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                   const __grid_constant__ CUtensorMap tdq, const float* __restrict__ lse2,
+                   const float* __restrict__ delta, const int* __restrict__ seqlens, int S, int nh, float scale,
+                   float scale_log2) {
+  using L = BwdQSmem<D>;
+  constexpr int NCH = L::NCH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;  // [2]
+  uint64_t* ds_full = bars + 7;
+  uint64_t* acc_done = bars + 8;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int len = seqlens ? min(seqlens[b], S) : S;
+  const int kv_end = kCausal ? min(len, q0 + 128) : len;
+  const int n_kv = (q0 < len) ? (kv_end + 63) / 64 : 0;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_bwd_dq: smem misaligned\n"); __trap(); }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&sdp_full[i], 1); }
+    mbar_init(ds_full, 128);
+    mbar_init(acc_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
+
+  if (warp == 4 && lane == 0 && n_kv > 0) {
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    mbar_arrive_expect_tx(q_full, 2 * 128 * D * 2);
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem + L::oQ + c * 16384, &tq, q_full, h * D + c * 64, q0, b);
+      tma_load_3d(smem + L::oDO + c * 16384, &tdo, q_full, h * D + c * 64, q0, b);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1, 30);
+      mbar_arrive_expect_tx(&kv_full[st], 2 * 64 * D * 2);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smem + L::oK + st * L::kKV + c * 8192, &tk, &kv_full[st], h * D + c * 64, j * 64, b);
+        tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &kv_full[st], h * D + c * 64, j * 64, b);
+      }
+    }
+  } else if (warp == 5 && lane == 0 && n_kv > 0) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+    const uint32_t sQ = smem_u32(smem + L::oQ), sDO = smem_u32(smem + L::oDO), sK = smem_u32(smem + L::oK),
+                   sV = smem_u32(smem + L::oV), sDS = smem_u32(smem + L::oDS);
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (j >> 1) & 1, 31);
+      tc_fence_after();
+      mma_tile(tmem_S + st * 64, sQ, false, 16384, sK + st * L::kKV, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_dP + st * 64, sDO, false, 16384, sV + st * L::kKV, false, 8192, D / 16, idesc_s, false);
+      umma_commit(&sdp_full[st]);
+    };
+    mbar_wait(q_full, 0, 32);
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_s(j + 1);
+      const int st = j & 1;
+      mbar_wait(ds_full, j & 1, 33);
+      tc_fence_after();
+      mma_tile(tmem_dQ, sDS, false, 0, sK + st * L::kKV, true, 8192, 4, idesc_acc, j > 0);
+      umma_commit(&kv_empty[st]);
+      umma_commit(acc_done);
+    }
+  } else if (warp < 4) {
+    const int row = warp * 32 + lane;
+    const int q_row = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    const size_t sidx = (static_cast<size_t>(b) * nh + h) * S + min(q_row, S - 1);
+    const float my_lse = lse2[sidx], my_delta = delta[sidx];
+    const bool row_ok = q_row < len;
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      mbar_wait(&sdp_full[st], (j >> 1) & 1, 34);
+      tc_fence_after();
+      if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 35);
+#pragma unroll 1
+      for (int half = 0; half < 2; ++half) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tmem_S + lane_off + st * 64 + half * 32, sv);
+        tmem_ld32(tmem_dP + lane_off + st * 64 + half * 32, dv);
+        tmem_ld_wait();
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int kvi = j * 64 + half * 32 + jj * 8 + e;
+            const bool ok = row_ok && (kvi < len) && (!kCausal || kvi <= q_row);
+            const float pe = ok ? exp2f(__uint_as_float(sv[jj * 8 + e]) * scale_log2 - my_lse) : 0.f;
+            ds[e] = pe * (__uint_as_float(dv[jj * 8 + e]) - my_delta) * scale;
+          }
+          store_row_chunk(smem + L::oDS, row, half * 4 + jj, ds);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(ds_full);
+    }
+    if (n_kv > 0) {
+      mbar_wait(acc_done, (n_kv - 1) & 1, 36);
+      tc_fence_after();
+      store_acc_tile<D>(tmem_dQ, smem + L::oQ, 1.f, &tdq, h * D, q0, b, warp, lane);
+    } else {
+      for (int c = 0; c < D / 64; ++c)
+        for (int jj = 0; jj < 8; ++jj) {
+          float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          store_row_chunk(smem + L::oQ + c * 16384, row, jj, z);
+        }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        for (int c = 0; c < D / 64; ++c) tma_store_3d(&tdq, smem + L::oQ + c * 16384 + warp * 4096, h * D + c * 64, q0 + warp * 32, b);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<1>(tmem_base, 512);
+}
+
+// ================================================================================================ host
+template <typename K>
+static int set_smem(K kern, int bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+template <int D, bool C>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
+                      const int* seqlens, int B, int S, int nh, float scale_log2, cudaStream_t st) {
+  auto kern = attn_fwd_kernel<D, C>;
+  static bool once = false;
+  if (!once) {
+    if (set_smem(kern, FwdSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    once = true;
+  }
+  dim3 grid((S + 127) / 128, nh, B);
+  kern<<<grid, kAttnThreads, FwdSmem<D>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, nh, scale_log2);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int nh,
+             int d, long ld_qkv, long ld_o, int causal, float scale, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || nh <= 0) return DLLM_ERR_SHAPE;
+  if (d != 128 && d != 64) return DLLM_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv, to;
+  int rc;
+  if ((rc = make_tmap_bsc(&tq, q, B, S, nh * d, ld_qkv, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tk, k, B, S, nh * d, ld_qkv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tv, v, B, S, nh * d, ld_qkv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&to, out, B, S, nh * d, ld_o, 32))) return rc;
+  const float sl2 = scale * kLog2e;
+  if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st)
+                              : launch_fwd<128, false>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st);
+  return causal ? launch_fwd<64, true>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st)
+                : launch_fwd<64, false>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st);
+}
+
+size_t attn_bwd_workspace(int B, int S, int nh, int) { return static_cast<size_t>(B) * S * nh * 2 * sizeof(float); }
+
+template <int D, bool C>
+static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const CUtensorMap& tk64, const CUtensorMap& tk128,
+                      const CUtensorMap& tv64, const CUtensorMap& tv128, const CUtensorMap& tdo64,
+                      const CUtensorMap& tdo128, const CUtensorMap& tdq, const CUtensorMap& tdk, const CUtensorMap& tdv,
+                      const bf16* dout, const bf16* out, const float* lse, float* delta, float* lse2, const int* seqlens,
+                      int B, int S, int nh, long ld_o, float scale, cudaStream_t st) {
+  auto k1 = attn_bwd_dkdv_kernel<D, C>;
+  auto k2 = attn_bwd_dq_kernel<D, C>;
+  static bool once = false;
+  if (!once) {
+    if (set_smem(k1, BwdKVSmem<D>::kBytes) || set_smem(k2, BwdQSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
+    once = true;
+  }
+  const long warps = static_cast<long>(B) * S * nh;
+  attn_bwd_prep_kernel<D><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(dout, out, lse, delta, lse2, B, S,
+                                                                                           nh, ld_o);
+  dim3 grid((S + 127) / 128, nh, B);
+  k1<<<grid, kAttnThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, nh, scale,
+                                                        scale * kLog2e);
+  k2<<<grid, kAttnThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, nh, scale,
+                                                       scale * kLog2e);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+int attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
+             void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int S, int nh, int d,
+             long ld_qkv, long ld_o, long ld_dqkv, int causal, float scale, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || nh <= 0) return DLLM_ERR_SHAPE;
+  if (d != 128 && d != 64) return DLLM_ERR_UNSUPPORTED;
+  if (workspace_bytes < attn_bwd_workspace(B, S, nh, d)) return DLLM_ERR_SHAPE;
+  float* delta = static_cast<float*>(workspace);
+  float* lse2 = delta + static_cast<size_t>(B) * S * nh;
+  CUtensorMap tq64, tq128, tk64, tk128, tv64, tv128, tdo64, tdo128, tdq, tdk, tdv;
+  int rc;
+  const int C = nh * d;
+  if ((rc = make_tmap_bsc(&tq64, q, B, S, C, ld_qkv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tq128, q, B, S, C, ld_qkv, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tk64, k, B, S, C, ld_qkv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tk128, k, B, S, C, ld_qkv, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tv64, v, B, S, C, ld_qkv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tv128, v, B, S, C, ld_qkv, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tdo64, dout, B, S, C, ld_o, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tdo128, dout, B, S, C, ld_o, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tdq, dq, B, S, C, ld_dqkv, 32))) return rc;
+  if ((rc = make_tmap_bsc(&tdk, dk, B, S, C, ld_dqkv, 32))) return rc;
+  if ((rc = make_tmap_bsc(&tdv, dv, B, S, C, ld_dqkv, 32))) return rc;
+#define DLLM_BWD(DD, CC)                                                                                             \
+  return launch_bwd<DD, CC>(tq64, tq128, tk64, tk128, tv64, tv128, tdo64, tdo128, tdq, tdk, tdv, (const bf16*)dout,     \
+                            (const bf16*)out, lse, delta, lse2, seqlens, B, S, nh, ld_o, scale, st)
+  if (d == 128) { if (causal) DLLM_BWD(128, true); else DLLM_BWD(128, false); }
+  if (causal) DLLM_BWD(64, true); else DLLM_BWD(64, false);
+#undef DLLM_BWD
+}
+
+}  // namespace dllm

@@ -261,3 +261,27 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 }  // namespace dllm
+
+// ----------------------------------------------------------------------------- 3D TMA (batched [B, S, cols] views)
+namespace dllm {
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+// Operand descriptor for one UMMA_K (=16) step `ks` of a 128B-swizzled smem tile.
+//   K-major : tile = [K/64 chunks][rows][128 B]; chunk_stride = bytes between 64-wide K chunks
+//   MN-major: tile = [MN/64 groups][K lines][128 B]; chunk_stride = bytes between 64-wide MN groups (LBO)
+__device__ __forceinline__ uint64_t op_desc(uint32_t base, bool mn, uint32_t chunk_stride, int ks) {
+  return mn ? make_smem_desc(base + ks * 2048u, chunk_stride, 1024u)
+            : make_smem_desc(base + (ks >> 2) * chunk_stride + (ks & 3) * 32u, 16u, 1024u);
+}
+}  // namespace dllm
