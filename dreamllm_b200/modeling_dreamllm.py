@@ -1,0 +1,568 @@
+"""B200-native mirror of the reference's `omni/models/dreamllm/modeling_dreamllm.py` decoder stack.
+
+Same class names, constructor / forward signatures, parameter names and state-dict keys as the reference
+ so the classes drop into `omni.models.dreamllm`; all arithmetic runs in libdreamllm_sm100.so.
+
+    DreamLLMRMSNorm            reference modeling_dreamllm.py:77-91
+    RotaryEmbedding            :97-128
+    DreamLLMMLP                :212-239
+    DreamLLMAttention          :254-400  (DreamLLMFlashAttention2 :403-583 is the same math)
+    DreamLLMDecoderLayer       :586-654
+    DreamLLMModel              :803-1043  (text / inputs_embeds path; plugin splice lives in modeling_plugins)
+    DreamLLMForCausalMLM       :1209-1509 (lm_head + shifted masked CE)
+
+There is no eager/CPU fallback: modules raise if their tensors are not on a CUDA device.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+BF16 = torch.bfloat16
+
+
+# ------------------------------------------------------------------------------------------------ config
+class DreamLLMConfig:
+    """Minimal stand-in for `configuration_dreamllm.DreamLLMConfig` (:64-278): the LLaMA hyper-parameters the
+    decoder reads.  Any object with these attributes (e.g. the reference's own config) works."""
+
+    model_type = "dreamllm"
+
+    def __init__(self, vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                 num_attention_heads=32, num_key_value_heads=None, hidden_act="silu", max_position_embeddings=2048,
+                 initializer_range=0.02, rms_norm_eps=1e-6, use_cache=True, pad_token_id=None, bos_token_id=1,
+                 eos_token_id=2, pretraining_tp=1, tie_word_embeddings=False, rope_theta=10000.0, rope_scaling=None,
+                 attention_bias=False, **kwargs):
+        self.vocab_size = vocab_size
+        self.hidden_size = hidden_size
+        self.intermediate_size = intermediate_size
+        self.num_hidden_layers = num_hidden_layers
+        self.num_attention_heads = num_attention_heads
+        self.num_key_value_heads = num_key_value_heads or num_attention_heads
+        self.hidden_act = hidden_act
+        self.max_position_embeddings = max_position_embeddings
+        self.initializer_range = initializer_range
+        self.rms_norm_eps = rms_norm_eps
+        self.use_cache = use_cache
+        self.pad_token_id = pad_token_id
+        self.bos_token_id = bos_token_id
+        self.eos_token_id = eos_token_id
+        self.pretraining_tp = pretraining_tp
+        self.tie_word_embeddings = tie_word_embeddings
+        self.rope_theta = rope_theta
+        self.rope_scaling = rope_scaling
+        self.attention_bias = attention_bias
+        for k, v in kwargs.items():
+            setattr(self, k, v)
+
+    @classmethod
+    def vicuna_7b(cls, **kw):
+        return cls(vocab_size=32008, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
+                   num_attention_heads=32, **kw)
+
+
+def _check_supported(config):
+    if getattr(config, "pretraining_tp", 1) != 1:
+        raise ValueError("pretraining_tp > 1 is out of scope (SURVEY.md §8a row a6)")
+    if getattr(config, "num_key_value_heads", config.num_attention_heads) != config.num_attention_heads:
+        raise ValueError("GQA (num_key_value_heads != num_attention_heads) is not supported on this path")
+    if getattr(config, "attention_bias", False):
+        raise ValueError("attention_bias=True is not supported")
+    if getattr(config, "hidden_act", "silu") != "silu":
+        raise ValueError("only SwiGLU (hidden_act='silu') is supported")
+    rs = getattr(config, "rope_scaling", None)
+    if rs is not None and not (isinstance(rs, dict) and rs.get("rope_type", rs.get("type")) == "default"):
+        raise ValueError("rope_scaling is not supported (no shipped DreamLLM config enables it)")
+    d = config.hidden_size // config.num_attention_heads
+    if d not in (64, 128):
+        raise ValueError(f"head_dim {d} unsupported (64 or 128)")
+
+
+# ------------------------------------------------------------------------------------------------ leaf modules
+class _RMSNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, eps):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        y, rstd, _ = ops.rmsnorm_fwd(x2, weight, eps)
+        ctx.save_for_backward(x2, weight, rstd)
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, weight, rstd = ctx.saved_tensors
+        dy2 = dy.reshape(x2.shape).contiguous()
+        dx, dw = ops.rmsnorm_bwd(dy2, x2, weight, rstd, need_dw=ctx.needs_input_grad[1])
+        return dx.view(dy.shape), dw, None
+
+
+class DreamLLMRMSNorm(nn.Module):
+    def __init__(self, hidden_size, eps=1e-6):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(hidden_size))
+        self.variance_epsilon = eps
+
+    def forward(self, hidden_states):
+        return _RMSNormFn.apply(hidden_states, self.weight, self.variance_epsilon)
+
+
+class RotaryEmbedding(nn.Module):
+    """Same buffers as the reference (:97-128): persistent `inv_freq`, non-persistent cos/sin caches built in fp32
+    and rounded to the model dtype at use."""
+
+    def __init__(self, dim, max_position_embeddings=2048, base=10000, device=None):
+        super().__init__()
+        self.dim = dim
+        self.max_position_embeddings = max_position_embeddings
+        self.base = base
+        inv_freq = 1.0 / (self.base ** (torch.arange(0, self.dim, 2).float().to(device) / self.dim))
+        self.register_buffer("inv_freq", inv_freq)
+        self._set_cos_sin_cache(max_position_embeddings, self.inv_freq.device, torch.get_default_dtype())
+
+    def _set_cos_sin_cache(self, seq_len, device, dtype):
+        self.max_seq_len_cached = seq_len
+        t = torch.arange(seq_len, device=device, dtype=self.inv_freq.dtype)
+        freqs = torch.einsum("i,j->ij", t, self.inv_freq)
+        emb = torch.cat((freqs, freqs), dim=-1)
+        self.register_buffer("cos_cached", emb.cos().to(dtype), persistent=False)
+        self.register_buffer("sin_cached", emb.sin().to(dtype), persistent=False)
+
+    def tables(self, seq_len, device):
+        if seq_len > self.max_seq_len_cached:
+            self._set_cos_sin_cache(seq_len, device, self.cos_cached.dtype)
+        if self.cos_cached.dtype != BF16 or self.cos_cached.device != device:
+            self.cos_cached = self.cos_cached.to(device=device, dtype=BF16)
+            self.sin_cached = self.sin_cached.to(device=device, dtype=BF16)
+        return self.cos_cached, self.sin_cached
+
+    def forward(self, x, seq_len=None):
+        cos, sin = self.tables(seq_len, x.device)
+        return cos[:seq_len].to(dtype=x.dtype), sin[:seq_len].to(dtype=x.dtype)
+
+
+def _fuse_rows(params):
+    """Make a list of [n_i, K] Parameters contiguous row blocks of one storage (so one GEMM reads them as a single
+    [sum n_i, K] weight) without changing their identity / state-dict keys.  Returns the fused view."""
+    p0 = params[0]
+    esz = p0.element_size()
+    ok = all(p.is_contiguous() and p.dtype == p0.dtype and p.device == p0.device for p in params)
+    if ok:
+        ptr = p0.data_ptr()
+        for p in params:
+            if p.data_ptr() != ptr or p.untyped_storage().data_ptr() != p0.untyped_storage().data_ptr():
+                ok = False
+                break
+            ptr += p.numel() * esz
+    K = p0.shape[1]
+    rows = sum(p.shape[0] for p in params)
+    if not ok:
+        fused = torch.empty((rows, K), dtype=p0.dtype, device=p0.device)
+        r = 0
+        with torch.no_grad():
+            for p in params:
+                fused[r:r + p.shape[0]].copy_(p.data)
+                p.data = fused[r:r + p.shape[0]]
+                r += p.shape[0]
+        return fused
+    off = p0.storage_offset()
+    return torch.as_strided(p0.data, (rows, K), (K, 1), off)
+
+
+class DreamLLMMLP(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.hidden_size = config.hidden_size
+        self.intermediate_size = config.intermediate_size
+        self.gate_proj = nn.Linear(self.hidden_size, self.intermediate_size, bias=False)
+        self.up_proj = nn.Linear(self.hidden_size, self.intermediate_size, bias=False)
+        self.down_proj = nn.Linear(self.intermediate_size, self.hidden_size, bias=False)
+
+    def forward(self, x):
+        return _MLPFn.apply(x, self.gate_proj.weight, self.up_proj.weight, self.down_proj.weight, self)
+
+
+class _MLPFn(torch.autograd.Function):
+    """Standalone DreamLLMMLP (the decoder layer uses its own fused Function)."""
+
+    @staticmethod
+    def forward(ctx, x, wg, wu, wd, mod):
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).contiguous()
+        wgu = _fuse_rows([mod.gate_proj.weight, mod.up_proj.weight])
+        gu = ops.linear(x2, wgu)
+        act = ops.swiglu_fwd(gu, mod.intermediate_size)
+        y = ops.linear(act, wd)
+        ctx.save_for_backward(x2, gu, act, wgu, wd)
+        ctx.inter = mod.intermediate_size
+        return y.view(shp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, gu, act, wgu, wd = ctx.saved_tensors
+        I = ctx.inter
+        dy2 = dy.reshape(-1, dy.shape[-1]).contiguous()
+        dact = ops.linear_dgrad(dy2, wd)
+        dwd = ops.linear_wgrad(dy2, act) if ctx.needs_input_grad[3] else None
+        dgu = ops.swiglu_bwd(dact, gu, I)
+        dx = ops.linear_dgrad(dgu, wgu)
+        dwg = dwu = None
+        if ctx.needs_input_grad[1] or ctx.needs_input_grad[2]:
+            dwgu = ops.linear_wgrad(dgu, x2)
+            dwg, dwu = dwgu[:I], dwgu[I:]
+        return dx.view(dy.shape), dwg, dwu, dwd, None
+
+
+class DreamLLMAttention(nn.Module):
+    """Parameter holder with the reference's names; the arithmetic runs inside the fused decoder-layer Function
+    (or `forward` below when used standalone)."""
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.hidden_size = config.hidden_size
+        self.num_heads = config.num_attention_heads
+        self.head_dim = self.hidden_size // self.num_heads
+        self.num_key_value_heads = getattr(config, "num_key_value_heads", self.num_heads)
+        self.num_key_value_groups = self.num_heads // self.num_key_value_heads
+        self.max_position_embeddings = config.max_position_embeddings
+        self.rope_theta = getattr(config, "rope_theta", 10000.0)
+        if (self.head_dim * self.num_heads) != self.hidden_size:
+            raise ValueError(
+                f"hidden_size must be divisible by num_heads (got `hidden_size`: {self.hidden_size}"
+                f" and `num_heads`: {self.num_heads})."
+            )
+        self.q_proj = nn.Linear(self.hidden_size, self.num_heads * self.head_dim, bias=False)
+        self.k_proj = nn.Linear(self.hidden_size, self.num_key_value_heads * self.head_dim, bias=False)
+        self.v_proj = nn.Linear(self.hidden_size, self.num_key_value_heads * self.head_dim, bias=False)
+        self.o_proj = nn.Linear(self.num_heads * self.head_dim, self.hidden_size, bias=False)
+        self.rotary_emb = RotaryEmbedding(self.head_dim, max_position_embeddings=self.max_position_embeddings,
+                                          base=self.rope_theta)
+
+
+DreamLLMFlashAttention2 = DreamLLMAttention  # same kernel either way
+
+
+# ------------------------------------------------------------------------------------------------ decoder layer
+@dataclass
+class _LayerMeta:
+    num_heads: int
+    head_dim: int
+    inter: int
+    eps: float
+    B: int
+    S: int
+    pos: torch.Tensor          # int32 [T]
+    cos: torch.Tensor
+    sin: torch.Tensor
+    seqlens: torch.Tensor | None
+    wqkv: torch.Tensor          # fused [3H, H] view
+    wgu: torch.Tensor           # fused [2I, H] view
+
+
+class _DecoderLayerFn(torch.autograd.Function):
+    """One DreamLLMDecoderLayer forward/backward (reference :599-654) as a fixed kernel sequence:
+
+    fwd: rmsnorm -> qkv GEMM -> rope(in place) -> flash-attn -> o GEMM -> (+residual, rmsnorm fused) -> gate|up GEMM
+         -> swiglu -> down GEMM -> +residual
+    bwd: the transposed sequence; dgrad = NN GEMM, wgrad = TN GEMM, wgrad skipped for frozen weights.
+    """
+
+    @staticmethod
+    def forward(ctx, x, w_in, wq, wk, wv, wo, w_post, wg, wu, wd, meta: _LayerMeta):
+        B, S, H = x.shape
+        T = B * S
+        nh, d, I = meta.num_heads, meta.head_dim, meta.inter
+        x2 = x.reshape(T, H)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        h1, rstd1, _ = ops.rmsnorm_fwd(x2, w_in, meta.eps)
+        qkv = ops.linear(h1, meta.wqkv)                                   # [T, 3H]
+        ops.rope_(qkv, meta.cos, meta.sin, meta.pos, 2 * nh, d)
+        q4 = qkv.view(B, S, 3, nh, d)
+        ao, lse = ops.attn_fwd(q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], causal=True, seqlens=meta.seqlens)
+        ao2 = ao.view(T, H)
+        o = ops.linear(ao2, wo)
+        h2, rstd2, xmid = ops.rmsnorm_fwd(x2, w_post, meta.eps, add=o)    # xmid = x + o
+        gu = ops.linear(h2, meta.wgu)                                     # [T, 2I]
+        act = ops.swiglu_fwd(gu, I)
+        dn = ops.linear(act, wd)
+        y = ops.add(xmid, dn)
+        ctx.save_for_backward(x2, w_in, rstd1, h1, qkv, ao2, lse, wo, xmid, w_post, rstd2, h2, gu, act, wd)
+        ctx.meta = meta
+        return y.view(B, S, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_in, rstd1, h1, qkv, ao2, lse, wo, xmid, w_post, rstd2, h2, gu, act, wd = ctx.saved_tensors
+        meta = ctx.meta
+        B, S, nh, d, I = meta.B, meta.S, meta.num_heads, meta.head_dim, meta.inter
+        T, H = x2.shape
+        need = ctx.needs_input_grad
+        dy2 = dy.reshape(T, H)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        # ---- MLP
+        dact = ops.linear_dgrad(dy2, wd)
+        dwd = ops.linear_wgrad(dy2, act) if need[9] else None
+        dgu = ops.swiglu_bwd(dact, gu, I)
+        del dact
+        dh2 = ops.linear_dgrad(dgu, meta.wgu)
+        dwg = dwu = None
+        if need[7] or need[8]:
+            dwgu = ops.linear_wgrad(dgu, h2)
+            dwg, dwu = dwgu[:I], dwgu[I:]
+        del dgu
+        dxmid, dw_post = ops.rmsnorm_bwd(dh2, xmid, w_post, rstd2, dres=dy2, need_dw=need[6])
+        # ---- attention
+        dao = ops.linear_dgrad(dxmid, wo)
+        dwo = ops.linear_wgrad(dxmid, ao2) if need[5] else None
+        dqkv = torch.empty_like(qkv)
+        q4 = qkv.view(B, S, 3, nh, d)
+        dq4 = dqkv.view(B, S, 3, nh, d)
+        ops.attn_bwd(dao.view(B, S, H), q4[:, :, 0], q4[:, :, 1], q4[:, :, 2], ao2.view(B, S, H), lse,
+                     dq4[:, :, 0], dq4[:, :, 1], dq4[:, :, 2], causal=True, seqlens=meta.seqlens)
+        ops.rope_(dqkv, meta.cos, meta.sin, meta.pos, 2 * nh, d, backward=True)
+        dh1 = ops.linear_dgrad(dqkv, meta.wqkv)
+        dwq = dwk = dwv = None
+        if need[2] or need[3] or need[4]:
+            dwqkv = ops.linear_wgrad(dqkv, h1)
+            dwq, dwk, dwv = dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]
+        dx, dw_in = ops.rmsnorm_bwd(dh1, x2, w_in, rstd1, dres=dxmid, need_dw=need[1])
+        return (dx.view(B, S, H) if need[0] else None, dw_in, dwq, dwk, dwv, dwo, dw_post, dwg, dwu, dwd, None)
+
+
+class DreamLLMDecoderLayer(nn.Module):
+    def __init__(self, config):
+        super().__init__()
+        _check_supported(config)
+        self.hidden_size = config.hidden_size
+        self.self_attn = DreamLLMAttention(config=config)
+        self.mlp = DreamLLMMLP(config)
+        self.input_layernorm = DreamLLMRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.post_attention_layernorm = DreamLLMRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+
+    def forward(self, hidden_states, attention_mask=None, position_ids=None, past_key_value=None,
+                output_attentions=False, use_cache=False, **kwargs):
+        """Same contract as the reference (:599-654).  `attention_mask` is the 2-D [B, S] padding mask of the
+        flash path (:960-962) or None; right padding as the collator produces (builder_dreamllm.py:467-482)."""
+        if not hidden_states.is_cuda:
+            raise RuntimeError("DreamLLMDecoderLayer (dreamllm_b200) requires CUDA tensors; there is no CPU fallback")
+        if hidden_states.dtype != BF16:
+            raise ValueError("dreamllm_b200 computes in bf16: cast the model and inputs with .to(torch.bfloat16)")
+        if past_key_value is not None:
+            raise NotImplementedError("kv-cache decode is SURVEY §8(f) row 2 (next), not built yet")
+        if output_attentions:
+            raise ValueError("output_attentions=True needs the materialised eager path, which this build does not have")
+        B, S, H = hidden_states.shape
+        if attention_mask is not None and attention_mask.dim() != 2:
+            raise ValueError(
+                f"Attention mask should be of size {(B, S)} (2-D padding mask, flash path), but is {tuple(attention_mask.size())}")
+        att = self.self_attn
+        dev = hidden_states.device
+        if position_ids is None:
+            pos = torch.arange(S, device=dev, dtype=torch.int32).repeat(B)
+        else:
+            pos = position_ids.to(torch.int32).expand(B, S).reshape(-1).contiguous()
+        cos, sin = att.rotary_emb.tables(max(S, att.max_position_embeddings), dev)
+        seqlens = None
+        if attention_mask is not None:
+            seqlens = attention_mask.sum(-1).to(torch.int32).contiguous()
+        meta = _LayerMeta(att.num_heads, att.head_dim, self.mlp.intermediate_size, self.input_layernorm.variance_epsilon,
+                          B, S, pos, cos, sin, seqlens,
+                          _fuse_rows([att.q_proj.weight, att.k_proj.weight, att.v_proj.weight]),
+                          _fuse_rows([self.mlp.gate_proj.weight, self.mlp.up_proj.weight]))
+        y = _DecoderLayerFn.apply(hidden_states, self.input_layernorm.weight, att.q_proj.weight, att.k_proj.weight,
+                                  att.v_proj.weight, att.o_proj.weight, self.post_attention_layernorm.weight,
+                                  self.mlp.gate_proj.weight, self.mlp.up_proj.weight, self.mlp.down_proj.weight, meta)
+        outputs = (y,)
+        if use_cache:
+            raise NotImplementedError("use_cache=True (kv-cache) is SURVEY §8(f) row 2 (next), not built yet")
+        return outputs
+
+
+# ------------------------------------------------------------------------------------------------ model
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, weight):
+        ctx.save_for_backward(ids)
+        ctx.vocab = weight.shape[0]
+        return ops.embedding_fwd(ids, weight)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (ids,) = ctx.saved_tensors
+        H = dy.shape[-1]
+        return None, ops.embedding_bwd(ids, dy.reshape(-1, H).contiguous(), ctx.vocab)
+
+
+class _LMHeadLossFn(torch.autograd.Function):
+    """lm_head GEMM + shifted masked-mean CE (reference :1452-1470).  The bf16 logits buffer is overwritten in place
+    by dlogits during forward, so nothing of size [T, V] is kept in fp32 and backward is two GEMMs."""
+
+    @staticmethod
+    def forward(ctx, h2, weight, shifted_labels):
+        logits = ops.linear(h2, weight)                       # [T, V] bf16 (as the reference: bf16 GEMM, then .float())
+        loss = ops.cross_entropy_(logits, shifted_labels, 1.0, write_grad=True)
+        ctx.save_for_backward(h2, weight, logits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        h2, weight, dlogits = ctx.saved_tensors
+        dh = ops.linear_dgrad(dlogits, weight) if ctx.needs_input_grad[0] else None
+        dw = ops.linear_wgrad(dlogits, h2) if ctx.needs_input_grad[1] else None
+        g = dloss.to(BF16)
+        if dh is not None:
+            dh.mul_(g)
+        if dw is not None:
+            dw.mul_(g)
+        return dh, dw, None
+
+
+@dataclass
+class BaseModelOutputWithPast:
+    last_hidden_state: torch.Tensor = None
+    past_key_values: tuple | None = None
+    hidden_states: tuple | None = None
+    attentions: tuple | None = None
+    additional_log_info: dict | None = None
+
+
+@dataclass
+class CausalLMOutputWithPast:
+    loss: torch.Tensor | None = None
+    logits: torch.Tensor | None = None
+    past_key_values: tuple | None = None
+    hidden_states: tuple | None = None
+    attentions: tuple | None = None
+    additional_log_info: dict | None = None
+
+
+class DreamLLMPreTrainedModel(nn.Module):
+    base_model_prefix = "model"
+    supports_gradient_checkpointing = True
+    _no_split_modules = ["DreamLLMDecoderLayer"]
+    _supports_flash_attn_2 = True
+
+    def _init_weights(self, module):
+        std = self.config.initializer_range
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.padding_idx is not None:
+                module.weight.data[module.padding_idx].zero_()
+
+    def post_init(self):
+        self.apply(self._init_weights)
+
+
+class DreamLLMModel(DreamLLMPreTrainedModel):
+    def __init__(self, config):
+        super().__init__()
+        _check_supported(config)
+        self.config = config
+        self.padding_idx = config.pad_token_id
+        self.vocab_size = config.vocab_size
+        self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size, self.padding_idx)
+        self.layers = nn.ModuleList([DreamLLMDecoderLayer(config) for _ in range(config.num_hidden_layers)])
+        self.norm = DreamLLMRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
+        self.gradient_checkpointing = False
+
+    def get_input_embeddings(self):
+        return self.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.embed_tokens = value
+
+    def _forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                 use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                 attention_mask_has_padding=None):
+        """reference :846-1043.  `attention_mask_has_padding` replaces the `0 in attention_mask` host sync (:962):
+        pass False when the collator knows there is no padding (None = decide on the device-free path: keep the
+        mask and let the kernel honour seqlens)."""
+        if input_ids is not None and inputs_embeds is not None:
+            raise ValueError("You cannot specify both input_ids and inputs_embeds at the same time")
+        if input_ids is None and inputs_embeds is None:
+            raise ValueError("You have to specify either input_ids or inputs_embeds")
+        if inputs_embeds is None:
+            inputs_embeds = _EmbeddingFn.apply(input_ids, self.embed_tokens.weight)
+        if attention_mask_has_padding is False:
+            attention_mask = None
+        hidden_states = inputs_embeds
+        all_hidden = () if output_hidden_states else None
+        for layer in self.layers:
+            if output_hidden_states:
+                all_hidden += (hidden_states,)
+            hidden_states = layer(hidden_states, attention_mask=attention_mask, position_ids=position_ids)[0]
+        hidden_states = self.norm(hidden_states)
+        if output_hidden_states:
+            all_hidden += (hidden_states,)
+        return BaseModelOutputWithPast(last_hidden_state=hidden_states, hidden_states=all_hidden)
+
+    forward = _forward
+
+
+class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
+    _tied_weights_keys = {"lm_head.weight": "model.embed_tokens.weight"}
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.model = DreamLLMModel(config)
+        self.vocab_size = config.vocab_size
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.loss_weight_lm = getattr(config, "loss_weight_lm", 1.0)
+        self.loss_weight_vm = getattr(config, "loss_weight_vm", 1.0)
+        self.post_init()
+
+    def get_input_embeddings(self):
+        return self.model.embed_tokens
+
+    def set_input_embeddings(self, value):
+        self.model.embed_tokens = value
+
+    def get_output_embeddings(self):
+        return self.lm_head
+
+    def set_output_embeddings(self, new_embeddings):
+        self.lm_head = new_embeddings
+
+    def set_decoder(self, decoder):
+        self.model = decoder
+
+    def get_decoder(self):
+        return self.model
+
+    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
+                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
+                attention_mask_has_padding=None, **kwargs):
+        """Text / inputs_embeds path of reference :1353-1509 (images / images_dm are handled by modeling_plugins)."""
+        out = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                         inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states,
+                         attention_mask_has_padding=attention_mask_has_padding)
+        hidden = out.last_hidden_state
+        B, S, H = hidden.shape
+        h2 = hidden.reshape(B * S, H)
+        loss = None
+        logits = None
+        lm_loss = 0.0
+        if labels is not None:
+            shifted = torch.full_like(labels, -100)
+            shifted[:, :-1] = labels[:, 1:]
+            lm_loss = _LMHeadLossFn.apply(h2, self.lm_head.weight, shifted.reshape(-1).contiguous())
+            loss = lm_loss * self.loss_weight_lm
+        else:
+            logits = ops.linear(h2, self.lm_head.weight).view(B, S, -1).float()
+        return CausalLMOutputWithPast(loss=loss, logits=logits, hidden_states=out.hidden_states,
+                                      additional_log_info={"lm_loss": lm_loss})

@@ -13,6 +13,41 @@ from ._lib import check, lib
 BF16 = torch.bfloat16
 
 
+class _LaunchCounter:
+    """Counts OUR kernel launches (bench.py's `gpu_launches`)."""
+
+    def __init__(self):
+        self.count = 0
+
+    def reset(self):
+        self.count = 0
+
+    def add(self, n=1):
+        self.count += n
+
+
+class _GemmProfile:
+    """Optional live CUDA-event timing of every GEMM launch on the launching stream (bench.py roofline)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []
+
+    def reset(self, enabled=False):
+        self.enabled = enabled
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e, _ in self.records)
+        fl = sum(f for _, _, f in self.records)
+        return {"ms": ms, "tflops": (fl / 1e9 / ms) if ms > 0 else None, "n": len(self.records)}
+
+
+LAUNCHES = _LaunchCounter()
+PROFILE = _GemmProfile()
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -51,9 +86,16 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
     assert out.shape == (M, N) and out.stride(1) == 1 and out.dtype in (BF16, torch.float32)
+    if PROFILE.enabled:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = lib().dllm_gemm_bf16(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
                               int(b_mn), int(out.dtype == torch.float32), cta_pair, _stream())
     check(rc, "dllm_gemm_bf16")
+    if PROFILE.enabled:
+        e1.record()
+        PROFILE.records.append((e0, e1, 2.0 * M * N * K))
+    LAUNCHES.add(1)
     return out
 
 
@@ -85,6 +127,7 @@ def rmsnorm_fwd(x2d, weight, eps, add=None, want_sum=True):
         assert add.is_contiguous() and add.shape == x2d.shape
     check(lib().dllm_rmsnorm_fwd(_p(x2d), _p(add), _p(weight), _p(x_out), _p(y), _p(rstd), T, H, float(eps), _stream()),
           "dllm_rmsnorm_fwd")
+    LAUNCHES.add(1)
     return y, rstd, (x_out if add is not None else x2d)
 
 
@@ -99,6 +142,7 @@ def rmsnorm_bwd(dy2d, x2d, weight, rstd, dres=None, need_dw=True):
     ws = torch.empty(max(wsb, 4), device=x2d.device, dtype=torch.uint8)
     check(lib().dllm_rmsnorm_bwd(_p(dy2d), _p(x2d), _p(weight), _p(rstd), _p(dres), _p(dx), _p(dw), 0, _p(ws), wsb, T, H,
                                  _stream()), "dllm_rmsnorm_bwd")
+    LAUNCHES.add(2)
     return dx, dw
 
 
@@ -111,6 +155,7 @@ def rope_(buf2d, cos_t, sin_t, pos_i32, heads_total, head_dim, backward=False):
     assert cos_t.dtype == BF16 and cos_t.is_contiguous() and cos_t.shape[1] == head_dim
     check(lib().dllm_rope_inplace(_p(buf2d), _p(cos_t), _p(sin_t), _p(pos_i32), buf2d.stride(0), T, heads_total, head_dim,
                                   -1 if backward else 1, _stream()), "dllm_rope_inplace")
+    LAUNCHES.add(1)
     return buf2d
 
 
@@ -120,6 +165,7 @@ def swiglu_fwd(gu2d, inter):
     assert gu2d.shape[1] == 2 * inter and gu2d.stride(1) == 1
     act = torch.empty((T, inter), device=gu2d.device, dtype=BF16)
     check(lib().dllm_swiglu_fwd(_p(gu2d), _p(act), gu2d.stride(0), T, inter, _stream()), "dllm_swiglu_fwd")
+    LAUNCHES.add(1)
     return act
 
 
@@ -129,6 +175,7 @@ def swiglu_bwd(dact2d, gu2d, inter, out=None):
     assert dact2d.is_contiguous() and gu2d.is_contiguous()
     dgu = torch.empty_like(gu2d) if out is None else out
     check(lib().dllm_swiglu_bwd(_p(dact2d), _p(gu2d), _p(dgu), gu2d.stride(0), T, inter, _stream()), "dllm_swiglu_bwd")
+    LAUNCHES.add(1)
     return dgu
 
 
@@ -137,6 +184,7 @@ def add(a, b, out=None):
     assert a.is_contiguous() and b.is_contiguous() and a.shape == b.shape
     out = torch.empty_like(a) if out is None else out
     check(lib().dllm_add_bf16(_p(a), _p(b), _p(out), a.numel(), _stream()), "dllm_add_bf16")
+    LAUNCHES.add(1)
     return out
 
 
@@ -151,6 +199,7 @@ def cross_entropy_(logits2d, shifted_labels, dloss=1.0, write_grad=True):
     ws = torch.empty(T + 2, device=logits2d.device, dtype=torch.float32)
     check(lib().dllm_cross_entropy(_p(logits2d), _p(shifted_labels), _p(loss), float(dloss), _p(ws), logits2d.stride(0), T,
                                    V, int(write_grad), _stream()), "dllm_cross_entropy")
+    LAUNCHES.add(3)
     return loss[0]
 
 
@@ -161,6 +210,7 @@ def embedding_fwd(ids, weight):
     H = weight.shape[1]
     out = torch.empty((*ids.shape, H), device=weight.device, dtype=weight.dtype)
     check(lib().dllm_embedding_fwd(_p(ids), _p(weight), _p(out), T, H, _stream()), "dllm_embedding_fwd")
+    LAUNCHES.add(1)
     return out
 
 
@@ -170,6 +220,7 @@ def embedding_bwd(ids, dy2d, vocab):
     sorted_ids, order = torch.sort(ids.reshape(-1), stable=True)
     dW = torch.zeros((vocab, H), device=dy2d.device, dtype=dy2d.dtype)
     check(lib().dllm_embedding_bwd(_p(sorted_ids), _p(order), _p(dy2d), _p(dW), T, H, 0, _stream()), "dllm_embedding_bwd")
+    LAUNCHES.add(1)
     return dW
 
 
@@ -187,6 +238,7 @@ def attn_fwd(q, k, v, causal=True, seqlens=None, scale=None):
     scale = float(d) ** -0.5 if scale is None else float(scale)
     check(lib().dllm_attn_fwd(_p(q), _p(k), _p(v), _p(out), _p(lse), _p(seqlens), B, S, nh, d, q.stride(1), nh * d,
                               int(causal), scale, _stream()), "dllm_attn_fwd")
+    LAUNCHES.add(1)
     return out, lse
 
 
@@ -202,4 +254,5 @@ def attn_bwd(dout, q, k, v, out, lse, dq, dk, dv, causal=True, seqlens=None, sca
     check(lib().dllm_attn_bwd(_p(dout), _p(q), _p(k), _p(v), _p(out), _p(lse), _p(dq), _p(dk), _p(dv), _p(seqlens), _p(ws),
                               wsb, B, S, nh, d, q.stride(1), nh * d, dq.stride(1), int(causal), scale, _stream()),
           "dllm_attn_bwd")
+    LAUNCHES.add(3)
     return dq, dk, dv

@@ -1,0 +1,60 @@
+"""CPU-side checks of the C-ABI boundary: the library builds for sm_100a, loads without a GPU, exports every
+symbol include/dreamllm_sm100.h declares, and the product path fails loudly (no CPU fallback)."""
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "dreamllm_sm100.h")).read()
+    return sorted(set(re.findall(r"\b(dllm_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dreamllm_b200 import _lib
+    _lib.build()
+    L = _lib.lib()
+    syms = _declared_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/dreamllm_sm100.h but not exported"
+        assert s in _lib.SIGNATURES, f"{s} has no ctypes signature"
+    assert L.dllm_version() >= 100
+    assert L.dllm_error_string(-1).decode().startswith("invalid")
+    # pure host queries work without a device
+    assert L.dllm_attn_bwd_workspace_bytes(2, 128, 4, 128) == 2 * 128 * 4 * 2 * 4
+
+
+def test_sass_contains_tcgen05_and_tma():
+    """The shipped cubin is Blackwell-native: tcgen05.mma (UTC*MMA), TMEM loads (LDTM), TMA (UTMALDG/UTMASTG)."""
+    import subprocess
+    from dreamllm_b200 import _lib
+    _lib.build()
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for mnem in ("UTCHMMA", "LDTM", "UTMALDG", "UTMASTG"):
+        assert mnem in sass, mnem
+    assert "HMMA.16816" not in sass      # no legacy mma.sync path
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    from dreamllm_b200 import ops
+    from dreamllm_b200.modeling_dreamllm import DreamLLMConfig, DreamLLMDecoderLayer
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ops.gemm(torch.zeros(8, 8, dtype=torch.bfloat16), torch.zeros(8, 8, dtype=torch.bfloat16))
+    layer = DreamLLMDecoderLayer(DreamLLMConfig(hidden_size=256, intermediate_size=512, num_attention_heads=2)).to(torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        layer(torch.zeros(1, 8, 256, dtype=torch.bfloat16))
+
+
+def test_product_does_not_import_oracle():
+    """oracle/ is test infrastructure: nothing under dreamllm_b200/ may reference it."""
+    for dp, _, files in os.walk(os.path.join(ROOT, "dreamllm_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dp, f)

@@ -1,0 +1,126 @@
+"""DreamLLMDecoderLayer fwd+bwd parity (CUDA path through the C ABI) against
+
+  (1) tests/golden/decoder_layer_*.npz — the REFERENCE's own fp32 outputs/gradients (oracle/gen_golden.py), and
+  (2) the CPU oracle run in bf16 (bit-identical to the reference's bf16 eager path, tests/test_oracle_pin.py).
+
+Tolerance (BASELINE.json north_star: rtol 1e-3 / atol 1e-5 "bf16"): bf16 has an 8-bit significand (1 ulp = 3.9e-3
+relative), so the reference's own bf16 path meets that bound against its fp32 path on only ~7% of elements.
+It is therefore applied like-for-like:
+  (a) kernels with an fp32 epilogue are checked against fp32 references at rtol 1e-3 (tests/test_gemm_gpu.py,
+      cross-entropy loss in tests/test_elementwise_gpu.py);
+  (b) here, end-to-end in bf16:  err(ours_bf16, ref_fp32) <= 1.25 * err(ref_bf16, ref_fp32) + eps, for the mean and the
+      99.9th-percentile absolute error of y, dx and every weight gradient — i.e. we are as close to the fp32 reference as
+      the reference's own bf16 run is.
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder_oracle as O
+from oracle import gen_golden
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "decoder_layer_*.npz")))
+
+
+def _err(a, ref):
+    e = (a.float() - ref.float()).abs().flatten()
+    k = max(1, int(e.numel() * 0.999))
+    return float(e.mean()), float(e.kthvalue(k).values)
+
+
+def _build_layer(hidden, inter, heads, p):
+    from dreamllm_b200.modeling_dreamllm import DreamLLMConfig, DreamLLMDecoderLayer
+    cfg = DreamLLMConfig(hidden_size=hidden, intermediate_size=inter, num_attention_heads=heads, num_hidden_layers=1)
+    layer = DreamLLMDecoderLayer(cfg)
+    sd = {k: v.clone() for k, v in p.items()}
+    sd["self_attn.rotary_emb.inv_freq"] = layer.self_attn.rotary_emb.inv_freq.clone()
+    layer.load_state_dict(sd)          # same keys as the reference layer (strict)
+    return layer.to(device="cuda", dtype=BF)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_layer_vs_reference_golden(path):
+    g = np.load(path)
+    hidden, inter, heads, bsz, seq, seed, pad = [int(v) for v in g["shape"]]
+    p = O.init_layer_params(hidden, inter, seed)
+    x, gy = gen_golden.make_inputs(hidden, bsz, seq, seed)
+    am = None
+    if pad:
+        am = torch.ones(bsz, seq, dtype=torch.long)
+        am[1, seq - pad:] = 0
+        gy = gy * am[..., None]
+    valid = torch.ones(bsz, seq, dtype=torch.bool) if am is None else am.bool()
+
+    # ---- reference-bf16 (CPU oracle in bf16 == reference bf16 eager path)
+    pb = {k: v.to(BF).requires_grad_(True) for k, v in p.items()}
+    xb = x.to(BF).requires_grad_(True)
+    cos, sin = O.rope_tables(hidden // heads, 2048, dtype=BF)
+    pos = torch.arange(seq)[None].expand(bsz, -1)
+    yb = O.decoder_layer(xb, pb, heads, cos, sin, pos, O.causal_additive_mask(bsz, seq, BF, am))
+    yb.backward(gy.to(BF))
+
+    # ---- ours
+    layer = _build_layer(hidden, inter, heads, p)
+    xc = x.to(BF).cuda().requires_grad_(True)
+    y = layer(xc, attention_mask=am.cuda() if am is not None else None)[0]
+    y.backward(gy.to(BF).cuda())
+    torch.cuda.synchronize()
+
+    gold_y, gold_dx = torch.from_numpy(g["y"]), torch.from_numpy(g["dx"])
+    checks = [("y", y.detach().cpu()[valid], yb.detach()[valid], gold_y[valid]),
+              ("dx", xc.grad.cpu()[valid], xb.grad[valid], gold_dx[valid])]
+    ours_named = dict(layer.named_parameters())
+    for k in O.LAYER_KEYS:
+        gr, grb = ours_named[k].grad.cpu(), pb[k].grad
+        sl = (lambda t: t[:8, :64]) if gr.dim() == 2 else (lambda t: t)
+        checks.append(("d_" + k, sl(gr), sl(grb), torch.from_numpy(g["d_" + k])))
+    report = []
+    for name, ours, refb, gold in checks:
+        m_o, p_o = _err(ours, gold)
+        m_r, p_r = _err(refb, gold)
+        scale = float(gold.abs().mean()) + 1e-12
+        report.append(f"{name}: ours mean {m_o:.3e} p99.9 {p_o:.3e} | ref-bf16 mean {m_r:.3e} p99.9 {p_r:.3e} | |gold| {scale:.3e}")
+        assert m_o <= 1.25 * m_r + 2e-3 * scale, report[-1]
+        assert p_o <= 1.5 * p_r + 2e-2 * scale, report[-1]
+    print("\n".join(report))
+    # like-for-like ulp report vs reference-bf16 (informational + loose bound)
+    d = (y.detach().cpu()[valid].float() - yb.detach()[valid].float()).abs()
+    frac_exact = float((d == 0).float().mean())
+    print(f"bf16-vs-bf16: {frac_exact*100:.1f}% bit-identical, max |d| {float(d.max()):.3e}")
+    # weight-gradient column sums (whole tensor, not just the stored slice)
+    for k in O.LAYER_KEYS:
+        tot = float(ours_named[k].grad.double().sum())
+        want = float(g["dsum_" + k])
+        ref_tot = float(pb[k].grad.double().sum())
+        assert abs(tot - want) <= 1.5 * abs(ref_tot - want) + 2e-2 * (abs(want) + 1e-3), (k, tot, want, ref_tot)
+
+
+def test_layer_state_dict_keys_match_reference():
+    from dreamllm_b200.modeling_dreamllm import DreamLLMConfig, DreamLLMDecoderLayer
+    layer = DreamLLMDecoderLayer(DreamLLMConfig(hidden_size=256, intermediate_size=512, num_attention_heads=2))
+    assert sorted(layer.state_dict().keys()) == sorted(list(O.LAYER_KEYS) + ["self_attn.rotary_emb.inv_freq"])
+
+
+def test_layer_frozen_weights_skip_wgrad_but_pass_dgrad():
+    """stage-1 freezing (configs/stage1/base.py:29-36): grads must still reach the input."""
+    p = O.init_layer_params(256, 512, 3)
+    layer = _build_layer(256, 512, 2, p)
+    for q in layer.parameters():
+        q.requires_grad_(False)
+    x = torch.randn(2, 64, 256, device="cuda").to(BF).requires_grad_(True)
+    layer(x)[0].float().pow(2).mean().backward()
+    assert x.grad is not None and float(x.grad.abs().sum()) > 0
+    assert all(q.grad is None for q in layer.parameters())
+
+
+def test_layer_recompute_is_deterministic():
+    """gradient checkpointing re-enters forward during backward (reference :994-1003): bitwise repeatable."""
+    p = O.init_layer_params(256, 512, 4)
+    layer = _build_layer(256, 512, 2, p)
+    x = torch.randn(1, 200, 256, device="cuda").to(BF)
+    assert torch.equal(layer(x)[0], layer(x)[0])
