@@ -7,6 +7,32 @@ using namespace dllm;
 
 static inline cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
 
+// Autograd may call us on a worker thread that has never touched CUDA (observed on B200: cuTensorMapEncodeTiled ->
+// CUDA_ERROR_INVALID_CONTEXT when the first CUDA work of the engine's device thread is one of our Functions).  Bind the
+// context that owns the caller's buffer — never "device 0" — before any driver/runtime call.
+typedef CUresult (*PFN_ctxGetCurrent)(CUcontext*);
+typedef CUresult (*PFN_ctxSetCurrent)(CUcontext);
+typedef CUresult (*PFN_ptrGetAttr)(void*, CUpointer_attribute, CUdeviceptr);
+static void ensure_context(const void* dev_ptr) {
+  static PFN_ctxGetCurrent get_cur = nullptr;
+  static PFN_ctxSetCurrent set_cur = nullptr;
+  static PFN_ptrGetAttr ptr_attr = nullptr;
+  static bool resolved = false;
+  if (!resolved) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &p, cudaEnableDefault, &q) == cudaSuccess) get_cur = (PFN_ctxGetCurrent)p;
+    if (cudaGetDriverEntryPoint("cuCtxSetCurrent", &p, cudaEnableDefault, &q) == cudaSuccess) set_cur = (PFN_ctxSetCurrent)p;
+    if (cudaGetDriverEntryPoint("cuPointerGetAttribute", &p, cudaEnableDefault, &q) == cudaSuccess) ptr_attr = (PFN_ptrGetAttr)p;
+    resolved = true;
+  }
+  if (!get_cur || !set_cur || !ptr_attr || !dev_ptr) return;
+  CUcontext cur = nullptr;
+  if (get_cur(&cur) == CUDA_SUCCESS && cur) return;
+  CUcontext owner = nullptr;
+  if (ptr_attr(&owner, CU_POINTER_ATTRIBUTE_CONTEXT, reinterpret_cast<CUdeviceptr>(dev_ptr)) == CUDA_SUCCESS && owner) set_cur(owner);
+}
+
 extern "C" {
 
 int dllm_version(void) { return 100; }
@@ -26,49 +52,63 @@ const char* dllm_error_string(int code) {
 
 int dllm_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
                    int b_mn, int out_fp32, int cta_pair, void* stream) {
+  ensure_context(A);
   return gemm_bf16(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_fp32, cta_pair, S(stream));
 }
 
 int dllm_rmsnorm_fwd(const void* x, const void* add, const void* weight, void* x_out, void* y, float* rstd, int T, int H,
                      float eps, void* stream) {
+  ensure_context(x);
   return rmsnorm_fwd(x, add, weight, x_out, y, rstd, T, H, eps, S(stream));
 }
 size_t dllm_rmsnorm_bwd_workspace_bytes(int T, int H) { return rmsnorm_bwd_workspace(T, H); }
 int dllm_rmsnorm_bwd(const void* dy, const void* x, const void* weight, const float* rstd, const void* dres, void* dx,
                      void* dweight, int dweight_accumulate, void* workspace, size_t workspace_bytes, int T, int H,
                      void* stream) {
+  ensure_context(dy);
   return rmsnorm_bwd(dy, x, weight, rstd, dres, dx, dweight, dweight_accumulate, workspace, workspace_bytes, T, H, S(stream));
 }
 int dllm_rope_inplace(void* buf, const void* cos_table, const void* sin_table, const int* pos, long ld, int T,
                       int heads_total, int head_dim, int mode, void* stream) {
+  ensure_context(buf);
   return rope_inplace(buf, cos_table, sin_table, pos, ld, T, heads_total, head_dim, mode, S(stream));
 }
 int dllm_swiglu_fwd(const void* gate_up, void* act, long ld, int T, int I, void* stream) {
+  ensure_context(gate_up);
   return swiglu_fwd(gate_up, act, ld, T, I, S(stream));
 }
 int dllm_swiglu_bwd(const void* dact, const void* gate_up, void* dgate_up, long ld, int T, int I, void* stream) {
+  ensure_context(dact);
   return swiglu_bwd(dact, gate_up, dgate_up, ld, T, I, S(stream));
 }
-int dllm_add_bf16(const void* a, const void* b, void* out, long n, void* stream) { return add_bf16(a, b, out, n, S(stream)); }
+int dllm_add_bf16(const void* a, const void* b, void* out, long n, void* stream) {
+  ensure_context(a);
+  return add_bf16(a, b, out, n, S(stream));
+}
 int dllm_cross_entropy(void* logits, const long long* labels, float* loss, float dloss, void* workspace, long ld, int T,
                        int V, int write_grad, void* stream) {
+  ensure_context(logits);
   return cross_entropy(logits, labels, loss, dloss, workspace, ld, T, V, write_grad, S(stream));
 }
 int dllm_embedding_fwd(const long long* ids, const void* weight, void* out, int T, int H, void* stream) {
+  ensure_context(weight);
   return embedding_fwd(ids, weight, out, T, H, S(stream));
 }
 int dllm_embedding_bwd(const long long* sorted_ids, const long long* order, const void* dy, void* dweight, int T, int H,
                        int accumulate, void* stream) {
+  ensure_context(dy);
   return embedding_bwd(sorted_ids, order, dy, dweight, T, H, accumulate, S(stream));
 }
 int dllm_attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int Sq,
                   int nh, int d, long ld_qkv, long ld_o, int causal, float scale, void* stream) {
+  ensure_context(q);
   return attn_fwd(q, k, v, out, lse, seqlens, B, Sq, nh, d, ld_qkv, ld_o, causal, scale, S(stream));
 }
 size_t dllm_attn_bwd_workspace_bytes(int B, int Sq, int nh, int d) { return attn_bwd_workspace(B, Sq, nh, d); }
 int dllm_attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse,
                   void* dq, void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B,
                   int Sq, int nh, int d, long ld_qkv, long ld_o, long ld_dqkv, int causal, float scale, void* stream) {
+  ensure_context(dout);
   return attn_bwd(dout, q, k, v, out, lse, dq, dk, dv, seqlens, workspace, workspace_bytes, B, Sq, nh, d, ld_qkv, ld_o,
                   ld_dqkv, causal, scale, S(stream));
 }

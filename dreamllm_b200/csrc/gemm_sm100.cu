@@ -283,6 +283,9 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t row
   CUtensorMapDataType dt = elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = enc(map, dt, 2, const_cast<void*>(ptr), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fprintf(stderr, "dllm: cuTensorMapEncodeTiled failed (CUresult %d): ptr=%p elem=%d rows=%llu cols=%llu ld=%llu box=[%u x %u]\n",
+            (int)r, ptr, elem_bytes, (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows, box_cols);
   return r == CUDA_SUCCESS ? 0 : DLLM_ERR_TMAP;
 }
 
