@@ -74,6 +74,13 @@ SIGNATURES = {
     "dllm_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _l, _l, _i, _f, _vp]),
     "dllm_attn_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "dllm_attn_bwd": (_i, [_vp] * 11 + [_sz, _i, _i, _i, _i, _l, _l, _l, _i, _f, _vp]),
+    "dllm_gemm_bf16_ex": (_i, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _i, _i, _i, _i, _vp, _vp, _l, _i, _vp]),
+    "dllm_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "dllm_clip_patchify": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dllm_clip_assemble": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dllm_copy_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "dllm_segment_sum_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "dllm_zero_rows": (_i, [_vp, _vp, _i, _i, _vp]),
 }
 
 _lib = None

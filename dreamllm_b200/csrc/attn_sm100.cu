@@ -65,12 +65,14 @@ __device__ __forceinline__ void store_row_chunk(uint8_t* tile, int row, int j, c
 
 // TMEM accumulator (128 lanes x D fp32 cols) -> *scale -> bf16 -> swizzled staging [D/64][128 rows][128 B] -> per-warp
 // TMA store of [32 rows x 64 cols] boxes at (col0 + c*64, row0 + 32*warp, b).
+// Only 64-column chunks [ch_begin, ch_end) are handled (lets two warpgroups split the columns).
 template <int D>
 __device__ __forceinline__ void store_acc_tile(uint32_t tmem_acc, uint8_t* stage, float mul, const CUtensorMap* tm,
-                                               int col0, int row0, int b, int warp, int lane) {
+                                               int col0, int row0, int b, int warp, int lane, int ch_begin = 0,
+                                               int ch_end = D / 64) {
   const int row = warp * 32 + lane;
 #pragma unroll 1
-  for (int c = 0; c < D / 32; ++c) {
+  for (int c = 2 * ch_begin; c < 2 * ch_end; ++c) {
     uint32_t v[32];
     tmem_ld32(tmem_acc + (static_cast<uint32_t>(warp * 32) << 16) + c * 32, v);
     tmem_ld_wait();
@@ -86,8 +88,7 @@ __device__ __forceinline__ void store_acc_tile(uint32_t tmem_acc, uint8_t* stage
   fence_proxy_async_smem();
   __syncwarp();
   if (lane == 0) {
-#pragma unroll
-    for (int c = 0; c < D / 64; ++c) tma_store_3d(tm, stage + c * 16384 + warp * 4096, col0 + c * 64, row0 + warp * 32, b);
+    for (int c = ch_begin; c < ch_end; ++c) tma_store_3d(tm, stage + c * 16384 + warp * 4096, col0 + c * 64, row0 + warp * 32, b);
     tma_store_commit();
     tma_store_wait_all<0>();
   }
@@ -293,17 +294,29 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 
 // ================================================================================================ backward prep
 // delta[b,h,s] = sum_d dO*O ; lse2 = lse*log2(e).  One warp per (token, head).
+// Output layout is padded to [B, nh, S_pad] (S_pad = S rounded up to 64, pad entries = 0) so the backward kernels can
+// fetch a q tile's 64 values with aligned float4 loads.
 template <int D>
 __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, const float* __restrict__ lse,
-                                     float* __restrict__ delta, float* __restrict__ lse2, int B, int S, int nh, long ld_o) {
+                                     float* __restrict__ delta, float* __restrict__ lse2, int B, int S, int S_pad, int nh,
+                                     long ld_o) {
   const long gw = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
-  const long total = static_cast<long>(B) * S * nh;
+  const long total = static_cast<long>(B) * S_pad * nh;
   if (gw >= total) return;
   const int h = static_cast<int>(gw % nh);
-  const long tok = gw / nh;
-  const int s = static_cast<int>(tok % S);
-  const int b = static_cast<int>(tok / S);
+  const long tokp = gw / nh;
+  const int s = static_cast<int>(tokp % S_pad);
+  const int b = static_cast<int>(tokp / S_pad);
+  if (s >= S) {
+    if (lane == 0) {
+      const size_t idxp = (static_cast<size_t>(b) * nh + h) * S_pad + s;
+      delta[idxp] = 0.f;
+      lse2[idxp] = 0.f;
+    }
+    return;
+  }
+  const long tok = static_cast<long>(b) * S + s;
   const bf16* po = out + tok * ld_o + h * D;
   const bf16* pd = dout + tok * ld_o + h * D;
   float acc = 0.f;
@@ -317,8 +330,9 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* 
   acc = warp_sum(acc);
   if (lane == 0) {
     const size_t idx = (static_cast<size_t>(b) * nh + h) * S + s;
-    delta[idx] = acc;
-    lse2[idx] = lse[idx] * kLog2e;
+    const size_t idxp = (static_cast<size_t>(b) * nh + h) * S_pad + s;
+    delta[idxp] = acc;
+    lse2[idxp] = lse[idx] * kLog2e;
   }
 }
 
@@ -327,23 +341,29 @@ __global__ void attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* 
 // MMAs consume as an A operand ([kv][q] tiles P^T and dS^T) is K-major as written.
 //   S^T  = K  Q_i^T      dP^T = V dO_i^T            (M = 128 kv, N = 64 q, K = d)
 //   dV  += P^T dO_i      dK  += dS^T Q_i            (M = 128 kv, N = d,    K = 64 q; B operands MN-major)
+// 320 threads: warps 0-7 are row warps — warp w owns TMEM lane quarter (w & 3) and q-column half (w >> 2), i.e. two
+// warps per SM sub-partition share a row and split its 64 columns (r01's 4-warp version was issue-latency bound:
+// tensor pipe 6 %, profiles/r01_ncu_full_summary.csv).  warp 8 = TMA producer, warp 9 = TMEM alloc + MMA issuer.
+// P^T / dS^T staging is double-buffered so the row warps never wait on the previous iteration's dV/dK MMAs.
+constexpr int kBwdThreads = 320;
+
 template <int D>
 struct BwdKVSmem {
   static constexpr int NCH = D / 64;
   static constexpr int kKV = NCH * 16384;  // [NCH][128][128B]
   static constexpr int kQ = NCH * 8192;    // [NCH][64][128B]
-  static constexpr int oK = 0, oV = kKV, oQ = 2 * kKV, oDO = oQ + 2 * kQ, oP = oDO + 2 * kQ, oDS = oP + 16384,
-                       oBar = oDS + 16384;
+  static constexpr int oK = 0, oV = kKV, oQ = 2 * kKV, oDO = oQ + 2 * kQ, oP = oDO + 2 * kQ, oDS = oP + 2 * 16384,
+                       oBar = oDS + 2 * 16384;
   static constexpr int kBytes = oBar + 256;
 };
 
 template <int D, bool kCausal>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                      const __grid_constant__ CUtensorMap tdk, const __grid_constant__ CUtensorMap tdv,
                      const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ seqlens,
-                     int S, int nh, float scale, float scale_log2) {
+                     int S, int S_pad, int nh, float scale, float scale_log2) {
   using L = BwdKVSmem<D>;
   constexpr int NCH = L::NCH;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -352,9 +372,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
   uint64_t* qdo_full = bars + 1;   // [2]
   uint64_t* qdo_empty = bars + 3;  // [2]
   uint64_t* sdp_full = bars + 5;   // [2]
-  uint64_t* pds_full = bars + 7;
-  uint64_t* acc_done = bars + 8;   // dV/dK MMAs of iteration i retired
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* pds_full = bars + 7;   // [2] (indexed i & 1: row warps may run one iteration ahead of the MMA warp)
+  uint64_t* acc_done = bars + 9;   // [2]: dV/dK MMAs of iteration i retired (indexed i & 1)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -366,12 +386,13 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_bwd_dkdv: smem misaligned\n"); __trap(); }
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&sdp_full[i], 1); }
-    mbar_init(pds_full, 128);
-    mbar_init(acc_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&pds_full[i], 256);
+    }
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  if (warp == 9) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -381,7 +402,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
   const uint32_t tmem_dV = tmem_base + 256;   // D
   const uint32_t tmem_dK = tmem_base + 256 + D;
 
-  if (warp == 4 && lane == 0 && n_it > 0) {
+  if (warp == 8 && lane == 0 && n_it > 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
     mbar_arrive_expect_tx(kv_full, 2 * 128 * D * 2);
     for (int c = 0; c < NCH; ++c) {
@@ -398,7 +419,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         tma_load_3d(smem + L::oDO + st * L::kQ + c * 8192, &tdo, &qdo_full[st], h * D + c * 64, qr0, b);
       }
     }
-  } else if (warp == 5 && lane == 0 && n_it > 0) {
+  } else if (warp == 9 && lane == 0 && n_it > 0) {
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
     const uint32_t sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV), sQ = smem_u32(smem + L::oQ),
@@ -416,59 +437,71 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     for (int it = 0; it < n_it; ++it) {
       if (it + 1 < n_it) issue_s(it + 1);
       const int st = it & 1;
-      mbar_wait(pds_full, it & 1, 23);
+      mbar_wait(&pds_full[st], (it >> 1) & 1, 23);
       tc_fence_after();
-      mma_tile(tmem_dV, sP, false, 0, sDO + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
-      mma_tile(tmem_dK, sDS, false, 0, sQ + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
+      mma_tile(tmem_dV, sP + st * 16384, false, 0, sDO + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
+      mma_tile(tmem_dK, sDS + st * 16384, false, 0, sQ + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
       umma_commit(&qdo_empty[st]);
-      umma_commit(acc_done);
+      umma_commit(&acc_done[st]);
     }
-  } else if (warp < 4) {
-    const int row = warp * 32 + lane;  // kv row within tile
+  } else if (warp < 8) {
+    const int wq = warp & 3, half = warp >> 2;
+    const int row = wq * 32 + lane;  // kv row within tile
     const int kv_row = kv0 + row;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const float* lse_bh = lse2 + (static_cast<size_t>(b) * nh + h) * S;
-    const float* del_bh = delta + (static_cast<size_t>(b) * nh + h) * S;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const float* lse_bh = lse2 + (static_cast<size_t>(b) * nh + h) * S_pad;
+    const float* del_bh = delta + (static_cast<size_t>(b) * nh + h) * S_pad;
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1;
-      const int qr0 = (i_begin + it) * 64;
+      const int qc0 = (i_begin + it) * 64 + half * 32;  // first q index of my 32 columns
+      // my 32 columns' lse / delta: 16 broadcast float4 loads (all lanes read the same addresses)
+      float lq[32], dq_[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(lse_bh + qc0) + i);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(del_bh + qc0) + i);
+        lq[4 * i] = a.x; lq[4 * i + 1] = a.y; lq[4 * i + 2] = a.z; lq[4 * i + 3] = a.w;
+        dq_[4 * i] = c.x; dq_[4 * i + 1] = c.y; dq_[4 * i + 2] = c.z; dq_[4 * i + 3] = c.w;
+      }
       mbar_wait(&sdp_full[st], (it >> 1) & 1, 24);
       tc_fence_after();
-      if (it > 0) mbar_wait(acc_done, (it - 1) & 1, 25);  // previous dV/dK MMAs finished reading sP/sDS
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_St + lane_off + st * 64 + half * 32, sv);
-        tmem_ld32(tmem_dPt + lane_off + st * 64 + half * 32, dv);
-        tmem_ld_wait();
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tmem_St + lane_off + st * 64 + half * 32, sv);
+      tmem_ld32(tmem_dPt + lane_off + st * 64 + half * 32, dv);
+      tmem_ld_wait();
+      // staging buffer `st` was last read by the dV/dK MMAs of iteration it-2
+      if (it >= 2) mbar_wait(&acc_done[st], ((it >> 1) & 1) ^ 1, 25);
+      const bool full_tile = (qc0 + 31 < len) && (kv0 + 127 < len) && (!kCausal || kv0 + 127 <= qc0);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float p[8], ds[8];
+      for (int jj = 0; jj < 4; ++jj) {
+        float p[8], ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = half * 32 + jj * 8 + e;
-            const int qi = qr0 + c;
-            const bool ok = (qi < len) && (kv_row < len) && (!kCausal || kv_row <= qi);
-            const int qs = min(qi, S - 1);
-            const float pe = ok ? exp2f(__uint_as_float(sv[jj * 8 + e]) * scale_log2 - __ldg(lse_bh + qs)) : 0.f;
-            p[e] = pe;
-            ds[e] = pe * (__uint_as_float(dv[jj * 8 + e]) - __ldg(del_bh + qs)) * scale;
-          }
-          store_row_chunk(smem + L::oP, row, half * 4 + jj, p);
-          store_row_chunk(smem + L::oDS, row, half * 4 + jj, ds);
+        for (int e = 0; e < 8; ++e) {
+          const int c = jj * 8 + e;
+          const int qi = qc0 + c;
+          const bool ok = full_tile || ((qi < len) && (kv_row < len) && (!kCausal || kv_row <= qi));
+          const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]) : 0.f;
+          p[e] = pe;
+          ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) * scale : 0.f;
         }
+        store_row_chunk(smem + L::oP + st * 16384, row, half * 4 + jj, p);
+        store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(pds_full);
+      mbar_arrive(&pds_full[st]);
     }
+    const bool my_store = (D == 128) || (half == 0);
+    const int cb = (D == 128) ? half : 0, ce = (D == 128) ? half + 1 : 1;
     if (n_it > 0) {
-      mbar_wait(acc_done, (n_it - 1) & 1, 26);
+      mbar_wait(&acc_done[(n_it - 1) & 1], ((n_it - 1) >> 1) & 1, 26);
       tc_fence_after();
-      store_acc_tile<D>(tmem_dV, smem + L::oV, 1.f, &tdv, h * D, kv0, b, warp, lane);
-      store_acc_tile<D>(tmem_dK, smem + L::oK, 1.f, &tdk, h * D, kv0, b, warp, lane);
-    } else {
-      for (int c = 0; c < D / 64; ++c)
+      if (my_store) {
+        store_acc_tile<D>(tmem_dV, smem + L::oV, 1.f, &tdv, h * D, kv0, b, wq, lane, cb, ce);
+        store_acc_tile<D>(tmem_dK, smem + L::oK, 1.f, &tdk, h * D, kv0, b, wq, lane, cb, ce);
+      }
+    } else if (my_store) {
+      for (int c = cb; c < ce; ++c)
         for (int jj = 0; jj < 8; ++jj) {
           float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           store_row_chunk(smem + L::oK + c * 16384, row, jj, z);
@@ -476,9 +509,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        for (int c = 0; c < D / 64; ++c) {
-          tma_store_3d(&tdk, smem + L::oK + c * 16384 + warp * 4096, h * D + c * 64, kv0 + warp * 32, b);
-          tma_store_3d(&tdv, smem + L::oK + c * 16384 + warp * 4096, h * D + c * 64, kv0 + warp * 32, b);
+        for (int c = cb; c < ce; ++c) {
+          tma_store_3d(&tdk, smem + L::oK + c * 16384 + wq * 4096, h * D + c * 64, kv0 + wq * 32, b);
+          tma_store_3d(&tdv, smem + L::oK + c * 16384 + wq * 4096, h * D + c * 64, kv0 + wq * 32, b);
         }
         tma_store_commit();
         tma_store_wait_all<0>();
@@ -487,27 +520,27 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<1>(tmem_base, 512);
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
 // ================================================================================================ backward: dQ
-// CTA = one 128-row q tile of one (b, h); loops over 64-row kv tiles.
+// CTA = one 128-row q tile of one (b, h); loops over 64-row kv tiles.  Same 320-thread role layout as above.
 //   S = Q K_j^T    dP = dO V_j^T     (M = 128 q, N = 64 kv, K = d)       dQ += dS K_j   (M = 128 q, N = d, K = 64 kv)
 template <int D>
 struct BwdQSmem {
   static constexpr int NCH = D / 64;
   static constexpr int kQ = NCH * 16384;
   static constexpr int kKV = NCH * 8192;
-  static constexpr int oQ = 0, oDO = kQ, oK = 2 * kQ, oV = oK + 2 * kKV, oDS = oV + 2 * kKV, oBar = oDS + 16384;
+  static constexpr int oQ = 0, oDO = kQ, oK = 2 * kQ, oV = oK + 2 * kKV, oDS = oV + 2 * kKV, oBar = oDS + 2 * 16384;
   static constexpr int kBytes = oBar + 256;
 };
 
 template <int D, bool kCausal>
-__global__ void __launch_bounds__(kAttnThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                    const __grid_constant__ CUtensorMap tdq, const float* __restrict__ lse2,
-                   const float* __restrict__ delta, const int* __restrict__ seqlens, int S, int nh, float scale,
+                   const float* __restrict__ delta, const int* __restrict__ seqlens, int S, int S_pad, int nh, float scale,
                    float scale_log2) {
   using L = BwdQSmem<D>;
   constexpr int NCH = L::NCH;
@@ -517,9 +550,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   uint64_t* kv_full = bars + 1;   // [2]
   uint64_t* kv_empty = bars + 3;  // [2]
   uint64_t* sdp_full = bars + 5;  // [2]
-  uint64_t* ds_full = bars + 7;
-  uint64_t* acc_done = bars + 8;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* ds_full = bars + 7;   // [2]
+  uint64_t* acc_done = bars + 9;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -530,19 +563,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_bwd_dq: smem misaligned\n"); __trap(); }
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&sdp_full[i], 1); }
-    mbar_init(ds_full, 128);
-    mbar_init(acc_done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&ds_full[i], 256);
+    }
     fence_mbar_init();
   }
-  if (warp == 5) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  if (warp == 9) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
 
-  if (warp == 4 && lane == 0 && n_kv > 0) {
+  if (warp == 8 && lane == 0 && n_kv > 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
     mbar_arrive_expect_tx(q_full, 2 * 128 * D * 2);
     for (int c = 0; c < NCH; ++c) {
@@ -558,7 +592,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &kv_full[st], h * D + c * 64, j * 64, b);
       }
     }
-  } else if (warp == 5 && lane == 0 && n_kv > 0) {
+  } else if (warp == 9 && lane == 0 && n_kv > 0) {
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
     const uint32_t sQ = smem_u32(smem + L::oQ), sDO = smem_u32(smem + L::oDO), sK = smem_u32(smem + L::oK),
@@ -576,53 +610,56 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) issue_s(j + 1);
       const int st = j & 1;
-      mbar_wait(ds_full, j & 1, 33);
+      mbar_wait(&ds_full[st], (j >> 1) & 1, 33);
       tc_fence_after();
-      mma_tile(tmem_dQ, sDS, false, 0, sK + st * L::kKV, true, 8192, 4, idesc_acc, j > 0);
+      mma_tile(tmem_dQ, sDS + st * 16384, false, 0, sK + st * L::kKV, true, 8192, 4, idesc_acc, j > 0);
       umma_commit(&kv_empty[st]);
-      umma_commit(acc_done);
+      umma_commit(&acc_done[st]);
     }
-  } else if (warp < 4) {
-    const int row = warp * 32 + lane;
+  } else if (warp < 8) {
+    const int wq = warp & 3, half = warp >> 2;
+    const int row = wq * 32 + lane;
     const int q_row = q0 + row;
-    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
-    const size_t sidx = (static_cast<size_t>(b) * nh + h) * S + min(q_row, S - 1);
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const size_t sidx = (static_cast<size_t>(b) * nh + h) * S_pad + min(q_row, S_pad - 1);
     const float my_lse = lse2[sidx], my_delta = delta[sidx];
     const bool row_ok = q_row < len;
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
+      const int kc0 = j * 64 + half * 32;
       mbar_wait(&sdp_full[st], (j >> 1) & 1, 34);
       tc_fence_after();
-      if (j > 0) mbar_wait(acc_done, (j - 1) & 1, 35);
-#pragma unroll 1
-      for (int half = 0; half < 2; ++half) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_S + lane_off + st * 64 + half * 32, sv);
-        tmem_ld32(tmem_dP + lane_off + st * 64 + half * 32, dv);
-        tmem_ld_wait();
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tmem_S + lane_off + st * 64 + half * 32, sv);
+      tmem_ld32(tmem_dP + lane_off + st * 64 + half * 32, dv);
+      tmem_ld_wait();
+      if (j >= 2) mbar_wait(&acc_done[st], ((j >> 1) & 1) ^ 1, 35);
+      const bool full_tile = (q0 + 127 < len) && (kc0 + 31 < len) && (!kCausal || kc0 + 31 <= q0);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float ds[8];
+      for (int jj = 0; jj < 4; ++jj) {
+        float ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int kvi = j * 64 + half * 32 + jj * 8 + e;
-            const bool ok = row_ok && (kvi < len) && (!kCausal || kvi <= q_row);
-            const float pe = ok ? exp2f(__uint_as_float(sv[jj * 8 + e]) * scale_log2 - my_lse) : 0.f;
-            ds[e] = pe * (__uint_as_float(dv[jj * 8 + e]) - my_delta) * scale;
-          }
-          store_row_chunk(smem + L::oDS, row, half * 4 + jj, ds);
+        for (int e = 0; e < 8; ++e) {
+          const int c = jj * 8 + e;
+          const int kvi = kc0 + c;
+          const bool ok = full_tile || (row_ok && (kvi < len) && (!kCausal || kvi <= q_row));
+          const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse) : 0.f;
+          ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) * scale : 0.f;
         }
+        store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(ds_full);
+      mbar_arrive(&ds_full[st]);
     }
+    const bool my_store = (D == 128) || (half == 0);
+    const int cb = (D == 128) ? half : 0, ce = (D == 128) ? half + 1 : 1;
     if (n_kv > 0) {
-      mbar_wait(acc_done, (n_kv - 1) & 1, 36);
+      mbar_wait(&acc_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1, 36);
       tc_fence_after();
-      store_acc_tile<D>(tmem_dQ, smem + L::oQ, 1.f, &tdq, h * D, q0, b, warp, lane);
-    } else {
-      for (int c = 0; c < D / 64; ++c)
+      if (my_store) store_acc_tile<D>(tmem_dQ, smem + L::oQ, 1.f, &tdq, h * D, q0, b, wq, lane, cb, ce);
+    } else if (my_store) {
+      for (int c = cb; c < ce; ++c)
         for (int jj = 0; jj < 8; ++jj) {
           float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
           store_row_chunk(smem + L::oQ + c * 16384, row, jj, z);
@@ -630,7 +667,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) {
-        for (int c = 0; c < D / 64; ++c) tma_store_3d(&tdq, smem + L::oQ + c * 16384 + warp * 4096, h * D + c * 64, q0 + warp * 32, b);
+        for (int c = cb; c < ce; ++c) tma_store_3d(&tdq, smem + L::oQ + c * 16384 + wq * 4096, h * D + c * 64, q0 + wq * 32, b);
         tma_store_commit();
         tma_store_wait_all<0>();
       }
@@ -638,7 +675,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 5) tmem_dealloc<1>(tmem_base, 512);
+  if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
 // ================================================================================================ host
@@ -679,7 +716,8 @@ int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
                 : launch_fwd<64, false>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st);
 }
 
-size_t attn_bwd_workspace(int B, int S, int nh, int) { return static_cast<size_t>(B) * S * nh * 2 * sizeof(float); }
+static inline int s_pad(int S) { return (S + 63) / 64 * 64; }
+size_t attn_bwd_workspace(int B, int S, int nh, int) { return static_cast<size_t>(B) * s_pad(S) * nh * 2 * sizeof(float); }
 
 template <int D, bool C>
 static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const CUtensorMap& tk64, const CUtensorMap& tk128,
@@ -694,14 +732,15 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
     if (set_smem(k1, BwdKVSmem<D>::kBytes) || set_smem(k2, BwdQSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
     once = true;
   }
-  const long warps = static_cast<long>(B) * S * nh;
+  const int Sp = s_pad(S);
+  const long warps = static_cast<long>(B) * Sp * nh;
   attn_bwd_prep_kernel<D><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(dout, out, lse, delta, lse2, B, S,
-                                                                                           nh, ld_o);
+                                                                                           Sp, nh, ld_o);
   dim3 grid((S + 127) / 128, nh, B);
-  k1<<<grid, kAttnThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, nh, scale,
-                                                        scale * kLog2e);
-  k2<<<grid, kAttnThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, nh, scale,
+  k1<<<grid, kBwdThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Sp, nh, scale,
                                                        scale * kLog2e);
+  k2<<<grid, kBwdThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, Sp, nh, scale,
+                                                      scale * kLog2e);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
@@ -712,7 +751,7 @@ int attn_bwd(const void* dout, const void* q, const void* k, const void* v, cons
   if (d != 128 && d != 64) return DLLM_ERR_UNSUPPORTED;
   if (workspace_bytes < attn_bwd_workspace(B, S, nh, d)) return DLLM_ERR_SHAPE;
   float* delta = static_cast<float*>(workspace);
-  float* lse2 = delta + static_cast<size_t>(B) * S * nh;
+  float* lse2 = delta + static_cast<size_t>(B) * s_pad(S) * nh;
   CUtensorMap tq64, tq128, tk64, tk128, tv64, tv128, tdo64, tdo128, tdq, tdk, tdv;
   int rc;
   const int C = nh * d;

@@ -113,4 +113,35 @@ int dllm_attn_bwd(const void* dout, const void* q, const void* k, const void* v,
                   ld_dqkv, causal, scale, S(stream));
 }
 
+int dllm_gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
+                      int b_mn, int out_fp32, int cta_pair, const void* bias, const void* residual, long ldr, int act,
+                      void* stream) {
+  ensure_context(A);
+  return gemm_bf16_ex(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_fp32, cta_pair, bias, residual, ldr, act, S(stream));
+}
+int dllm_layernorm_fwd(const void* x, const void* weight, const void* bias, void* y, int T, int H, float eps, void* stream) {
+  ensure_context(x);
+  return layernorm_fwd(x, weight, bias, y, T, H, eps, S(stream));
+}
+int dllm_clip_patchify(const void* images, void* out, int N, int R, int patch, int Kpad, void* stream) {
+  ensure_context(images);
+  return clip_patchify(images, out, N, R, patch, Kpad, S(stream));
+}
+int dllm_clip_assemble(const void* patches, const void* cls, const void* pos, void* out, int N, int P, int C, void* stream) {
+  ensure_context(patches);
+  return clip_assemble(patches, cls, pos, out, N, P, C, S(stream));
+}
+int dllm_copy_rows(void* dst, const int* dst_idx, const void* src, const int* src_idx, int R, int H, int mode, void* stream) {
+  ensure_context(dst);
+  return copy_rows(dst, dst_idx, src, src_idx, R, H, mode, S(stream));
+}
+int dllm_segment_sum_rows(void* dst, const void* src, const int* seg, const int* rows, int Q, int H, void* stream) {
+  ensure_context(dst);
+  return segment_sum_rows(dst, src, seg, rows, Q, H, S(stream));
+}
+int dllm_zero_rows(void* dst, const int* idx, int R, int H, void* stream) {
+  ensure_context(dst);
+  return zero_rows(dst, idx, R, H, S(stream));
+}
+
 }  // extern "C"

@@ -90,71 +90,91 @@ __global__ void __launch_bounds__(kNormThreads) rmsnorm_fwd_kernel(const bf16* _
   }
 }
 
-// backward: g = bf16(dy*w); dx = rstd*(g - xhat*mean(g*xhat)) (+ dres); dw += dy * bf16(xhat)
-// Each CTA walks rows blockIdx.x, +gridDim.x, ... and keeps its dw partial in registers; partials [grid, H] fp32.
-__global__ void __launch_bounds__(kNormThreads) rmsnorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                                   const bf16* __restrict__ w, const float* __restrict__ rstd,
-                                                                   const bf16* __restrict__ dres, bf16* __restrict__ dx,
-                                                                   float* __restrict__ dw_partial, int T, int H) {
+// backward, two kernels (the first fused version kept dw partials in registers: 161 regs, 12 % occupancy, 18 % of DRAM
+// peak in ncu — profiles/r01_ncu_full_summary.csv):
+//   dx kernel : one CTA per row.  g = bf16(dy*w); dx = rstd*(g - xhat*mean(g*xhat)) (+ dres)
+//   dw kernel : 2-D grid (256-column blocks x row splits); dw_partial[split, h] = sum_rows dy * bf16(x*rstd)
+__global__ void __launch_bounds__(kNormThreads) rmsnorm_bwd_dx_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                      const bf16* __restrict__ w, const float* __restrict__ rstd,
+                                                                      const bf16* __restrict__ dres, bf16* __restrict__ dx, int H) {
   __shared__ float red[kNormThreads / 32];
+  const int row = blockIdx.x;
   const int nvec = H >> 3;
-  float dwacc[kNormMaxV][8];
-  float wf[kNormMaxV][8];
+  const size_t off = static_cast<size_t>(row) * H;
+  const float rs = rstd[row];
+  float g[kNormMaxV][8], xh[kNormMaxV][8];
+  float dot = 0.f;
 #pragma unroll
   for (int i = 0; i < kNormMaxV; ++i) {
     const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      float d[8], xx[8], wf[8];
+      unpack8(reinterpret_cast<const Vec8*>(dy + off)[v], d);
+      unpack8(reinterpret_cast<const Vec8*>(x + off)[v], xx);
+      unpack8(reinterpret_cast<const Vec8*>(w)[v], wf);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) dwacc[i][j] = 0.f;
-    if (v < nvec) unpack8(reinterpret_cast<const Vec8*>(w)[v], wf[i]);
-  }
-  for (int row = blockIdx.x; row < T; row += gridDim.x) {
-    const size_t off = static_cast<size_t>(row) * H;
-    const float rs = rstd[row];
-    float g[kNormMaxV][8], xh[kNormMaxV][8];
-    float dot = 0.f;
-#pragma unroll
-    for (int i = 0; i < kNormMaxV; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
-      if (v < nvec) {
-        float d[8], xx[8];
-        unpack8(reinterpret_cast<const Vec8*>(dy + off)[v], d);
-        unpack8(reinterpret_cast<const Vec8*>(x + off)[v], xx);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh[i][j] = xx[j] * rs;
-          g[i][j] = bf16r(d[j] * wf[i][j]);
-          dot += g[i][j] * xh[i][j];
-          dwacc[i][j] += d[j] * bf16r(xh[i][j]);
-        }
-      }
-    }
-    dot = block_sum<kNormThreads>(dot, red) / static_cast<float>(H);
-#pragma unroll
-    for (int i = 0; i < kNormMaxV; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
-      if (v < nvec) {
-        float o[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - xh[i][j] * dot);
-        if (dres) {
-          float r[8];
-          unpack8(reinterpret_cast<const Vec8*>(dres + off)[v], r);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += r[j];
-        }
-        reinterpret_cast<Vec8*>(dx + off)[v] = pack8(o);
+      for (int j = 0; j < 8; ++j) {
+        xh[i][j] = xx[j] * rs;
+        g[i][j] = bf16r(d[j] * wf[j]);
+        dot += g[i][j] * xh[i][j];
       }
     }
   }
-  if (dw_partial) {
+  dot = block_sum<kNormThreads>(dot, red) / static_cast<float>(H);
 #pragma unroll
-    for (int i = 0; i < kNormMaxV; ++i) {
-      const int v = threadIdx.x + i * kNormThreads;
-      if (v < nvec) {
-        float4* p = reinterpret_cast<float4*>(dw_partial + static_cast<size_t>(blockIdx.x) * H + v * 8);
-        p[0] = make_float4(dwacc[i][0], dwacc[i][1], dwacc[i][2], dwacc[i][3]);
-        p[1] = make_float4(dwacc[i][4], dwacc[i][5], dwacc[i][6], dwacc[i][7]);
+  for (int i = 0; i < kNormMaxV; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - xh[i][j] * dot);
+      if (dres) {
+        float r[8];
+        unpack8(reinterpret_cast<const Vec8*>(dres + off)[v], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
       }
+      reinterpret_cast<Vec8*>(dx + off)[v] = pack8(o);
+    }
+  }
+}
+
+constexpr int kDwSplits = 64;
+__global__ void __launch_bounds__(256) rmsnorm_bwd_dw_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                             const float* __restrict__ rstd, float* __restrict__ dw_partial,
+                                                             int T, int H) {
+  __shared__ float sm[8][32][9];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int v = blockIdx.x * 32 + tx;  // 8-column vector index
+  const int nvec = H >> 3;
+  const int rows_per = (T + kDwSplits - 1) / kDwSplits;
+  const int r0 = blockIdx.y * rows_per;
+  const int r1 = min(T, r0 + rows_per);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (v < nvec) {
+#pragma unroll 4
+    for (int r = r0 + ty; r < r1; r += 8) {
+      const size_t off = static_cast<size_t>(r) * H;
+      float d[8], xx[8];
+      unpack8(reinterpret_cast<const Vec8*>(dy + off)[v], d);
+      unpack8(reinterpret_cast<const Vec8*>(x + off)[v], xx);
+      const float rs = __ldg(rstd + r);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += d[j] * bf16r(xx[j] * rs);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm[ty][tx][j] = acc[j];
+  __syncthreads();
+  if (ty == 0 && v < nvec) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s += sm[y][tx][j];
+      dw_partial[static_cast<size_t>(blockIdx.y) * H + v * 8 + j] = s;
     }
   }
 }
@@ -178,21 +198,19 @@ int rmsnorm_fwd(const void* x, const void* add, const void* w, void* x_out, void
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
-size_t rmsnorm_bwd_workspace(int T, int H) {
-  int grid = num_sms() * 4;
-  if (grid > T) grid = T;
-  return static_cast<size_t>(grid) * H * sizeof(float);
-}
+size_t rmsnorm_bwd_workspace(int T, int H) { return static_cast<size_t>(kDwSplits) * H * sizeof(float); }
 
 int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx, void* dw,
                 int dw_accumulate, void* workspace, size_t workspace_bytes, int T, int H, cudaStream_t s) {
   if (H % 8 || H > kNormThreads * kNormMaxV * 8 || T <= 0) return DLLM_ERR_SHAPE;
-  int grid = num_sms() * 4;
-  if (grid > T) grid = T;
-  if (dw && workspace_bytes < static_cast<size_t>(grid) * H * sizeof(float)) return DLLM_ERR_SHAPE;
-  rmsnorm_bwd_kernel<<<grid, kNormThreads, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd,
-                                                   (const bf16*)dres, (bf16*)dx, dw ? (float*)workspace : nullptr, T, H);
-  if (dw) colsum_partials_kernel<<<(H + 255) / 256, 256, 0, s>>>((const float*)workspace, (bf16*)dw, grid, H, dw_accumulate);
+  if (dw && workspace_bytes < rmsnorm_bwd_workspace(T, H)) return DLLM_ERR_SHAPE;
+  rmsnorm_bwd_dx_kernel<<<T, kNormThreads, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (const bf16*)dres,
+                                                   (bf16*)dx, H);
+  if (dw) {
+    dim3 grid((H / 8 + 31) / 32, kDwSplits);
+    rmsnorm_bwd_dw_kernel<<<grid, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, rstd, (float*)workspace, T, H);
+    colsum_partials_kernel<<<(H + 255) / 256, 256, 0, s>>>((const float*)workspace, (bf16*)dw, kDwSplits, H, dw_accumulate);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
@@ -484,6 +502,188 @@ int embedding_bwd(const long long* sorted_ids, const long long* order, const voi
                   int accumulate, cudaStream_t s) {
   if (H % 8 || T <= 0) return DLLM_ERR_SHAPE;
   embedding_bwd_kernel<<<T, 128, 0, s>>>(sorted_ids, order, (const bf16*)dy, (bf16*)dW, T, H, accumulate);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+
+// ------------------------------------------------------------------------------------------------ LayerNorm (fwd)
+// CLIP ViT / UNet transformer blocks (transformers CLIPEncoderLayer.layer_norm1/2, pre_layrnorm; diffusers
+// BasicTransformerBlock.norm1-3): y = (x - mean) * rsqrt(var + eps) * w + b, fp32 statistics, one rounding to bf16.
+// Frozen towers on this path (modeling_plugins.py:235-236 freeze CLIP; UNet frozen) -> forward only.
+__global__ void __launch_bounds__(kNormThreads) layernorm_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                     const bf16* __restrict__ b, bf16* __restrict__ y, int H,
+                                                                     float eps) {
+  __shared__ float red[kNormThreads / 32];
+  const int row = blockIdx.x;
+  const int nvec = H >> 3;
+  const Vec8* xr = reinterpret_cast<const Vec8*>(x + static_cast<size_t>(row) * H);
+  float xv[kNormMaxV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNormMaxV; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      unpack8(xr[v], xv[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += xv[i][j];
+    }
+  }
+  const float mean = block_sum<kNormThreads>(sum, red) / static_cast<float>(H);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < kNormMaxV; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = xv[i][j] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(block_sum<kNormThreads>(sq, red) / static_cast<float>(H) + eps);
+  Vec8* yr = reinterpret_cast<Vec8*>(y + static_cast<size_t>(row) * H);
+#pragma unroll
+  for (int i = 0; i < kNormMaxV; ++i) {
+    const int v = threadIdx.x + i * kNormThreads;
+    if (v < nvec) {
+      float wf[8], bf[8], o[8];
+      unpack8(reinterpret_cast<const Vec8*>(w)[v], wf);
+      unpack8(reinterpret_cast<const Vec8*>(b)[v], bf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (xv[i][j] - mean) * rstd * wf[j] + bf[j];
+      yr[v] = pack8(o);
+    }
+  }
+}
+int layernorm_fwd(const void* x, const void* w, const void* b, void* y, int T, int H, float eps, cudaStream_t s) {
+  if (H % 8 || H > kNormThreads * kNormMaxV * 8 || T <= 0) return DLLM_ERR_SHAPE;
+  layernorm_fwd_kernel<<<T, kNormThreads, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------------ CLIP patch embedding
+// transformers CLIPVisionEmbeddings: Conv2d(3, C, k=s=patch, bias=False) == GEMM over unfolded patches.
+// patchify: images [N,3,R,R] (NCHW bf16) -> rows [N*G*G, Kpad], k = (c*patch + ky)*patch + kx (the conv weight's
+// flatten order), zero-padded to Kpad (multiple of 8 so the row stride is 16-byte aligned for TMA).
+__global__ void patchify_kernel(const bf16* __restrict__ img, bf16* __restrict__ out, int N, int R, int patch, int G,
+                                int Kpad) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(N) * G * G * Kpad;
+  if (gid >= total) return;
+  const int k = static_cast<int>(gid % Kpad);
+  const long pr = gid / Kpad;
+  const int gx = static_cast<int>(pr % G);
+  const int gy = static_cast<int>((pr / G) % G);
+  const int n = static_cast<int>(pr / (static_cast<long>(G) * G));
+  bf16 v = __float2bfloat16_rn(0.f);
+  if (k < 3 * patch * patch) {
+    const int kx = k % patch, ky = (k / patch) % patch, c = k / (patch * patch);
+    v = img[((static_cast<size_t>(n) * 3 + c) * R + gy * patch + ky) * R + gx * patch + kx];
+  }
+  out[gid] = v;
+}
+// x[n, 0] = cls + pos[0];  x[n, 1+p] = patch[n, p] + pos[1+p]   (bf16 adds as torch.cat + position_embedding)
+__global__ void clip_assemble_kernel(const bf16* __restrict__ patches, const bf16* __restrict__ cls,
+                                     const bf16* __restrict__ pos, bf16* __restrict__ out, int N, int P, int C) {
+  const int nvec = C >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(N) * (P + 1) * nvec;
+  if (gid >= total) return;
+  const int v = static_cast<int>(gid % nvec);
+  const long tr = gid / nvec;
+  const int t = static_cast<int>(tr % (P + 1));
+  const long n = tr / (P + 1);
+  float a[8], b[8];
+  if (t == 0) unpack8(reinterpret_cast<const Vec8*>(cls)[v], a);
+  else unpack8(reinterpret_cast<const Vec8*>(patches + (n * P + (t - 1)) * C)[v], a);
+  unpack8(reinterpret_cast<const Vec8*>(pos + static_cast<size_t>(t) * C)[v], b);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] += b[j];
+  reinterpret_cast<Vec8*>(out + tr * C)[v] = pack8(a);
+}
+int clip_patchify(const void* img, void* out, int N, int R, int patch, int Kpad, cudaStream_t s) {
+  if (N <= 0 || R % patch || Kpad % 8 || Kpad < 3 * patch * patch) return DLLM_ERR_SHAPE;
+  const int G = R / patch;
+  const long total = static_cast<long>(N) * G * G * Kpad;
+  patchify_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)img, (bf16*)out, N, R, patch, G, Kpad);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int clip_assemble(const void* patches, const void* cls, const void* pos, void* out, int N, int P, int C, cudaStream_t s) {
+  if (N <= 0 || P <= 0 || C % 8) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(N) * (P + 1) * (C / 8);
+  clip_assemble_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)patches, (const bf16*)cls,
+                                                                                (const bf16*)pos, (bf16*)out, N, P, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------------ row gather / scatter
+// Index paths of DreamLLMModel.forward's embedding splice (modeling_dreamllm.py:1082-1141) and the dream-query
+// conditioning gather (:1401-1418): bit-exact row copies driven by a host-built (dst_row, src_row) map.
+//   mode 0: dst[dst_idx[r]]  = src[src_idx[r]]          (splice / gather; duplicates in src_idx allowed)
+//   mode 1: dst[dst_idx[r]] += src[src_idx[r]]          (gradient of a gather with UNIQUE dst rows per launch)
+__global__ void copy_rows_kernel(bf16* __restrict__ dst, const int* __restrict__ dst_idx, const bf16* __restrict__ src,
+                                 const int* __restrict__ src_idx, int R, int H, int mode) {
+  const int nvec = H >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(R) * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  const int r = static_cast<int>(gid / nvec);
+  const Vec8 sv = reinterpret_cast<const Vec8*>(src + static_cast<size_t>(src_idx[r]) * H)[v];
+  Vec8* d = reinterpret_cast<Vec8*>(dst + static_cast<size_t>(dst_idx[r]) * H) + v;
+  if (mode == 0) {
+    *d = sv;
+  } else {
+    float a[8], b[8];
+    unpack8(*d, a);
+    unpack8(sv, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] += b[j];
+    *d = pack8(a);
+  }
+}
+// dst[q] = sum over the CSR segment [seg[q], seg[q+1]) of src[rows[i]]   (fp32 accumulate, deterministic):
+// gradient of the dream-query broadcast (every <dream_start> occurrence reads the same Q rows).
+__global__ void segment_sum_rows_kernel(bf16* __restrict__ dst, const bf16* __restrict__ src, const int* __restrict__ seg,
+                                        const int* __restrict__ rows, int H) {
+  const int q = blockIdx.x;
+  const int nvec = H >> 3;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int i = seg[q]; i < seg[q + 1]; ++i) {
+      float f[8];
+      unpack8(reinterpret_cast<const Vec8*>(src + static_cast<size_t>(rows[i]) * H)[v], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    reinterpret_cast<Vec8*>(dst + static_cast<size_t>(q) * H)[v] = pack8(acc);
+  }
+}
+__global__ void zero_rows_kernel(bf16* __restrict__ dst, const int* __restrict__ idx, int R, int H) {
+  const int nvec = H >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(R) * nvec) return;
+  Vec8 z;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) z.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+  reinterpret_cast<Vec8*>(dst + static_cast<size_t>(idx[gid / nvec]) * H)[gid % nvec] = z;
+}
+int copy_rows(void* dst, const int* dst_idx, const void* src, const int* src_idx, int R, int H, int mode, cudaStream_t s) {
+  if (H % 8 || R < 0) return DLLM_ERR_SHAPE;
+  if (R == 0) return 0;
+  const long total = static_cast<long>(R) * (H / 8);
+  copy_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((bf16*)dst, dst_idx, (const bf16*)src, src_idx, R, H, mode);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int segment_sum_rows(void* dst, const void* src, const int* seg, const int* rows, int Q, int H, cudaStream_t s) {
+  if (H % 8 || Q <= 0) return DLLM_ERR_SHAPE;
+  segment_sum_rows_kernel<<<Q, 128, 0, s>>>((bf16*)dst, (const bf16*)src, seg, rows, H);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int zero_rows(void* dst, const int* idx, int R, int H, cudaStream_t s) {
+  if (H % 8 || R < 0) return DLLM_ERR_SHAPE;
+  if (R == 0) return 0;
+  const long total = static_cast<long>(R) * (H / 8);
+  zero_rows_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((bf16*)dst, idx, R, H);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 

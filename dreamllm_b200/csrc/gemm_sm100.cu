@@ -39,10 +39,26 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024 /*align slack*/;
 };
 
+// Fused epilogue:  out = act( bf16(acc + bias[col]) ) (+ residual[row, col])   — rounding points as the reference's
+// unfused bf16 sequence (Linear output rounded, activation rounded, residual add rounded).
+struct GemmEpi {
+  const bf16* bias;      // [N] or nullptr
+  const bf16* residual;  // [M, ldr] or nullptr
+  long ldr;
+  int act;               // 0 none, 1 quick_gelu x*sigmoid(1.702x), 2 gelu (erf), 3 silu
+};
+
+__device__ __forceinline__ float epi_act(float x, int act) {
+  if (act == 1) return x / (1.f + expf(-1.702f * x));
+  if (act == 2) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+  if (act == 3) return x / (1.f + expf(-x));
+  return x;
+}
+
 template <int kCta, bool kAMN, bool kBMN, typename OutT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m) {
+            const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi) {
   using Cfg = GemmCfg<kCta>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kOutF32 = sizeof(OutT) == 4;
@@ -212,6 +228,36 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tmem_ld32(taddr0 + c * CH, v);
         if constexpr (!kOutF32) tmem_ld32(taddr0 + c * CH + 32, v + 32);
         tmem_ld_wait();
+        if (epi.bias != nullptr || epi.act != 0 || epi.residual != nullptr) {
+          const int gcol = col0 + c * CH;
+          const int grow = row0 + lane;
+#pragma unroll
+          for (int j = 0; j < CH / 8; ++j) {
+            const int cj = gcol + j * 8;
+            float bsv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            float rsv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            const bool col_ok = cj + 8 <= N;
+            if (epi.bias != nullptr && col_ok) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(epi.bias + cj));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); bsv[2 * e] = f.x; bsv[2 * e + 1] = f.y; }
+            }
+            if (epi.residual != nullptr && col_ok && grow < M) {
+              const uint4 q = *reinterpret_cast<const uint4*>(epi.residual + static_cast<size_t>(grow) * epi.ldr + cj);
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); rsv[2 * e] = f.x; rsv[2 * e + 1] = f.y; }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              float x = __uint_as_float(v[j * 8 + e]) + bsv[e];
+              if (epi.act != 0) x = epi_act(__bfloat162float(__float2bfloat16_rn(x)), epi.act);
+              if (epi.residual != nullptr) x = __bfloat162float(__float2bfloat16_rn(x)) + rsv[e];
+              v[j * 8 + e] = __float_as_uint(x);
+            }
+          }
+        }
         // the staging buffer we are about to overwrite was handed to TMA two stores ago
         if (lane == 0) tma_store_wait_read<1>();
         __syncwarp();
@@ -301,7 +347,7 @@ int num_sms() {
 
 template <int kCta, bool kAMN, bool kBMN, typename OutT>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
-                       cudaStream_t stream) {
+                       const GemmEpi& epi, cudaStream_t stream) {
   using Cfg = GemmCfg<kCta>;
   auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT>;
   static bool attr_set = false;
@@ -327,13 +373,23 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi);
   return e == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
               int b_mn, int out_fp32, int cta_pair, cudaStream_t stream) {
-  if (M <= 0 || N <= 0 || K <= 0) return DLLM_ERR_SHAPE;
+  return gemm_bf16_ex(A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, out_fp32, cta_pair, nullptr, nullptr, 0, 0, stream);
+}
+
+int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
+                 int b_mn, int out_fp32, int cta_pair, const void* bias, const void* residual, long ldr, int act,
+                 cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || act < 0 || act > 3) return DLLM_ERR_SHAPE;
+  if ((bias || residual) && (N % 8)) return DLLM_ERR_SHAPE;
+  if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || ((ldr * 2) & 15))) return DLLM_ERR_ALIGN;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return DLLM_ERR_ALIGN;
+  GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), ldr, act};
   const int kcta = (cta_pair < 0) ? (M > BM ? 2 : 1) : (cta_pair ? 2 : 1);
   CUtensorMap ta, tb, tc;
   int rc;
@@ -351,8 +407,8 @@ int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long l
 
 #define DLLM_GEMM_CASE(CTA, AMN, BMN)                                                                 \
   if (kcta == CTA && (a_mn != 0) == AMN && (b_mn != 0) == BMN) {                                      \
-    return out_fp32 ? launch_gemm<CTA, AMN, BMN, float>(ta, tb, tc, M, N, K, stream)                  \
-                    : launch_gemm<CTA, AMN, BMN, bf16>(ta, tb, tc, M, N, K, stream);                  \
+    return out_fp32 ? launch_gemm<CTA, AMN, BMN, float>(ta, tb, tc, M, N, K, epi, stream)             \
+                    : launch_gemm<CTA, AMN, BMN, bf16>(ta, tb, tc, M, N, K, epi, stream);             \
   }
   DLLM_GEMM_CASE(1, false, false)
   DLLM_GEMM_CASE(1, false, true)

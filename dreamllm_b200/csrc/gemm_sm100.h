@@ -22,4 +22,9 @@ int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t row
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
               int b_mn, int out_fp32, int cta_pair, cudaStream_t stream);
 
+// same, with the fused epilogue out = act(bf16(acc + bias)) (+ residual); act: 0 none, 1 quick_gelu, 2 gelu(erf), 3 silu
+int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
+                 int b_mn, int out_fp32, int cta_pair, const void* bias, const void* residual, long ldr, int act,
+                 cudaStream_t stream);
+
 }  // namespace dllm

@@ -19,6 +19,12 @@ int cross_entropy(void* logits, const long long* labels, float* loss, float dlos
 int embedding_fwd(const long long* ids, const void* W, void* out, int T, int H, cudaStream_t s);
 int embedding_bwd(const long long* sorted_ids, const long long* order, const void* dy, void* dW, int T, int H,
                   int accumulate, cudaStream_t s);
+int layernorm_fwd(const void* x, const void* w, const void* b, void* y, int T, int H, float eps, cudaStream_t s);
+int clip_patchify(const void* img, void* out, int N, int R, int patch, int Kpad, cudaStream_t s);
+int clip_assemble(const void* patches, const void* cls, const void* pos, void* out, int N, int P, int C, cudaStream_t s);
+int copy_rows(void* dst, const int* dst_idx, const void* src, const int* src_idx, int R, int H, int mode, cudaStream_t s);
+int segment_sum_rows(void* dst, const void* src, const int* seg, const int* rows, int Q, int H, cudaStream_t s);
+int zero_rows(void* dst, const int* idx, int R, int H, cudaStream_t s);
 int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int nh,
              int d, long ld_qkv, long ld_o, int causal, float scale, cudaStream_t s);
 size_t attn_bwd_workspace(int B, int S, int nh, int d);

@@ -160,10 +160,11 @@ def _fuse_rows(params):
                 ok = False
                 break
             ptr += p.numel() * esz
-    K = p0.shape[1]
+    one_d = p0.dim() == 1
+    K = 1 if one_d else p0.shape[1]
     rows = sum(p.shape[0] for p in params)
     if not ok:
-        fused = torch.empty((rows, K), dtype=p0.dtype, device=p0.device)
+        fused = torch.empty((rows,) if one_d else (rows, K), dtype=p0.dtype, device=p0.device)
         r = 0
         with torch.no_grad():
             for p in params:
@@ -172,6 +173,8 @@ def _fuse_rows(params):
                 r += p.shape[0]
         return fused
     off = p0.storage_offset()
+    if one_d:
+        return torch.as_strided(p0.data, (rows,), (1,), off)
     return torch.as_strided(p0.data, (rows, K), (K, 1), off)
 
 
@@ -510,7 +513,51 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
             all_hidden += (hidden_states,)
         return BaseModelOutputWithPast(last_hidden_state=hidden_states, hidden_states=all_hidden)
 
-    forward = _forward
+    # ---- plugins (reference :822-831 `init_plugin_modules` instantiates them from config; here they are attached) ----
+    def attach_plugins(self, clip_vision_embedding=None, dream_embedding=None, image_start_id=None, dream_start_id=None):
+        """Attribute names are the reference's hard-wired ones (:1083, :1093, :1102)."""
+        if clip_vision_embedding is not None:
+            self.clip_vision_embedding = clip_vision_embedding
+        if dream_embedding is not None:
+            self.dream_embedding = dream_embedding
+        st = getattr(self.config, "special_tokens2ids_dict", None)
+        if st is not None:
+            image_start_id = st["additional_special_tokens"]["<im_start>"] if image_start_id is None else image_start_id
+            dream_start_id = st["additional_special_tokens"]["<dream_start>"] if dream_start_id is None else dream_start_id
+        self.image_start_id, self.dream_start_id = image_start_id, dream_start_id
+
+    def forward(self, input_ids=None, images=None, images_dm=None, attention_mask=None, position_ids=None,
+                past_key_values=None, inputs_embeds=None, use_cache=None, output_attentions=None, output_hidden_states=None,
+                return_dict=None, attention_mask_has_padding=None, input_ids_cpu=None, splice_plan=None):
+        """reference :1045-1158: embed_tokens -> dream-query splice -> CLIP features -> image splice -> `_forward`.
+        `input_ids_cpu` (the collator's host copy) lets the index maps be built without a device->host sync;
+        `splice_plan` lets the caller pass prebuilt maps."""
+        need_splice = (images is not None) or (images_dm is not None)
+        if not need_splice:
+            return self._forward(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
+                                 inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states,
+                                 attention_mask_has_padding=attention_mask_has_padding)
+        from .modeling_plugins import build_splice_plan, splice_embeddings
+        if input_ids is None:
+            raise ValueError("image / dream splicing needs input_ids")
+        if inputs_embeds is None:
+            inputs_embeds = _EmbeddingFn.apply(input_ids, self.embed_tokens.weight)
+        image_features = self.clip_vision_embedding(images) if images is not None else None
+        dq = self.dream_embedding.dream_queries if images_dm is not None else None
+        if splice_plan is None:
+            ids_cpu = input_ids_cpu if input_ids_cpu is not None else input_ids.cpu()
+            P = self.clip_vision_embedding.embed_len if images is not None else 0
+            Q = self.dream_embedding.embed_len if images_dm is not None else 0
+            splice_plan = build_splice_plan(ids_cpu, self.image_start_id if images is not None else -1,
+                                            self.dream_start_id if images_dm is not None else -1, P, Q,
+                                            0 if images is None else images.shape[0],
+                                            None if images_dm is None else images_dm.shape[0], inputs_embeds.device)
+        self._last_splice_plan = splice_plan
+        if image_features is not None:
+            image_features = image_features.to(inputs_embeds.dtype)
+        inputs_embeds = splice_embeddings(inputs_embeds, image_features, dq, splice_plan)
+        return self._forward(attention_mask=attention_mask, position_ids=position_ids, inputs_embeds=inputs_embeds,
+                             output_hidden_states=output_hidden_states, attention_mask_has_padding=attention_mask_has_padding)
 
 
 class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
@@ -544,13 +591,17 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
     def get_decoder(self):
         return self.model
 
-    def forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
-                labels=None, use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
-                attention_mask_has_padding=None, **kwargs):
-        """Text / inputs_embeds path of reference :1353-1509 (images / images_dm are handled by modeling_plugins)."""
-        out = self.model(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
-                         inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states,
-                         attention_mask_has_padding=attention_mask_has_padding)
+    def forward(self, input_ids=None, images=None, images_dm=None, attention_mask=None, position_ids=None,
+                past_key_values=None, inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
+                output_hidden_states=None, return_dict=None, attention_mask_has_padding=None, input_ids_cpu=None,
+                splice_plan=None, **kwargs):
+        """reference :1353-1509.  Comprehension path (images -> CLIP -> splice -> LM loss) is complete; the creation
+        path returns the gathered dream-query conditioning in `additional_log_info["dream_conditioning"]` — the
+        StableDiffusionHead (UNet) that consumes it (:1441) is the next §8 row."""
+        out = self.model(input_ids=input_ids, images=images, images_dm=images_dm, attention_mask=attention_mask,
+                         position_ids=position_ids, inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states,
+                         attention_mask_has_padding=attention_mask_has_padding, input_ids_cpu=input_ids_cpu,
+                         splice_plan=splice_plan)
         hidden = out.last_hidden_state
         B, S, H = hidden.shape
         h2 = hidden.reshape(B * S, H)
@@ -564,5 +615,10 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
             loss = lm_loss * self.loss_weight_lm
         else:
             logits = ops.linear(h2, self.lm_head.weight).view(B, S, -1).float()
-        return CausalLMOutputWithPast(loss=loss, logits=logits, hidden_states=out.hidden_states,
-                                      additional_log_info={"lm_loss": lm_loss})
+        info = {"lm_loss": lm_loss}
+        if images_dm is not None:
+            from .modeling_plugins import gather_rows
+            plan = self.model._last_splice_plan
+            Q = self.model.dream_embedding.embed_len
+            info["dream_conditioning"] = gather_rows(hidden, plan.cond_rows).view(plan.n_dreams, Q, H)   # (:1401-1418)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, hidden_states=out.hidden_states, additional_log_info=info)

@@ -1,0 +1,372 @@
+"""B200-native mirror of `omni/models/dreamllm/modeling_plugins.py` (plugin ABCs :32-112, DreamEmbedding :116-181,
+CLIPVisionEmbedding :184-331) plus the index plumbing of the embedding splice / conditioning gather
+(modeling_dreamllm.py:1082-1141, :1401-1418).
+
+Plugin contract kept: `plugin_type`, `processor`, `config`, `embed_len`, `embed_dim`, `save_model(dir)`, `load_model(dir)`,
+`forward`, `fsdp_ignored_modules()`; attribute names `clip_vision_model`, `projector`, `dream_queries`; save files
+`clip_vision_embedding.bin`, `dream_embedding.bin`.  `StableDiffusionHead` (UNet/VAE) is the next row.
+"""
+from __future__ import annotations
+
+import os
+from abc import ABC, abstractmethod
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+
+from . import ops
+from .clip_vision import CLIPVisionConfigLite, CLIPVisionModel
+from .projector import build_projector
+
+BF16 = torch.bfloat16
+
+
+class PluginBase(ABC, nn.Module):
+    initializer_range: float = 0.02
+    plugin_type: str | None = None
+
+    def _init_weights(self, module):
+        std = self.initializer_range
+        if isinstance(module, nn.Linear):
+            module.weight.data.normal_(mean=0.0, std=std)
+            if module.bias is not None:
+                module.bias.data.zero_()
+        elif isinstance(module, nn.Embedding):
+            module.weight.data.normal_(mean=0.0, std=std)
+        elif isinstance(module, nn.Parameter):
+            module.data.normal_(mean=0.0, std=std)
+        elif isinstance(module, nn.Module):
+            for m in module.modules():
+                if isinstance(m, nn.Linear):
+                    self._init_weights(m)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    def fsdp_ignored_modules(self) -> list:
+        return []
+
+    @property
+    @abstractmethod
+    def processor(self):
+        pass
+
+    @property
+    @abstractmethod
+    def config(self):
+        pass
+
+    @abstractmethod
+    def save_model(self, output_dir: str):
+        pass
+
+    @abstractmethod
+    def load_model(self, output_dir: str):
+        pass
+
+    @abstractmethod
+    def forward(self):
+        pass
+
+
+class MultimodalEmbedding(PluginBase):
+    plugin_type = "embedding"
+
+    @property
+    @abstractmethod
+    def embed_len(self):
+        pass
+
+    @property
+    @abstractmethod
+    def embed_dim(self):
+        pass
+
+
+class MultimodalHead(PluginBase):
+    plugin_type = "head"
+
+    @abstractmethod
+    @torch.no_grad()
+    def pipeline(self):
+        pass
+
+
+class DreamEmbedding(MultimodalEmbedding):
+    def __init__(self, pretrained_model_name_or_path: str | None = None, num_dream_queries: int = 64,
+                 embed_hidden_size: int = 4096, freeze_dream_queries: bool = False):
+        super().__init__()
+        self.save_model_name = "dream_embedding"
+        self.pretrained_model_name_or_path = pretrained_model_name_or_path
+        self.num_dream_queries = num_dream_queries
+        self.embed_hidden_size = embed_hidden_size
+        self.freeze_dream_queries = freeze_dream_queries
+        self.dream_queries = nn.Parameter(torch.zeros(1, num_dream_queries, embed_hidden_size))
+        self._init_weights(self.dream_queries)
+        if pretrained_model_name_or_path is not None:
+            self.load_model(pretrained_model_name_or_path)
+        self.dream_queries.requires_grad_(not freeze_dream_queries)
+
+    def fsdp_ignored_modules(self) -> list:
+        return [self] if self.freeze_dream_queries else []
+
+    @property
+    def processor(self):
+        return None
+
+    @property
+    def embed_len(self):
+        return self.num_dream_queries
+
+    @property
+    def embed_dim(self):
+        return self.embed_hidden_size
+
+    @property
+    def config(self):
+        return dict(pretrained_model_name_or_path=self.pretrained_model_name_or_path, num_dream_queries=self.num_dream_queries,
+                    embed_len=self.embed_len, embed_dim=self.embed_dim, freeze_dream_queries=self.freeze_dream_queries)
+
+    def save_model(self, output_dir: str):
+        torch.save(self.state_dict(), os.path.join(output_dir, f"{self.save_model_name}.bin"))
+
+    def load_model(self, output_dir: str):
+        f = os.path.join(output_dir, f"{self.save_model_name}.bin")
+        if os.path.isfile(f):
+            self.load_state_dict(torch.load(f, map_location="cpu"))
+
+    def forward(self, batch_size: int = 1):
+        return self.dream_queries.repeat(batch_size, 1, 1)
+
+
+class CLIPVisionEmbedding(MultimodalEmbedding):
+    """`clip_vision_model_name_or_path` may be a checkpoint directory (weights are read through transformers and loaded
+    into the native tower — identical state-dict keys) or a dict / CLIPVisionConfig with the architecture for random init
+    (no checkpoints exist in the build sandbox)."""
+
+    def __init__(self, clip_vision_model_name_or_path, projector_type: str = "linear", projector_depth: int = 1,
+                 projector_name_or_path: str = None, pretrained_model_name_or_path: str | None = None,
+                 use_additional_post_layernorm: bool = False, select_layer: int = -2, embed_hidden_size: int = 4096,
+                 freeze_clip_vision_model: bool = True, freeze_embedding_layers: bool = True, freeze_projector: bool = False,
+                 local_files_only: bool = False):
+        super().__init__()
+        self.save_model_name = "clip_vision_embedding"
+        self.clip_vision_model_name_or_path = clip_vision_model_name_or_path
+        self.projector_type = projector_type
+        self.projector_depth = projector_depth
+        self.projector_name_or_path = projector_name_or_path
+        self.pretrained_model_name_or_path = pretrained_model_name_or_path
+        self.use_additional_post_layernorm = use_additional_post_layernorm
+        self.select_layer = select_layer
+        self.embed_hidden_size = embed_hidden_size
+        self.freeze_clip_vision_model = freeze_clip_vision_model
+        self.freeze_embedding_layers = freeze_embedding_layers
+        self.freeze_projector = freeze_projector
+        if use_additional_post_layernorm:
+            raise ValueError("use_additional_post_layernorm=True is not used by any shipped config and is not built")
+        if not freeze_clip_vision_model:
+            raise ValueError("the native CLIP tower is forward-only: freeze_clip_vision_model must be True "
+                             "(projects/dreamllm/configs/common.py:35)")
+
+        src = clip_vision_model_name_or_path
+        if isinstance(src, str):
+            from transformers import CLIPVisionModel as HFCLIP
+            hf = HFCLIP.from_pretrained(src, local_files_only=local_files_only)
+            cfg = CLIPVisionConfigLite(**{k: getattr(hf.config, k) for k in
+                                          ("hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads", "image_size",
+                                           "patch_size", "layer_norm_eps", "hidden_act", "num_channels")})
+            self.clip_vision_model = CLIPVisionModel(cfg)
+            self.clip_vision_model.load_state_dict(hf.state_dict())
+        else:
+            cfg = src if isinstance(src, CLIPVisionConfigLite) else CLIPVisionConfigLite(**(src if isinstance(src, dict) else src.to_dict()))
+            self.clip_vision_model = CLIPVisionModel(cfg)
+        self._processor = None
+
+        projector_cfg = dict(projector=projector_type, freeze_projector=freeze_projector, depth=projector_depth,
+                             save_model_name=self.save_model_name, model_name_or_path=None)
+        self.projector = build_projector(projector_cfg, in_hidden_size=cfg.hidden_size, out_hidden_size=embed_hidden_size, bias=True)
+        self._init_weights(self.projector)
+        self.post_layernorm = nn.Identity()
+        self.image_embed_len = (cfg.image_size // cfg.patch_size) ** 2
+        if pretrained_model_name_or_path is not None:
+            self.load_model(pretrained_model_name_or_path)
+        self.projector.load_model(projector_name_or_path)
+        self.clip_vision_model.requires_grad_(False)
+        self.projector.requires_grad_(not freeze_projector)
+
+    @property
+    def processor(self):
+        if self._processor is None:
+            from transformers import CLIPImageProcessor
+            r = self.clip_vision_model.config.image_size
+            self._processor = CLIPImageProcessor(size={"shortest_edge": r}, crop_size={"height": r, "width": r})
+        return self._processor
+
+    @property
+    def embed_len(self):
+        return self.image_embed_len
+
+    @property
+    def embed_dim(self):
+        return self.embed_hidden_size
+
+    @property
+    def config(self) -> dict:
+        return dict(clip_vision_model_name_or_path=self.clip_vision_model_name_or_path,
+                    clip_vision_model_config=self.clip_vision_model.config.to_dict(),
+                    pretrained_model_name_or_path=self.pretrained_model_name_or_path, select_layer=self.select_layer,
+                    embed_len=self.embed_len, embed_dim=self.embed_dim, freeze_clip_vision_model=self.freeze_clip_vision_model,
+                    freeze_embedding_layers=self.freeze_embedding_layers, freeze_projector=self.freeze_projector)
+
+    def fsdp_ignored_modules(self) -> list:
+        out = [self.clip_vision_model]
+        if self.freeze_projector:
+            out.append(self.projector)
+        return out
+
+    def save_model(self, output_dir: str):
+        torch.save(self.state_dict(), os.path.join(output_dir, f"{self.save_model_name}.bin"))
+
+    def load_model(self, output_dir: str):
+        f = os.path.join(output_dir, f"{self.save_model_name}.bin")
+        if os.path.isfile(f):
+            self.load_state_dict(torch.load(f, map_location="cpu"))
+
+    def forward(self, images: torch.Tensor | None = None):
+        """[Ni,3,R,R] -> [Ni,P,H].  `images=None` returns None: the reference's dummy CLIP pass on a zero image (:316-319,
+        :328-329) only exists to satisfy DDP's unused-parameter check, which our reducer does not need."""
+        if images is None:
+            return None
+        hidden_state = self.clip_vision_model.hidden_state(images, self.select_layer)
+        image_features = hidden_state[:, 1:]
+        image_embeds = self.projector(image_features)[-1]
+        return self.post_layernorm(image_embeds)
+
+
+# ------------------------------------------------------------------------------------------------ splice plumbing
+@dataclass
+class SplicePlan:
+    """Host-built index maps for one batch (all int32, on device).  Built once per batch from input_ids — this is what
+    SURVEY §8(f) row 3 moves into the collator; it replaces the per-sample torch.where / torch.cat loops and their host
+    syncs (modeling_dreamllm.py:1082-1141)."""
+    img_dst: torch.Tensor      # rows of [B*S] that receive image features
+    img_src: torch.Tensor      # rows of [Ni*P]
+    dq_dst: torch.Tensor       # rows of [B*S] that receive dream queries
+    dq_src: torch.Tensor       # rows of [Q]
+    dq_seg: torch.Tensor       # CSR over query index -> positions in dq_rows  (gradient of the broadcast)
+    dq_rows: torch.Tensor
+    cond_rows: torch.Tensor    # rows of [B*S] gathered as SD conditioning, [Nd*Q]
+    n_images_used: int
+    n_dreams: int
+
+
+def build_splice_plan(input_ids_cpu: torch.Tensor, image_start_id: int, dream_start_id: int, P: int, Q: int, n_images: int,
+                      n_dream_images: int | None, device) -> SplicePlan:
+    """Pure host integer bookkeeping, semantics of the reference loops:
+      * dream queries: for every <dream_start> at (b, p): rows [p+1, p+1+Q) <- dream_queries        (:1082-1099)
+      * images: the j-th <im_start> counted globally in batch-major order, while j < n_images: rows [p+1, p+1+P)
+        <- image_features[j]                                                                         (:1104-1141)
+      * conditioning gather: for every <dream_start> in batch-major order until n_dream_images: rows [p+1, p+1+Q)  (:1401-1418)
+    """
+    ids = input_ids_cpu
+    assert ids.device.type == "cpu" and ids.dim() == 2
+    B, S = ids.shape
+    flat = ids.reshape(-1)
+    ar = torch.arange(B * S)
+    img_pos = ar[flat == image_start_id][:max(n_images, 0)] if n_images else ar[:0]
+    dq_pos = ar[flat == dream_start_id]
+    for pos, L in ((img_pos, P), (dq_pos, Q)):
+        if pos.numel():
+            assert int(((pos % S) + L + 1).max()) <= S, "span runs past the end of the sequence (reference assert :1126)"
+    img_dst = (img_pos[:, None] + 1 + torch.arange(P)[None]).reshape(-1)
+    img_src = torch.arange(img_pos.numel() * P)
+    dq_dst = (dq_pos[:, None] + 1 + torch.arange(Q)[None]).reshape(-1)
+    dq_src = torch.arange(Q).repeat(dq_pos.numel())
+    K = dq_pos.numel()
+    dq_seg = torch.arange(Q + 1) * K
+    dq_rows = (dq_pos[None, :] + 1 + torch.arange(Q)[:, None]).reshape(-1)          # query-major
+    nd = K if n_dream_images is None else min(K, n_dream_images)
+    cond_rows = (dq_pos[:nd, None] + 1 + torch.arange(Q)[None]).reshape(-1)
+    to = lambda t: t.to(torch.int32).to(device, non_blocking=True)
+    return SplicePlan(to(img_dst), to(img_src), to(dq_dst), to(dq_src), to(dq_seg), to(dq_rows), to(cond_rows),
+                      int(img_pos.numel()), int(nd))
+
+
+class _SpliceFn(torch.autograd.Function):
+    """inputs_embeds with image-feature / dream-query rows written in (bit-exact row copies); backward routes row
+    gradients back (token-embedding grads are zero at replaced positions, exactly as torch.cat drops them)."""
+
+    @staticmethod
+    def forward(ctx, embeds, image_features, dream_queries, plan: SplicePlan):
+        B, S, H = embeds.shape
+        out = embeds.reshape(B * S, H).clone()
+        if image_features is not None and plan.img_dst.numel():
+            ops.copy_rows_(out, plan.img_dst, image_features.reshape(-1, H).contiguous(), plan.img_src)
+        if dream_queries is not None and plan.dq_dst.numel():
+            ops.copy_rows_(out, plan.dq_dst, dream_queries.reshape(-1, H).contiguous(), plan.dq_src)
+        ctx.plan = plan
+        ctx.shapes = (None if image_features is None else image_features.shape, None if dream_queries is None else dream_queries.shape)
+        return out.view(B, S, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        plan = ctx.plan
+        B, S, H = dy.shape
+        dy2 = dy.reshape(B * S, H).contiguous()
+        d_img = d_dq = None
+        img_shape, dq_shape = ctx.shapes
+        if img_shape is not None and ctx.needs_input_grad[1]:
+            d_img = torch.zeros(img_shape, device=dy.device, dtype=dy.dtype)
+            if plan.img_dst.numel():
+                ops.copy_rows_(d_img.view(-1, H), plan.img_src, dy2, plan.img_dst)
+        if dq_shape is not None and ctx.needs_input_grad[2]:
+            if plan.dq_dst.numel():
+                d_dq = ops.segment_sum_rows(dy2, plan.dq_seg, plan.dq_rows, dq_shape[-2]).view(dq_shape)
+            else:
+                d_dq = torch.zeros(dq_shape, device=dy.device, dtype=dy.dtype)
+        d_emb = None
+        if ctx.needs_input_grad[0]:
+            d_emb = dy2.clone()
+            if plan.img_dst.numel():
+                ops.zero_rows_(d_emb, plan.img_dst)
+            if plan.dq_dst.numel():
+                ops.zero_rows_(d_emb, plan.dq_dst)
+            d_emb = d_emb.view(B, S, H)
+        return d_emb, d_img, d_dq, None
+
+
+class _GatherRowsFn(torch.autograd.Function):
+    """out[r] = x2d[rows[r]] (unique rows) — the dream-query conditioning gather (:1401-1418)."""
+
+    @staticmethod
+    def forward(ctx, x, rows):
+        H = x.shape[-1]
+        x2 = x.reshape(-1, H).contiguous()
+        out = torch.empty((rows.numel(), H), device=x.device, dtype=x.dtype)
+        ident = torch.arange(rows.numel(), device=x.device, dtype=torch.int32)
+        ops.copy_rows_(out, ident, x2, rows)
+        ctx.save_for_backward(rows, ident)
+        ctx.shape = x.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        rows, ident = ctx.saved_tensors
+        H = dy.shape[-1]
+        dx = torch.zeros(ctx.shape, device=dy.device, dtype=dy.dtype)
+        ops.copy_rows_(dx.view(-1, H), rows, dy.contiguous(), ident)
+        return dx, None
+
+
+def splice_embeddings(embeds, image_features, dream_queries, plan):
+    return _SpliceFn.apply(embeds, image_features, dream_queries, plan)
+
+
+def gather_rows(x, rows):
+    return _GatherRowsFn.apply(x, rows)

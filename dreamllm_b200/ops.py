@@ -63,8 +63,12 @@ def _chk_cuda(*ts):
 
 
 # ----------------------------------------------------------------------------------------------- GEMM
+ACT_NONE, ACT_QUICK_GELU, ACT_GELU, ACT_SILU = 0, 1, 2, 3
+
+
 def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = False, out: torch.Tensor | None = None,
-         out_dtype=BF16, cta_pair: int = -1) -> torch.Tensor:
+         out_dtype=BF16, cta_pair: int = -1, bias: torch.Tensor | None = None, residual: torch.Tensor | None = None,
+         act: int = 0) -> torch.Tensor:
     """C[M,N] = op(A) @ op(B) on tcgen05.
 
     a_mn=False: a is [M,K];  a_mn=True: a is [K,M] (uses a^T)
@@ -89,8 +93,20 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if PROFILE.enabled:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    rc = lib().dllm_gemm_bf16(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
-                              int(b_mn), int(out.dtype == torch.float32), cta_pair, _stream())
+    if bias is None and residual is None and act == 0:
+        rc = lib().dllm_gemm_bf16(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
+                                  int(b_mn), int(out.dtype == torch.float32), cta_pair, _stream())
+    else:
+        _chk_cuda(bias, residual)
+        if bias is not None:
+            assert bias.dtype == BF16 and bias.is_contiguous() and bias.numel() == N
+        ldr = 0
+        if residual is not None:
+            assert residual.dtype == BF16 and residual.shape == (M, N) and residual.stride(1) == 1
+            ldr = residual.stride(0)
+        rc = lib().dllm_gemm_bf16_ex(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
+                                     int(b_mn), int(out.dtype == torch.float32), cta_pair, _p(bias), _p(residual), ldr,
+                                     int(act), _stream())
     check(rc, "dllm_gemm_bf16")
     if PROFILE.enabled:
         e1.record()
@@ -99,9 +115,9 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
-def linear(x2d: torch.Tensor, weight: torch.Tensor, out=None, out_dtype=BF16) -> torch.Tensor:
-    """y = x @ W^T (nn.Linear forward)."""
-    return gemm(x2d, weight, out=out, out_dtype=out_dtype)
+def linear(x2d: torch.Tensor, weight: torch.Tensor, out=None, out_dtype=BF16, bias=None, residual=None, act=0) -> torch.Tensor:
+    """y = act(x @ W^T + bias) + residual (nn.Linear forward with the fused epilogue)."""
+    return gemm(x2d, weight, out=out, out_dtype=out_dtype, bias=bias, residual=residual, act=act)
 
 
 def linear_dgrad(dy2d: torch.Tensor, weight: torch.Tensor, out=None) -> torch.Tensor:
@@ -142,7 +158,7 @@ def rmsnorm_bwd(dy2d, x2d, weight, rstd, dres=None, need_dw=True):
     ws = torch.empty(max(wsb, 4), device=x2d.device, dtype=torch.uint8)
     check(lib().dllm_rmsnorm_bwd(_p(dy2d), _p(x2d), _p(weight), _p(rstd), _p(dres), _p(dx), _p(dw), 0, _p(ws), wsb, T, H,
                                  _stream()), "dllm_rmsnorm_bwd")
-    LAUNCHES.add(2)
+    LAUNCHES.add(3 if need_dw else 1)
     return dx, dw
 
 
@@ -256,3 +272,61 @@ def attn_bwd(dout, q, k, v, out, lse, dq, dk, dv, causal=True, seqlens=None, sca
           "dllm_attn_bwd")
     LAUNCHES.add(3)
     return dq, dk, dv
+
+
+# ----------------------------------------------------------------------------------------------- CLIP / splice helpers
+def layernorm_fwd(x2d, weight, bias, eps):
+    _chk_cuda(x2d, weight, bias)
+    T, H = x2d.shape
+    assert x2d.is_contiguous() and x2d.dtype == BF16
+    y = torch.empty_like(x2d)
+    check(lib().dllm_layernorm_fwd(_p(x2d), _p(weight), _p(bias), _p(y), T, H, float(eps), _stream()), "dllm_layernorm_fwd")
+    LAUNCHES.add(1)
+    return y
+
+
+def clip_patchify(images, patch, kpad):
+    """images [N,3,R,R] bf16 NCHW -> [N*(R/patch)^2, kpad] unfolded patches (conv-weight flatten order, zero padded)."""
+    _chk_cuda(images)
+    N, C, R, R2 = images.shape
+    assert C == 3 and R == R2 and images.is_contiguous() and images.dtype == BF16
+    G = R // patch
+    out = torch.empty((N * G * G, kpad), device=images.device, dtype=BF16)
+    check(lib().dllm_clip_patchify(_p(images), _p(out), N, R, patch, kpad, _stream()), "dllm_clip_patchify")
+    LAUNCHES.add(1)
+    return out
+
+
+def clip_assemble(patches2d, cls, pos, N, P):
+    _chk_cuda(patches2d, cls, pos)
+    C = patches2d.shape[1]
+    out = torch.empty((N, P + 1, C), device=patches2d.device, dtype=BF16)
+    check(lib().dllm_clip_assemble(_p(patches2d), _p(cls), _p(pos), _p(out), N, P, C, _stream()), "dllm_clip_assemble")
+    LAUNCHES.add(1)
+    return out
+
+
+def copy_rows_(dst2d, dst_idx, src2d, src_idx, accumulate=False):
+    _chk_cuda(dst2d, dst_idx, src2d, src_idx)
+    assert dst2d.is_contiguous() and src2d.is_contiguous() and dst_idx.dtype == torch.int32 and src_idx.dtype == torch.int32
+    R, H = dst_idx.numel(), dst2d.shape[1]
+    assert src_idx.numel() == R and src2d.shape[1] == H
+    check(lib().dllm_copy_rows(_p(dst2d), _p(dst_idx), _p(src2d), _p(src_idx), R, H, int(accumulate), _stream()), "dllm_copy_rows")
+    LAUNCHES.add(1)
+    return dst2d
+
+
+def segment_sum_rows(src2d, seg, rows, Q):
+    _chk_cuda(src2d, seg, rows)
+    H = src2d.shape[1]
+    out = torch.empty((Q, H), device=src2d.device, dtype=BF16)
+    check(lib().dllm_segment_sum_rows(_p(out), _p(src2d), _p(seg), _p(rows), Q, H, _stream()), "dllm_segment_sum_rows")
+    LAUNCHES.add(1)
+    return out
+
+
+def zero_rows_(dst2d, idx):
+    _chk_cuda(dst2d, idx)
+    check(lib().dllm_zero_rows(_p(dst2d), _p(idx), idx.numel(), dst2d.shape[1], _stream()), "dllm_zero_rows")
+    LAUNCHES.add(1)
+    return dst2d

@@ -83,6 +83,26 @@ int dllm_attn_bwd(const void* dout, const void* q, const void* k, const void* v,
                   void* dq, void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B,
                   int S, int nh, int d, long ld_qkv, long ld_o, long ld_dqkv, int causal, float scale, void* stream);
 
+/* GEMM with fused epilogue: out = act(bf16(acc + bias[col])) (+ residual[row, col]); act 0 none, 1 quick_gelu
+ * (CLIP MLP, transformers activations.QuickGELU), 2 gelu-erf (MLPProjector, mlp_projector.py:30-50), 3 silu.
+ * Replaces nn.Linear(bias=True) + activation + residual add in the CLIP tower / projectors / UNet transformer blocks. */
+int dllm_gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc,
+                      int a_mn, int b_mn, int out_fp32, int cta_pair, const void* bias, const void* residual, long ldr,
+                      int act, void* stream);
+
+/* nn.LayerNorm forward (CLIP layer_norm1/2 + pre_layrnorm, modeling_plugins.py:321 -> transformers CLIPVisionModel). */
+int dllm_layernorm_fwd(const void* x, const void* weight, const void* bias, void* y, int T, int H, float eps, void* stream);
+
+/* CLIP patch embedding (Conv2d k=s=patch, no bias) as unfold + GEMM, and CLS/position-embedding assembly. */
+int dllm_clip_patchify(const void* images_nchw, void* out, int N, int R, int patch, int Kpad, void* stream);
+int dllm_clip_assemble(const void* patches, const void* cls, const void* pos, void* out, int N, int P, int C, void* stream);
+
+/* Index-driven row copies: the embedding splice of DreamLLMModel.forward (modeling_dreamllm.py:1082-1141) and the
+ * dream-query conditioning gather (:1401-1418).  mode 0: dst[dst_idx[r]] = src[src_idx[r]]; mode 1: += (unique dst). */
+int dllm_copy_rows(void* dst, const int* dst_idx, const void* src, const int* src_idx, int R, int H, int mode, void* stream);
+int dllm_segment_sum_rows(void* dst, const void* src, const int* seg, const int* rows, int Q, int H, void* stream);
+int dllm_zero_rows(void* dst, const int* idx, int R, int H, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

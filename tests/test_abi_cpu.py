@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert L.dllm_version() >= 100
     assert L.dllm_error_string(-1).decode().startswith("invalid")
     # pure host queries work without a device
-    assert L.dllm_attn_bwd_workspace_bytes(2, 128, 4, 128) == 2 * 128 * 4 * 2 * 4
+    assert L.dllm_attn_bwd_workspace_bytes(2, 100, 4, 128) == 2 * 128 * 4 * 2 * 4
 
 
 def test_sass_contains_tcgen05_and_tma():
