@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.path.join(_HERE, "libdreamllm_sm100.so")
-SOURCES = ["capi.cu", "gemm_sm100.cu", "elementwise.cu", "attn_sm100.cu"]
+SOURCES = ["capi.cu", "gemm_sm100.cu", "elementwise.cu", "attn_sm100.cu", "unet_ops.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
@@ -81,6 +81,18 @@ SIGNATURES = {
     "dllm_copy_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "dllm_segment_sum_rows": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp]),
     "dllm_zero_rows": (_i, [_vp, _vp, _i, _i, _vp]),
+    "dllm_attn_fwd_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _l, _l, _l, _i, _f, _vp]),
+    "dllm_conv3x3_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dllm_groupnorm_workspace_bytes": (_sz, [_i, _i, _i]),
+    "dllm_groupnorm_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _i, _vp]),
+    "dllm_geglu": (_i, [_vp, _vp, _i, _i, _vp]),
+    "dllm_upsample2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dllm_im2col_s2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dllm_copy_cols": (_i, [_vp, _vp, _l, _i, _i, _i, _vp]),
+    "dllm_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "dllm_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dllm_timestep_embedding": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "dllm_sampler_step": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _l, _vp]),
 }
 
 _lib = None

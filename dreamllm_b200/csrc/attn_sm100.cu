@@ -109,7 +109,7 @@ template <int D, bool kCausal>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, float* __restrict__ lse,
-                const int* __restrict__ seqlens, int S, int nh, float scale_log2) {
+                const int* __restrict__ seqlens, int S, int Skv, int nh, float scale_log2) {
   using L = FwdSmem<D>;
   constexpr int NCH = L::NCH;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -126,7 +126,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int kv_len = seqlens ? min(seqlens[b], S) : S;
+  const int kv_len = seqlens ? min(seqlens[b], Skv) : Skv;   // Skv != S only for cross-attention (non-causal)
+  const int q_len = seqlens ? kv_len : S;                    // right-padded self-attention: rows >= len are padding
   const int kv_end = kCausal ? min(kv_len, q0 + 128) : kv_len;
   const int n_kv = (kv_end + 63) / 64;
 
@@ -265,7 +266,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       mbar_wait(pv_done, (n_kv - 1) & 1, 18);
       tc_fence_after();
     }
-    const bool valid_row = (q_row < kv_len) && n_kv > 0 && l_run > 0.f;
+    const bool valid_row = (q_row < q_len) && n_kv > 0 && l_run > 0.f;
     const float inv = valid_row ? 1.f / l_run : 0.f;
     if (n_kv > 0) {
       store_acc_tile<D>(tmem_O, smem + L::oQ, inv, &to, h * D, q0, b, warp, lane);
@@ -686,7 +687,7 @@ static int set_smem(K kern, int bytes) {
 
 template <int D, bool C>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
-                      const int* seqlens, int B, int S, int nh, float scale_log2, cudaStream_t st) {
+                      const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st) {
   auto kern = attn_fwd_kernel<D, C>;
   static bool once = false;
   if (!once) {
@@ -695,25 +696,32 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     once = true;
   }
   dim3 grid((S + 127) / 128, nh, B);
-  kern<<<grid, kAttnThreads, FwdSmem<D>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, nh, scale_log2);
+  kern<<<grid, kAttnThreads, FwdSmem<D>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, Skv, nh, scale_log2);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
 int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int nh,
              int d, long ld_qkv, long ld_o, int causal, float scale, cudaStream_t st) {
-  if (B <= 0 || S <= 0 || nh <= 0) return DLLM_ERR_SHAPE;
+  return attn_fwd_ex(q, k, v, out, lse, seqlens, B, S, S, nh, d, ld_qkv, ld_qkv, ld_o, causal, scale, st);
+}
+
+// q: [B, S, nh, d] (token stride ld_q); k, v: [B, Skv, nh, d] (token stride ld_kv).  Skv != S = cross-attention.
+int attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int Skv,
+                int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || Skv <= 0 || nh <= 0) return DLLM_ERR_SHAPE;
   if (d != 128 && d != 64) return DLLM_ERR_UNSUPPORTED;
+  if (S != Skv && (causal || seqlens)) return DLLM_ERR_UNSUPPORTED;
   CUtensorMap tq, tk, tv, to;
   int rc;
-  if ((rc = make_tmap_bsc(&tq, q, B, S, nh * d, ld_qkv, 128))) return rc;
-  if ((rc = make_tmap_bsc(&tk, k, B, S, nh * d, ld_qkv, 64))) return rc;
-  if ((rc = make_tmap_bsc(&tv, v, B, S, nh * d, ld_qkv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tq, q, B, S, nh * d, ld_q, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tk, k, B, Skv, nh * d, ld_kv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tv, v, B, Skv, nh * d, ld_kv, 64))) return rc;
   if ((rc = make_tmap_bsc(&to, out, B, S, nh * d, ld_o, 32))) return rc;
   const float sl2 = scale * kLog2e;
-  if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st)
-                              : launch_fwd<128, false>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st);
-  return causal ? launch_fwd<64, true>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st)
-                : launch_fwd<64, false>(tq, tk, tv, to, lse, seqlens, B, S, nh, sl2, st);
+  if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st)
+                              : launch_fwd<128, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st);
+  return causal ? launch_fwd<64, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st)
+                : launch_fwd<64, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st);
 }
 
 static inline int s_pad(int S) { return (S + 63) / 64 * 64; }

@@ -144,4 +144,51 @@ int dllm_zero_rows(void* dst, const int* idx, int R, int H, void* stream) {
   return zero_rows(dst, idx, R, H, S(stream));
 }
 
+int dllm_attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int Sq,
+                     int Skv, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, void* stream) {
+  ensure_context(q);
+  return attn_fwd_ex(q, k, v, out, lse, seqlens, B, Sq, Skv, nh, d, ld_q, ld_kv, ld_o, causal, scale, S(stream));
+}
+int dllm_conv3x3_nhwc(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, const void* bias,
+                      const void* rowbias, const void* residual, void* stream) {
+  ensure_context(x);
+  return conv3x3_nhwc(x, w, y, N, H, W, Cin, Cout, bias, rowbias, residual, S(stream));
+}
+size_t dllm_groupnorm_workspace_bytes(int N, int HW, int G) { return groupnorm_workspace(N, HW, G); }
+int dllm_groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW,
+                        int C, int G, float eps, int silu, void* stream) {
+  ensure_context(x);
+  return groupnorm_nhwc(x, w, b, y, workspace, ws_bytes, N, HW, C, G, eps, silu, S(stream));
+}
+int dllm_geglu(const void* in, void* out, int T, int I, void* stream) { ensure_context(in); return geglu(in, out, T, I, S(stream)); }
+int dllm_upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream) {
+  ensure_context(x);
+  return upsample2x_nhwc(x, y, N, H, W, C, S(stream));
+}
+int dllm_im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, void* stream) {
+  ensure_context(x);
+  return im2col_s2_nhwc(x, out, N, H, W, C, S(stream));
+}
+int dllm_copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, void* stream) {
+  ensure_context(src);
+  return copy_cols(src, dst, rows, Cs, Cd, col0, S(stream));
+}
+int dllm_conv_in(const float* x, const void* w, const void* bias, void* y, int B, int Bsrc, int Cin, int H, int W, int Cout,
+                 void* stream) {
+  ensure_context(x);
+  return conv_in_nchw_to_nhwc(x, w, bias, y, B, Bsrc, Cin, H, W, Cout, S(stream));
+}
+int dllm_conv_out(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout, void* stream) {
+  ensure_context(x);
+  return conv_out_nhwc_to_nchw(x, w, bias, y, B, C, H, W, Cout, S(stream));
+}
+int dllm_timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, void* stream) {
+  ensure_context(out);
+  return timestep_embedding(timesteps, step, out, B, dim, S(stream));
+}
+int dllm_sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance,
+                      int use_cfg, int mode, long n, void* stream) {
+  ensure_context(eps);
+  return sampler_step(eps, latents, noise, coef, step, guidance, use_cfg, mode, n, S(stream));
+}
 }  // extern "C"

@@ -46,6 +46,17 @@ struct GemmEpi {
   const bf16* residual;  // [M, ldr] or nullptr
   long ldr;
   int act;               // 0 none, 1 quick_gelu x*sigmoid(1.702x), 2 gelu (erf), 3 silu
+  const bf16* rowbias;   // [M / rows_per_group, N] or nullptr: per-row-group bias (ResnetBlock2D's time-embedding add)
+  int rows_per_group;
+};
+
+// Implicit-GEMM 3x3 / stride 1 / pad 1 convolution on NHWC activations: A[m, k] = x[n, h + r - 1, w + s - 1, c] with
+// m = (n, h, w), k = (r, s, c).  A 128-row tile is the 4-D TMA box {64 c, Wb, Hb, Nb} (Wb*Hb*Nb = 128) fetched at
+// coordinates (c0, s - 1, h0 + r - 1, n0): out-of-range rows/columns are zero-filled by TMA == the conv's zero padding.
+struct ConvGeom {
+  int cpt;       // Cin / 64: K blocks per filter tap
+  int W, H;      // plane
+  int HW;
 };
 
 __device__ __forceinline__ float epi_act(float x, int act) {
@@ -55,10 +66,10 @@ __device__ __forceinline__ float epi_act(float x, int act) {
   return x;
 }
 
-template <int kCta, bool kAMN, bool kBMN, typename OutT>
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi) {
+            const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi, ConvGeom cg) {
   using Cfg = GemmCfg<kCta>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kOutF32 = sizeof(OutT) == 4;
@@ -138,9 +149,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         uint8_t* a_s = smem + stage * Cfg::kStageBytes;
         uint8_t* b_s = a_s + Cfg::kABytes;
         const int k0 = kb * BK;
+        // implicit-conv coordinates of this CTA's 128-pixel tile and this K block's filter tap
+        int cv_c = 0, cv_w = 0, cv_h = 0, cv_n = 0;
+        if constexpr (kConv) {
+          const int tap = kb / cg.cpt;
+          cv_c = (kb - tap * cg.cpt) * BK;
+          const int r = tap / 3, sx = tap - 3 * r;
+          cv_n = m0 / cg.HW;
+          cv_h = (m0 - cv_n * cg.HW) / cg.W + r - 1;
+          cv_w = sx - 1;
+        }
         if constexpr (kCta == 1) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if constexpr (!kAMN) {
+          if constexpr (kConv) {
+            tma_load_4d(a_s, &tma_a, &full_bar[stage], cv_c, cv_w, cv_h, cv_n);
+          } else if constexpr (!kAMN) {
             tma_load_2d(a_s, &tma_a, &full_bar[stage], k0, m0);
           } else {
 #pragma unroll
@@ -157,7 +180,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           // both CTAs' bytes are counted on the leader's barrier
           if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
           const uint32_t fb = full0_cluster + stage * 8;
-          if constexpr (!kAMN) {
+          if constexpr (kConv) {
+            tma_load_4d_2cta(a_s, &tma_a, fb, cv_c, cv_w, cv_h, cv_n);
+          } else if constexpr (!kAMN) {
             tma_load_2d_2cta(a_s, &tma_a, fb, k0, m0);
           } else {
 #pragma unroll
@@ -228,7 +253,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tmem_ld32(taddr0 + c * CH, v);
         if constexpr (!kOutF32) tmem_ld32(taddr0 + c * CH + 32, v + 32);
         tmem_ld_wait();
-        if (epi.bias != nullptr || epi.act != 0 || epi.residual != nullptr) {
+        if (epi.bias != nullptr || epi.act != 0 || epi.residual != nullptr || epi.rowbias != nullptr) {
           const int gcol = col0 + c * CH;
           const int grow = row0 + lane;
 #pragma unroll
@@ -242,6 +267,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
               for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); bsv[2 * e] = f.x; bsv[2 * e + 1] = f.y; }
+            }
+            if (epi.rowbias != nullptr && col_ok && grow < M) {
+              const uint4 q = __ldg(reinterpret_cast<const uint4*>(epi.rowbias + static_cast<size_t>(grow / epi.rows_per_group) * N + cj));
+              const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); bsv[2 * e] += f.x; bsv[2 * e + 1] += f.y; }
             }
             if (epi.residual != nullptr && col_ok && grow < M) {
               const uint4 q = *reinterpret_cast<const uint4*>(epi.residual + static_cast<size_t>(grow) * epi.ldr + cj);
@@ -345,11 +376,11 @@ int num_sms() {
   return n;
 }
 
-template <int kCta, bool kAMN, bool kBMN, typename OutT>
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
-                       const GemmEpi& epi, cudaStream_t stream) {
+                       const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}) {
   using Cfg = GemmCfg<kCta>;
-  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT>;
+  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
@@ -373,7 +404,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi, cg);
   return e == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
@@ -389,7 +420,7 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   if ((bias || residual) && (N % 8)) return DLLM_ERR_SHAPE;
   if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || ((ldr * 2) & 15))) return DLLM_ERR_ALIGN;
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return DLLM_ERR_ALIGN;
-  GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), ldr, act};
+  GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), ldr, act, nullptr, 1};
   const int kcta = (cta_pair < 0) ? (M > BM ? 2 : 1) : (cta_pair ? 2 : 1);
   CUtensorMap ta, tb, tc;
   int rc;
@@ -420,6 +451,48 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   DLLM_GEMM_CASE(2, true, false)
 #undef DLLM_GEMM_CASE
   return DLLM_ERR_SHAPE;
+}
+
+// 4-D NHWC activation map: dims {C, W, H, N}, box {64, Wb, Hb, Nb}, 128B swizzle.
+static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int Nimg, int H, int W, int C, int Wb, int Hb, int Nb) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return DLLM_ERR_DRIVER;
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (C % 8)) return DLLM_ERR_ALIGN;
+  cuuint64_t gdim[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Nimg};
+  cuuint64_t gstr[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {64, (cuuint32_t)Wb, (cuuint32_t)Hb, (cuuint32_t)Nb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) fprintf(stderr, "dllm: cuTensorMapEncodeTiled(4D) failed (CUresult %d)\n", (int)r);
+  return r == CUDA_SUCCESS ? 0 : DLLM_ERR_TMAP;
+}
+
+// y[n,h,w,:] = conv3x3(x, w) + bias + rowbias[n] (+ residual);  x NHWC [Nimg,H,W,Cin], w [Cout, 3,3,Cin] (K-major), y NHWC
+int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, const void* bias,
+                 const void* rowbias, const void* residual, cudaStream_t stream) {
+  if (Nimg <= 0 || Cin % 64 || Cout % 8 || W > 128 || (128 % W)) return DLLM_ERR_SHAPE;
+  const int HW = H * W;
+  int Wb = W, Hb = 128 / W, Nb = 1;
+  if (Hb > H) {  // small planes: the 128-pixel tile spans several whole images
+    if (Hb % H) return DLLM_ERR_SHAPE;
+    Nb = Hb / H;
+    Hb = H;
+  } else if (H % Hb) {
+    return DLLM_ERR_SHAPE;
+  }
+  const int M = Nimg * HW, K = 9 * Cin;
+  const int kcta = (M > BM) ? 2 : 1;
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap_nhwc(&ta, x, Nimg, H, W, Cin, Wb, Hb, Nb))) return rc;
+  if ((rc = make_tmap_2d(&tb, w, 2, Cout, K, K, BN / kcta, BK))) return rc;
+  if ((rc = make_tmap_2d(&tc, y, 2, M, Cout, Cout, 32, 64))) return rc;
+  GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), Cout, 0, static_cast<const bf16*>(rowbias), HW};
+  ConvGeom cg{Cin / 64, W, H, HW};
+  if (kcta == 2) return launch_gemm<2, false, false, bf16, true>(ta, tb, tc, M, Cout, K, epi, stream, cg);
+  return launch_gemm<1, false, false, bf16, true>(ta, tb, tc, M, Cout, K, epi, stream, cg);
 }
 
 }  // namespace dllm

@@ -27,4 +27,8 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
                  int b_mn, int out_fp32, int cta_pair, const void* bias, const void* residual, long ldr, int act,
                  cudaStream_t stream);
 
+// implicit-GEMM 3x3 stride-1 pad-1 convolution, NHWC bf16 (see gemm_sm100.cu)
+int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, const void* bias,
+                 const void* rowbias, const void* residual, cudaStream_t stream);
+
 }  // namespace dllm

@@ -27,6 +27,22 @@ int segment_sum_rows(void* dst, const void* src, const int* seg, const int* rows
 int zero_rows(void* dst, const int* idx, int R, int H, cudaStream_t s);
 int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int nh,
              int d, long ld_qkv, long ld_o, int causal, float scale, cudaStream_t s);
+int attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int Skv,
+                int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, cudaStream_t s);
+size_t groupnorm_workspace(int N, int HW, int G);
+int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW, int C,
+                   int G, float eps, int silu, cudaStream_t s);
+int geglu(const void* in, void* out, int T, int I, cudaStream_t s);
+int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
+int im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
+int copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, cudaStream_t s);
+int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* y, int B, int Bsrc, int Cin, int H, int W,
+                         int Cout, cudaStream_t s);
+int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout,
+                          cudaStream_t s);
+int timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, cudaStream_t s);
+int sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance, int use_cfg,
+                 int mode, long n, cudaStream_t s);
 size_t attn_bwd_workspace(int B, int S, int nh, int d);
 int attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
              void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int S, int nh, int d,

@@ -1,0 +1,344 @@
+// HBM-bound kernels of the SD-2.1 UNet denoising step (sm_100a), NHWC bf16 activations.
+// Reference call sites: StableDiffusionHead.pipeline, modeling_plugins.py:809-833 (unet(...) -> CFG combine ->
+// scheduler.step), whose arithmetic is diffusers 0.24 (ResnetBlock2D GroupNorm+SiLU, GEGLU, Upsample2D, Downsample2D,
+// Timesteps, DDIM/DDPM step) — restated in oracle/unet_oracle.py.
+#include "common.cuh"
+#include "gemm_sm100.h"
+#include "ops.h"
+
+namespace dllm {
+
+struct alignas(16) V8 {
+  __nv_bfloat162 v[4];
+};
+__device__ __forceinline__ void up8(const V8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ V8 pk8(const float* f) {
+  V8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+__device__ __forceinline__ float r16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// ------------------------------------------------------------------------------------------------ GroupNorm (+SiLU)
+// x [N, HW, C]; G groups of C/G channels.  Pass 1: per (n, pixel-chunk) partial sum / sum-of-squares per group.
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxV = 2;  // C <= 256 * 2 * 8 = 4096
+
+__global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW,
+                                                                int C, int G, int rows_per_cta) {
+  extern __shared__ float sm[];  // [2][C]
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int nvec = C >> 3;
+  const int r0 = chunk * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  float s[kGnMaxV][8], q[kGnMaxV][8];
+#pragma unroll
+  for (int i = 0; i < kGnMaxV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[i][j] = q[i][j] = 0.f;
+  const bf16* xb = x + (static_cast<size_t>(n) * HW) * C;
+  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int i = 0; i < kGnMaxV; ++i) {
+      const int v = threadIdx.x + i * kGnThreads;
+      if (v < nvec) {
+        float f[8];
+        up8(reinterpret_cast<const V8*>(xb + static_cast<size_t>(r) * C)[v], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[i][j] += f[j]; q[i][j] += f[j] * f[j]; }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kGnMaxV; ++i) {
+    const int v = threadIdx.x + i * kGnThreads;
+    if (v < nvec)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sm[v * 8 + j] = s[i][j]; sm[C + v * 8 + j] = q[i][j]; }
+  }
+  __syncthreads();
+  const int cpg = C / G;
+  for (int g = threadIdx.x; g < G; g += kGnThreads) {
+    float a = 0.f, b = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sm[c]; b += sm[C + c]; }
+    float* p = partial + ((static_cast<size_t>(n) * nchunks + chunk) * G + g) * 2;
+    p[0] = a;
+    p[1] = b;
+  }
+}
+// stats[n, g] = {mean, rstd}
+__global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks, int G, float count,
+                                   float eps, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * G + g
+  if (i >= total) return;
+  const int n = i / G, g = i - n * G;
+  float a = 0.f, b = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* p = partial + ((static_cast<size_t>(n) * nchunks + c) * G + g) * 2;
+    a += p[0];
+    b += p[1];
+  }
+  const float mean = a / count;
+  const float var = fmaxf(b / count - mean * mean, 0.f);
+  stats[2 * i] = mean;
+  stats[2 * i + 1] = rsqrtf(var + eps);
+}
+// y = silu?( bf16( (x - mean) * rstd * w + b ) )
+__global__ void gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                const float* __restrict__ stats, bf16* __restrict__ y, int HW, int C, int G, int silu,
+                                long total_vec) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total_vec) return;
+  const int nvec = C >> 3;
+  const int v = static_cast<int>(gid % nvec);
+  const long pix = gid / nvec;
+  const int n = static_cast<int>(pix / HW);
+  const int cpg = C / G;
+  float f[8], wf[8], bf[8];
+  up8(reinterpret_cast<const V8*>(x)[gid], f);
+  up8(reinterpret_cast<const V8*>(w)[v], wf);
+  up8(reinterpret_cast<const V8*>(b)[v], bf);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (v * 8 + j) / cpg;
+    const float mean = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2);
+    const float rstd = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2 + 1);
+    float o = r16((f[j] - mean) * rstd * wf[j] + bf[j]);
+    if (silu) o = o / (1.f + expf(-o));
+    f[j] = o;
+  }
+  reinterpret_cast<V8*>(y)[gid] = pk8(f);
+}
+
+size_t groupnorm_workspace(int N, int HW, int G) {
+  const int rows = 64;
+  const int nchunks = (HW + rows - 1) / rows;
+  return (static_cast<size_t>(N) * nchunks * G * 2 + static_cast<size_t>(N) * G * 2) * sizeof(float);
+}
+int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW, int C,
+                   int G, float eps, int silu, cudaStream_t s) {
+  if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
+  if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
+  const int rows = 64;
+  const int nchunks = (HW + rows - 1) / rows;
+  float* partial = static_cast<float*>(workspace);
+  float* stats = partial + static_cast<size_t>(N) * nchunks * G * 2;
+  gn_partial_kernel<<<dim3(nchunks, N), kGnThreads, 2 * C * sizeof(float), s>>>((const bf16*)x, partial, HW, C, G, rows);
+  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, stats, nchunks, G, static_cast<float>(HW) * (C / G), eps, N * G);
+  const long total_vec = static_cast<long>(N) * HW * (C / 8);
+  gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, stats,
+                                                                               (bf16*)y, HW, C, G, silu, total_vec);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------------ GEGLU
+// diffusers GEGLU: h, gate = proj(x).chunk(2); out = h * gelu(gate)      in [T, 2I] -> out [T, I]
+__global__ void geglu_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int T, int I) {
+  const int nvec = I >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(T) * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  const long t = gid / nvec;
+  float a[8], g[8];
+  up8(*reinterpret_cast<const V8*>(in + t * 2 * I + v * 8), a);
+  up8(*reinterpret_cast<const V8*>(in + t * 2 * I + I + v * 8), g);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] *= r16(0.5f * g[j] * (1.f + erff(g[j] * 0.70710678118654752f)));
+  *reinterpret_cast<V8*>(out + t * I + v * 8) = pk8(a);
+}
+int geglu(const void* in, void* out, int T, int I, cudaStream_t s) {
+  if (I % 8 || T <= 0) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(T) * (I / 8);
+  geglu_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)in, (bf16*)out, T, I);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------------ spatial data movement
+// nearest 2x upsample (Upsample2D's F.interpolate), NHWC
+__global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__ y, int N, int H, int W, int C) {
+  const int nvec = C >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(N) * 4 * H * W * nvec;
+  if (gid >= total) return;
+  const int v = static_cast<int>(gid % nvec);
+  long p = gid / nvec;
+  const int wo = static_cast<int>(p % (2 * W)); p /= 2 * W;
+  const int ho = static_cast<int>(p % (2 * H));
+  const int n = static_cast<int>(p / (2 * H));
+  reinterpret_cast<uint4*>(y)[gid] = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + ho / 2) * W + wo / 2) * C)[v];
+}
+// im2col for the stride-2 3x3 pad-1 Downsample2D conv: out [N*Ho*Wo, 9*C], k = (r, s, c)
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C) {
+  const int nvec = C >> 3;
+  const int Ho = H / 2, Wo = W / 2;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(N) * Ho * Wo * 9 * nvec;
+  if (gid >= total) return;
+  const int v = static_cast<int>(gid % nvec);
+  long p = gid / nvec;
+  const int tap = static_cast<int>(p % 9); p /= 9;
+  const int wo = static_cast<int>(p % Wo); p /= Wo;
+  const int ho = static_cast<int>(p % Ho);
+  const int n = static_cast<int>(p / Ho);
+  const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+  uint4 val = make_uint4(0, 0, 0, 0);
+  if (h >= 0 && h < H && w >= 0 && w < W) val = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + h) * W + w) * C)[v];
+  reinterpret_cast<uint4*>(out)[gid] = val;
+}
+// dst[:, col0 : col0 + Cs] = src  (channel concat of skip connections, NHWC => a strided 2-D copy)
+__global__ void copy_cols_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long rows, int Cs, int Cd, int col0) {
+  const int nvec = Cs >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= rows * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  const long r = gid / nvec;
+  *reinterpret_cast<uint4*>(dst + r * Cd + col0 + v * 8) = reinterpret_cast<const uint4*>(src + r * Cs)[v];
+}
+int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 8) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(N) * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, N, H, W, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 8 || H % 2 || W % 2) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(N) * (H / 2) * (W / 2) * 9 * (C / 8);
+  im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)x, (bf16*)out, N, H, W, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, cudaStream_t s) {
+  if (Cs % 8 || Cd % 8 || col0 % 8 || rows <= 0) return DLLM_ERR_SHAPE;
+  const long total = rows * (Cs / 8);
+  copy_cols_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)src, (bf16*)dst, rows, Cs, Cd, col0);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------------ conv_in / conv_out
+// conv_in: latents fp32 NCHW [B,Cin(=4),H,W] (rounded to bf16 as the bf16 pipeline feeds them) -> NHWC bf16 [B,H,W,Cout];
+// w [Cout, Cin, 3, 3] bf16 (diffusers layout).  One thread = one pixel x 8 output channels.
+__global__ void conv_in_kernel(const float* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias,
+                               bf16* __restrict__ y, int B, int Bsrc, int Cin, int H, int W, int Cout) {
+  const int nvec = Cout >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(B) * H * W * nvec;
+  if (gid >= total) return;
+  const int v = static_cast<int>(gid % nvec);
+  long p = gid / nvec;
+  const int wx = static_cast<int>(p % W); p /= W;
+  const int hy = static_cast<int>(p % H);
+  const int n = static_cast<int>(p / H) % Bsrc;  // CFG: the same latents feed the uncond and cond halves (:811)
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = __bfloat162float(bias[v * 8 + j]);
+  for (int c = 0; c < Cin; ++c)
+    for (int r = 0; r < 3; ++r)
+      for (int sx = 0; sx < 3; ++sx) {
+        const int h = hy + r - 1, ww = wx + sx - 1;
+        if (h < 0 || h >= H || ww < 0 || ww >= W) continue;
+        const float xv = r16(x[((static_cast<size_t>(n) * Cin + c) * H + h) * W + ww]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += xv * __bfloat162float(w[((static_cast<size_t>(v * 8 + j) * Cin + c) * 3 + r) * 3 + sx]);
+      }
+  reinterpret_cast<V8*>(y)[gid] = pk8(acc);
+}
+// conv_out: NHWC bf16 [B,H,W,C] -> fp32 NCHW [B,Cout(=4),H,W]; w [Cout, C, 3, 3] bf16.  One warp = one pixel.
+template <int COUT>
+__global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias,
+                                float* __restrict__ y, int B, int C, int H, int W) {
+  const long warp = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= static_cast<long>(B) * H * W) return;
+  const int wx = static_cast<int>(warp % W);
+  const int hy = static_cast<int>((warp / W) % H);
+  const int n = static_cast<int>(warp / (static_cast<long>(W) * H));
+  float acc[COUT];
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = 0.f;
+  for (int r = 0; r < 3; ++r)
+    for (int sx = 0; sx < 3; ++sx) {
+      const int h = hy + r - 1, ww = wx + sx - 1;
+      if (h < 0 || h >= H || ww < 0 || ww >= W) continue;
+      const bf16* xp = x + ((static_cast<size_t>(n) * H + h) * W + ww) * C;
+      for (int c = lane; c < C; c += 32) {
+        const float xv = __bfloat162float(xp[c]);
+#pragma unroll
+        for (int o = 0; o < COUT; ++o) acc[o] += xv * __bfloat162float(w[((static_cast<size_t>(o) * C + c) * 3 + r) * 3 + sx]);
+      }
+    }
+#pragma unroll
+  for (int o = 0; o < COUT; ++o) acc[o] = warp_sum(acc[o]);
+  if (lane == 0)
+#pragma unroll
+    for (int o = 0; o < COUT; ++o)
+      y[((static_cast<size_t>(n) * COUT + o) * H + hy) * W + wx] = r16(acc[o] + __bfloat162float(bias[o]));
+}
+int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* y, int B, int Bsrc, int Cin, int H, int W,
+                         int Cout, cudaStream_t s) {
+  if (Cout % 8 || Bsrc <= 0) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(B) * H * W * (Cout / 8);
+  conv_in_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(x, (const bf16*)w, (const bf16*)bias, (bf16*)y, B, Bsrc, Cin, H, W, Cout);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout,
+                          cudaStream_t s) {
+  if (Cout != 4) return DLLM_ERR_UNSUPPORTED;
+  const long warps = static_cast<long>(B) * H * W;
+  conv_out_kernel<4><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, y, B, C, H, W);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ------------------------------------------------------------------------------------------------ time embedding / sampler
+// Timesteps(320, flip_sin_to_cos=True, shift 0): emb[b] = [cos(t*f_i) | sin(t*f_i)], f_i = exp(-ln(10000) i / half).
+// t is read from the device-side schedule: timesteps[*step] (so one captured CUDA graph serves every step).
+__global__ void timestep_embedding_kernel(const int* __restrict__ timesteps, const int* __restrict__ step, bf16* __restrict__ out,
+                                          int B, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i - b * half;
+  const float t = static_cast<float>(timesteps[*step]);
+  const float f = expf(-logf(10000.f) * static_cast<float>(k) / static_cast<float>(half));
+  out[b * dim + k] = __float2bfloat16_rn(cosf(t * f));
+  out[b * dim + half + k] = __float2bfloat16_rn(sinf(t * f));
+}
+int timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, cudaStream_t s) {
+  timestep_embedding_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, s>>>(timesteps, step, (bf16*)out, B, dim);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// One sampler update, fused: CFG combine (modeling_plugins.py:824-830) + scheduler.step (:833), then advance the device-side
+// step counter.  eps [2B,...] = [uncond | cond] (guidance > 1, as the reference's torch.cat order :774-784) or [B,...].
+// coef[step] = {sqrt(a_t), sqrt(1-a_t), c_x0, c_xt_or_eps, sigma}:
+//   DDIM (eta 0): x' = c_x0 * x0 + c_eps * eps             (c_x0 = sqrt(a_prev), c_eps = sqrt(1-a_prev), sigma = 0)
+//   DDPM        : x' = c_x0 * x0 + c_xt * x_t + sigma * z  (mode 1)
+__global__ void sampler_step_kernel(const float* __restrict__ eps, float* __restrict__ latents, const float* __restrict__ noise,
+                                    const float* __restrict__ coef, int* __restrict__ step, float guidance, int use_cfg, int mode,
+                                    long n) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int st = *step;
+  if (i < n) {
+    const float* c = coef + st * 5;
+    float e = eps[i];
+    if (use_cfg) e = e + guidance * (eps[n + i] - e);
+    const float xt = latents[i];
+    const float x0 = (xt - c[1] * e) / c[0];
+    float out = (mode == 0) ? c[2] * x0 + c[3] * e : c[2] * x0 + c[3] * xt + (noise ? c[4] * noise[static_cast<size_t>(st) * n + i] : 0.f);
+    latents[i] = out;
+  }
+}
+__global__ void advance_step_kernel(int* step) { *step += 1; }
+int sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance, int use_cfg,
+                 int mode, long n, cudaStream_t s) {
+  sampler_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(eps, latents, noise, coef, step, guidance, use_cfg, mode, n);
+  advance_step_kernel<<<1, 1, 0, s>>>(step);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+}  // namespace dllm

@@ -330,3 +330,120 @@ def zero_rows_(dst2d, idx):
     check(lib().dllm_zero_rows(_p(dst2d), _p(idx), idx.numel(), dst2d.shape[1], _stream()), "dllm_zero_rows")
     LAUNCHES.add(1)
     return dst2d
+
+
+# ----------------------------------------------------------------------------------------------- UNet ops (NHWC bf16)
+def attn_fwd_cross(q, k, v, scale=None):
+    """q [B,Sq,nh,d], k/v [B,Skv,nh,d] (views; k and v share a token stride). Non-causal. returns out [B,Sq,nh*d]."""
+    _chk_cuda(q, k, v)
+    B, Sq, nh, d = q.shape
+    Skv = k.shape[1]
+    assert k.stride(1) == v.stride(1) and q.stride(3) == 1 and k.stride(3) == 1 and q.stride(2) == d and k.stride(2) == d
+    out = torch.empty((B, Sq, nh * d), device=q.device, dtype=BF16)
+    lse = torch.empty((B, nh, Sq), device=q.device, dtype=torch.float32)
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    check(lib().dllm_attn_fwd_ex(_p(q), _p(k), _p(v), _p(out), _p(lse), 0, B, Sq, Skv, nh, d, q.stride(1), k.stride(1), nh * d, 0,
+                                 scale, _stream()), "dllm_attn_fwd_ex")
+    LAUNCHES.add(1)
+    return out
+
+
+def conv3x3(x_nhwc, w_k, bias=None, rowbias=None, residual=None):
+    """x [N,H,W,Cin] bf16 contiguous; w_k [Cout, 9*Cin] ((r,s,c)-major); returns [N,H,W,Cout]."""
+    _chk_cuda(x_nhwc, w_k, bias, rowbias, residual)
+    N, H, W, Cin = x_nhwc.shape
+    Cout = w_k.shape[0]
+    assert x_nhwc.is_contiguous() and w_k.is_contiguous() and w_k.shape[1] == 9 * Cin
+    y = torch.empty((N, H, W, Cout), device=x_nhwc.device, dtype=BF16)
+    if residual is not None:
+        assert residual.is_contiguous() and residual.numel() == y.numel()
+    if rowbias is not None:
+        assert rowbias.is_contiguous() and rowbias.shape == (N, Cout)
+    check(lib().dllm_conv3x3_nhwc(_p(x_nhwc), _p(w_k), _p(y), N, H, W, Cin, Cout, _p(bias), _p(rowbias), _p(residual), _stream()),
+          "dllm_conv3x3_nhwc")
+    LAUNCHES.add(1)
+    return y
+
+
+def groupnorm(x_nhwc, weight, bias, groups, eps, silu):
+    _chk_cuda(x_nhwc, weight, bias)
+    N, C = x_nhwc.shape[0], x_nhwc.shape[-1]
+    HW = x_nhwc.numel() // (N * C)
+    assert x_nhwc.is_contiguous()
+    wsb = lib().dllm_groupnorm_workspace_bytes(N, HW, groups)
+    ws = torch.empty(wsb, device=x_nhwc.device, dtype=torch.uint8)
+    y = torch.empty_like(x_nhwc)
+    check(lib().dllm_groupnorm_nhwc(_p(x_nhwc), _p(weight), _p(bias), _p(y), _p(ws), wsb, N, HW, C, groups, float(eps), int(silu),
+                                    _stream()), "dllm_groupnorm_nhwc")
+    LAUNCHES.add(3)
+    return y
+
+
+def geglu(x2d):
+    _chk_cuda(x2d)
+    T, I2 = x2d.shape
+    assert x2d.is_contiguous()
+    out = torch.empty((T, I2 // 2), device=x2d.device, dtype=BF16)
+    check(lib().dllm_geglu(_p(x2d), _p(out), T, I2 // 2, _stream()), "dllm_geglu")
+    LAUNCHES.add(1)
+    return out
+
+
+def upsample2x(x_nhwc):
+    N, H, W, C = x_nhwc.shape
+    y = torch.empty((N, 2 * H, 2 * W, C), device=x_nhwc.device, dtype=BF16)
+    check(lib().dllm_upsample2x_nhwc(_p(x_nhwc), _p(y), N, H, W, C, _stream()), "dllm_upsample2x_nhwc")
+    LAUNCHES.add(1)
+    return y
+
+
+def im2col_s2(x_nhwc):
+    N, H, W, C = x_nhwc.shape
+    out = torch.empty((N * (H // 2) * (W // 2), 9 * C), device=x_nhwc.device, dtype=BF16)
+    check(lib().dllm_im2col_s2_nhwc(_p(x_nhwc), _p(out), N, H, W, C, _stream()), "dllm_im2col_s2_nhwc")
+    LAUNCHES.add(1)
+    return out
+
+
+def concat_channels(a_nhwc, b_nhwc):
+    N, H, W, Ca = a_nhwc.shape
+    Cb = b_nhwc.shape[-1]
+    out = torch.empty((N, H, W, Ca + Cb), device=a_nhwc.device, dtype=BF16)
+    rows = N * H * W
+    check(lib().dllm_copy_cols(_p(a_nhwc), _p(out), rows, Ca, Ca + Cb, 0, _stream()), "dllm_copy_cols")
+    check(lib().dllm_copy_cols(_p(b_nhwc), _p(out), rows, Cb, Ca + Cb, Ca, _stream()), "dllm_copy_cols")
+    LAUNCHES.add(2)
+    return out
+
+
+def conv_in(latents_nchw_f32, weight, bias, batch_out):
+    Bs, Cin, H, W = latents_nchw_f32.shape
+    Cout = weight.shape[0]
+    y = torch.empty((batch_out, H, W, Cout), device=weight.device, dtype=BF16)
+    check(lib().dllm_conv_in(_p(latents_nchw_f32), _p(weight), _p(bias), _p(y), batch_out, Bs, Cin, H, W, Cout, _stream()), "dllm_conv_in")
+    LAUNCHES.add(1)
+    return y
+
+
+def conv_out(x_nhwc, weight, bias, out=None):
+    N, H, W, C = x_nhwc.shape
+    Cout = weight.shape[0]
+    y = torch.empty((N, Cout, H, W), device=x_nhwc.device, dtype=torch.float32) if out is None else out
+    check(lib().dllm_conv_out(_p(x_nhwc), _p(weight), _p(bias), _p(y), N, C, H, W, Cout, _stream()), "dllm_conv_out")
+    LAUNCHES.add(1)
+    return y
+
+
+def timestep_embedding(timesteps_i32, step_i32, B, dim):
+    out = torch.empty((B, dim), device=timesteps_i32.device, dtype=BF16)
+    check(lib().dllm_timestep_embedding(_p(timesteps_i32), _p(step_i32), _p(out), B, dim, _stream()), "dllm_timestep_embedding")
+    LAUNCHES.add(1)
+    return out
+
+
+def sampler_step_(eps_f32, latents_f32, coef_f32, step_i32, guidance, use_cfg, mode=0, noise=None):
+    n = latents_f32.numel()
+    check(lib().dllm_sampler_step(_p(eps_f32), _p(latents_f32), _p(noise), _p(coef_f32), _p(step_i32), float(guidance), int(use_cfg),
+                                  int(mode), n, _stream()), "dllm_sampler_step")
+    LAUNCHES.add(2)
+    return latents_f32

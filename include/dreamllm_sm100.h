@@ -103,6 +103,34 @@ int dllm_copy_rows(void* dst, const int* dst_idx, const void* src, const int* sr
 int dllm_segment_sum_rows(void* dst, const void* src, const int* seg, const int* rows, int Q, int H, void* stream);
 int dllm_zero_rows(void* dst, const int* idx, int R, int H, void* stream);
 
+/* ---- Stable-Diffusion-2.1 UNet denoising step (reference: StableDiffusionHead.pipeline, modeling_plugins.py:809-833;
+ * arithmetic = diffusers 0.24 UNet2DConditionModel / DDPMScheduler / DDIM, restated in oracle/unet_oracle.py). NHWC bf16. ---- */
+
+/* attention with separate kv length (UNet cross-attention on the dream-query conditioning: Skv = 64 / 77). */
+int dllm_attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int Sq,
+                     int Skv, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, void* stream);
+/* ResnetBlock2D / Upsample2D conv: implicit-GEMM 3x3 stride-1 pad-1 on tcgen05 (4-D TMA im2col, zero-fill padding).
+ * y = conv(x, w) + bias[c] + rowbias[n, c] (+ residual);  w is [Cout, 3, 3, Cin]. */
+int dllm_conv3x3_nhwc(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, const void* bias,
+                      const void* rowbias, const void* residual, void* stream);
+size_t dllm_groupnorm_workspace_bytes(int N, int HW, int G);
+int dllm_groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW,
+                        int C, int G, float eps, int silu, void* stream);
+int dllm_geglu(const void* in, void* out, int T, int I, void* stream);
+int dllm_upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);
+int dllm_im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, void* stream);
+int dllm_copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, void* stream);
+/* latents x_nchw [Bsrc,Cin,H,W] fp32 -> y_nhwc [B,H,W,Cout]; image n reads latents[n % Bsrc] (CFG duplication, plugins:811) */
+int dllm_conv_in(const float* x_nchw, const void* w, const void* bias, void* y_nhwc, int B, int Bsrc, int Cin, int H, int W, int Cout,
+                 void* stream);
+int dllm_conv_out(const void* x_nhwc, const void* w, const void* bias, float* y_nchw, int B, int C, int H, int W, int Cout, void* stream);
+/* timestep = timesteps[*step] (device-side schedule so one captured CUDA graph serves every step) */
+int dllm_timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, void* stream);
+/* fused CFG combine + DDIM (mode 0) / DDPM (mode 1) update; coef[step] = {sqrt(a_t), sqrt(1-a_t), c_x0, c_eps|c_xt, sigma};
+ * advances *step. */
+int dllm_sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance,
+                      int use_cfg, int mode, long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
