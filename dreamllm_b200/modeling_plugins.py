@@ -370,3 +370,108 @@ def splice_embeddings(embeds, image_features, dream_queries, plan):
 
 def gather_rows(x, rows):
     return _GatherRowsFn.apply(x, rows)
+
+
+# ------------------------------------------------------------------------------------------------ StableDiffusionHead
+class StableDiffusionHead(MultimodalHead):
+    """Mirror of reference `StableDiffusionHead` (modeling_plugins.py:335-850): same constructor arguments, `projector` /
+    `unet` attribute names (state-dict keys `projector.projector.weight`, `unet.*`), `pipeline(...)` signature.
+
+    Built this round: the sampler (`pipeline`, :672-850) on the native UNet with a CUDA-graph loop, `output_type="latent"`.
+    Not built yet: the training `forward` (:493-577: VAE encode + add_noise + UNet fwd + dgrad-only
+    backward + MSE) and VAE decode for `output_type != "latent"` — both raise NotImplementedError instead of silently
+    falling back to anything.
+    `diffusion_name_or_path` may be a dict of UNet config overrides for random init (no checkpoints exist in the sandbox);
+    a checkpoint directory is loaded through safetensors into the native module (identical key names).
+    """
+
+    def __init__(self, diffusion_name_or_path=None, projector_type="linear", projector_depth: int = 1,
+                 projector_name_or_path: str = None, pretrained_model_name_or_path: str = None, embed_hidden_size: int = 4096,
+                 drop_prob: float | None = None, noise_offset: float = 0.0, input_perturbation: float = 0.0,
+                 snr_gamma: float | None = None, resolution: int = 512, center_crop: bool = True, random_flip: bool = True,
+                 freeze_vae: bool = True, freeze_unet: bool = True, freeze_projector: bool = False, local_files_only: bool = False):
+        super().__init__()
+        from .unet import UNet2DConditionModel
+        self.save_model_name = "stable_diffusion_head"
+        self.diffusion_name_or_path = diffusion_name_or_path
+        self.projector_type, self.projector_depth = projector_type, projector_depth
+        self.projector_name_or_path = projector_name_or_path
+        self.pretrained_model_name_or_path = pretrained_model_name_or_path
+        self.embed_hidden_size = embed_hidden_size
+        self.drop_prob, self.noise_offset, self.input_perturbation, self.snr_gamma = drop_prob, noise_offset, input_perturbation, snr_gamma
+        self.resolution, self.center_crop, self.random_flip = resolution, center_crop, random_flip
+        self.freeze_vae, self.freeze_unet, self.freeze_projector = freeze_vae, freeze_unet, freeze_projector
+        if not freeze_unet:
+            raise ValueError("the native UNet is a frozen tower (freeze_unet=True in every shipped config)")
+        if isinstance(diffusion_name_or_path, str):
+            import glob
+            self.unet = UNet2DConditionModel()
+            files = glob.glob(os.path.join(diffusion_name_or_path, "unet", "*.safetensors"))
+            if not files:
+                raise FileNotFoundError(f"no unet/*.safetensors under {diffusion_name_or_path}")
+            from safetensors.torch import load_file
+            self.unet.load_state_dict(load_file(files[0]))
+        else:
+            self.unet = UNet2DConditionModel(diffusion_name_or_path)
+        projector_cfg = dict(projector=projector_type, freeze_projector=freeze_projector, depth=projector_depth,
+                             save_model_name=self.save_model_name, model_name_or_path=None)
+        self.projector = build_projector(projector_cfg, in_hidden_size=embed_hidden_size,
+                                         out_hidden_size=self.unet.cfg["cross_attention_dim"], bias=False)
+        self._init_weights(self.projector)
+        self.vae_scale_factor = 8
+        if pretrained_model_name_or_path is not None:
+            self.load_model(pretrained_model_name_or_path)
+        self.projector.load_model(projector_name_or_path)
+        self.unet.requires_grad_(False)
+        self.projector.requires_grad_(not freeze_projector)
+
+    @property
+    def processor(self):
+        return None
+
+    @property
+    def config(self):
+        return dict(diffusion_name_or_path=self.diffusion_name_or_path, pretrained_model_name_or_path=self.pretrained_model_name_or_path,
+                    embed_hidden_size=self.embed_hidden_size, drop_prob=self.drop_prob, noise_offset=self.noise_offset,
+                    input_perturbation=self.input_perturbation, snr_gamma=self.snr_gamma, resolution=self.resolution,
+                    freeze_vae=self.freeze_vae, freeze_unet=self.freeze_unet, freeze_projector=self.freeze_projector)
+
+    def fsdp_ignored_modules(self) -> list:
+        return [self.unet] + ([self.projector] if self.freeze_projector else [])
+
+    def save_model(self, output_dir: str):
+        torch.save(self.state_dict(), os.path.join(output_dir, f"{self.save_model_name}.bin"))
+
+    def load_model(self, output_dir: str):
+        f = os.path.join(output_dir, f"{self.save_model_name}.bin")
+        if os.path.isfile(f):
+            self.load_state_dict(torch.load(f, map_location="cpu"), strict=False)
+
+    def forward(self, images, encoder_hidden_states, u_encoder_hidden_states=None, dream_embeddings=None):
+        raise NotImplementedError("StableDiffusionHead.forward (VAE encode + UNet fwd/dgrad + MSE, reference :493-577) is the next "
+                                  "§8 row; this build has the sampler (`pipeline`) only")
+
+    @torch.no_grad()
+    def pipeline(self, height: int | None = None, width: int | None = None, num_inference_steps: int = 50, guidance_scale: float = 7.5,
+                 num_images_per_prompt: int | None = 1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
+                 negative_prompt_embeds=None, output_type: str | None = "latent", callback=None, callback_steps: int = 1,
+                 cross_attention_kwargs=None, guidance_rescale: float = 0.0, scheduler: str = "ddpm", use_cuda_graph: bool = True):
+        """reference :672-850.  `scheduler="ddpm"` is what the reference runs (its training DDPMScheduler, :379/:833);
+        `"ddim"` (eta 0) is BASELINE.json's C4 sampler."""
+        from .unet import DenoiseLoop
+        height = height or self.resolution
+        width = width or self.resolution
+        if height % 8 or width % 8:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        assert prompt_embeds is not None, "`prompt_embeds` must be provided by LLM."
+        if guidance_rescale > 0.0 or callback is not None or (num_images_per_prompt or 1) != 1:
+            raise NotImplementedError("guidance_rescale / callback / num_images_per_prompt>1 are not built")
+        if output_type != "latent":
+            raise NotImplementedError("VAE decode is SURVEY §8(f) row 1 (next); use output_type='latent'")
+        cond = self.projector(prompt_embeds)[-1]
+        if guidance_scale > 1.0:
+            assert negative_prompt_embeds is not None, "When using classifier free guidance, `negative_prompt_embeds` must be provided by LLM."
+            cond = torch.cat([self.projector(negative_prompt_embeds)[-1], cond])
+        loop = DenoiseLoop(self.unet, cond, num_inference_steps, guidance_scale, scheduler, latents=latents, height=height, width=width,
+                           use_cuda_graph=use_cuda_graph, generator=generator)
+        return loop.run()
