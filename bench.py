@@ -195,6 +195,8 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        from dreamllm_b200.ddp import configure_nccl_env
+        configure_nccl_env()
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = DreamLLMConfig.vicuna_7b(num_hidden_layers=args.layers) if args.layers != L else DreamLLMConfig.vicuna_7b()

@@ -60,6 +60,8 @@ _vp, _i, _l, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_fl
 SIGNATURES = {
     "dllm_version": (_i, []),
     "dllm_error_string": (ctypes.c_char_p, [_i]),
+    "dllm_set_reserved_sms": (_i, [_i]),
+    "dllm_get_reserved_sms": (_i, []),
     "dllm_gemm_bf16": (_i, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _i, _i, _i, _i, _vp]),
     "dllm_rmsnorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
     "dllm_rmsnorm_bwd_workspace_bytes": (_sz, [_i, _i]),

@@ -36,6 +36,8 @@ static void ensure_context(const void* dev_ptr) {
 extern "C" {
 
 int dllm_version(void) { return 100; }
+int dllm_set_reserved_sms(int n) { set_reserved_sms(n); return 0; }
+int dllm_get_reserved_sms(void) { return reserved_sms(); }
 
 const char* dllm_error_string(int code) {
   switch (code) {

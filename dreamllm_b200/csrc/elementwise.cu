@@ -553,8 +553,67 @@ __global__ void __launch_bounds__(kNormThreads) layernorm_fwd_kernel(const bf16*
     }
   }
 }
+// Small rows (UNet C = 320/640/1280, CLIP 1024): one WARP per row, no block barriers (the CTA-per-row version ran at 130 us
+// for 84 MB of traffic on the UNet's [131072, 320] LayerNorms — profiles/r01_unet_launch_list_summary.md).
+template <int VPL>  // 8-element vectors per lane
+__global__ void __launch_bounds__(256) layernorm_fwd_warp_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                                                 const bf16* __restrict__ b, bf16* __restrict__ y, int T, int H,
+                                                                 float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= T) return;
+  const int nvec = H >> 3;
+  const Vec8* xr = reinterpret_cast<const Vec8*>(x + row * H);
+  float xv[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      unpack8(xr[v], xv[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += xv[i][j];
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(H);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = xv[i][j] - mean; sq += d * d; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(H) + eps);
+  Vec8* yr = reinterpret_cast<Vec8*>(y + row * H);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float wf[8], bf[8], o[8];
+      unpack8(reinterpret_cast<const Vec8*>(w)[v], wf);
+      unpack8(reinterpret_cast<const Vec8*>(b)[v], bf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (xv[i][j] - mean) * rstd * wf[j] + bf[j];
+      yr[v] = pack8(o);
+    }
+  }
+}
+
 int layernorm_fwd(const void* x, const void* w, const void* b, void* y, int T, int H, float eps, cudaStream_t s) {
   if (H % 8 || H > kNormThreads * kNormMaxV * 8 || T <= 0) return DLLM_ERR_SHAPE;
+  const int nvec = H / 8;
+  if (nvec <= 32 * 6) {
+    const unsigned grid = static_cast<unsigned>((static_cast<long>(T) * 32 + 255) / 256);
+    if (nvec <= 64)
+      layernorm_fwd_warp_kernel<2><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, T, H, eps);
+    else if (nvec <= 128)
+      layernorm_fwd_warp_kernel<4><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, T, H, eps);
+    else
+      layernorm_fwd_warp_kernel<6><<<grid, 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, T, H, eps);
+    return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+  }
   layernorm_fwd_kernel<<<T, kNormThreads, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, (bf16*)y, H, eps);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }

@@ -15,6 +15,8 @@
 namespace dllm {
 
 int num_sms();
+void set_reserved_sms(int n);
+int reserved_sms();
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,
                  uint32_t box_rows, uint32_t box_cols);
 

@@ -223,30 +223,41 @@ int copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, c
 // ------------------------------------------------------------------------------------------------ conv_in / conv_out
 // conv_in: latents fp32 NCHW [B,Cin(=4),H,W] (rounded to bf16 as the bf16 pipeline feeds them) -> NHWC bf16 [B,H,W,Cout];
 // w [Cout, Cin, 3, 3] bf16 (diffusers layout).  One thread = one pixel x 8 output channels.
-__global__ void conv_in_kernel(const float* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ bias,
-                               bf16* __restrict__ y, int B, int Bsrc, int Cin, int H, int W, int Cout) {
+__global__ void __launch_bounds__(128) conv_in_kernel(const float* __restrict__ x, const bf16* __restrict__ w,
+                                                      const bf16* __restrict__ bias, bf16* __restrict__ y, int B, int Bsrc, int Cin,
+                                                      int H, int W, int Cout) {
+  // weights staged once per CTA as fp32 [Cin*9][Cout] so the inner loop reads 8 consecutive output channels
+  extern __shared__ float wsm[];
+  const int K = Cin * 9;
+  for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+    const int o = i % Cout, k = i / Cout;  // k = (c*3 + r)*3 + s, the conv weight's own flatten order
+    wsm[i] = __bfloat162float(w[static_cast<size_t>(o) * K + k]);
+  }
+  __syncthreads();
   const int nvec = Cout >> 3;
-  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long total = static_cast<long>(B) * H * W * nvec;
-  if (gid >= total) return;
-  const int v = static_cast<int>(gid % nvec);
-  long p = gid / nvec;
-  const int wx = static_cast<int>(p % W); p /= W;
-  const int hy = static_cast<int>(p % H);
-  const int n = static_cast<int>(p / H) % Bsrc;  // CFG: the same latents feed the uncond and cond halves (:811)
-  float acc[8];
+  for (long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; gid < total; gid += static_cast<long>(gridDim.x) * blockDim.x) {
+    const int v = static_cast<int>(gid % nvec);
+    long p = gid / nvec;
+    const int wx = static_cast<int>(p % W); p /= W;
+    const int hy = static_cast<int>(p % H);
+    const int nb = static_cast<int>(p / H);
+    const int n = nb % Bsrc;  // CFG: the same latents feed the uncond and cond halves (:811)
+    float acc[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) acc[j] = __bfloat162float(bias[v * 8 + j]);
-  for (int c = 0; c < Cin; ++c)
-    for (int r = 0; r < 3; ++r)
-      for (int sx = 0; sx < 3; ++sx) {
-        const int h = hy + r - 1, ww = wx + sx - 1;
-        if (h < 0 || h >= H || ww < 0 || ww >= W) continue;
-        const float xv = r16(x[((static_cast<size_t>(n) * Cin + c) * H + h) * W + ww]);
+    for (int j = 0; j < 8; ++j) acc[j] = __bfloat162float(bias[v * 8 + j]);
+    for (int c = 0; c < Cin; ++c)
+      for (int r = 0; r < 3; ++r)
+        for (int sx = 0; sx < 3; ++sx) {
+          const int h = hy + r - 1, ww = wx + sx - 1;
+          if (h < 0 || h >= H || ww < 0 || ww >= W) continue;
+          const float xv = r16(x[((static_cast<size_t>(n) * Cin + c) * H + h) * W + ww]);
+          const float* wk = wsm + ((c * 3 + r) * 3 + sx) * Cout + v * 8;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += xv * __bfloat162float(w[((static_cast<size_t>(v * 8 + j) * Cin + c) * 3 + r) * 3 + sx]);
-      }
-  reinterpret_cast<V8*>(y)[gid] = pk8(acc);
+          for (int j = 0; j < 8; ++j) acc[j] += xv * wk[j];
+        }
+    reinterpret_cast<V8*>(y)[gid] = pk8(acc);
+  }
 }
 // conv_out: NHWC bf16 [B,H,W,C] -> fp32 NCHW [B,Cout(=4),H,W]; w [Cout, C, 3, 3] bf16.  One warp = one pixel.
 template <int COUT>
@@ -282,8 +293,11 @@ __global__ void conv_out_kernel(const bf16* __restrict__ x, const bf16* __restri
 int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* y, int B, int Bsrc, int Cin, int H, int W,
                          int Cout, cudaStream_t s) {
   if (Cout % 8 || Bsrc <= 0) return DLLM_ERR_SHAPE;
-  const long total = static_cast<long>(B) * H * W * (Cout / 8);
-  conv_in_kernel<<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(x, (const bf16*)w, (const bf16*)bias, (bf16*)y, B, Bsrc, Cin, H, W, Cout);
+  const size_t smem = static_cast<size_t>(Cin) * 9 * Cout * sizeof(float);
+  if (smem > 96 * 1024) return DLLM_ERR_UNSUPPORTED;
+  static bool once = false;
+  if (!once) { cudaFuncSetAttribute(conv_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); once = true; }
+  conv_in_kernel<<<num_sms() * 4, 128, smem, s>>>(x, (const bf16*)w, (const bf16*)bias, (bf16*)y, B, Bsrc, Cin, H, W, Cout);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout,

@@ -14,6 +14,18 @@ import torch
 import torch.distributed as dist
 
 
+NCCL_CTAS = 2          # SM budget handed to the overlapped all-reduce
+RESERVED_SMS = 4       # = 2 CTA pairs (TPCs) kept out of the persistent GEMM grids while gradients are in flight
+
+
+def configure_nccl_env():
+    """Call BEFORE init_process_group: cap the all-reduce at NCCL_CTAS CTAs.  13.5 GB of bf16 gradients need only ~35 GB/s to
+    hide under a ~0.4 s backward, so a couple of SMs suffice; the persistent tcgen05 GEMMs keep the rest (see reserve below)."""
+    import os
+    os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
+    os.environ.setdefault("NCCL_MIN_CTAS", "1")
+
+
 class BucketedGradReducer:
     def __init__(self, params, bucket_cap_mb: float = 256.0, process_group=None, average: bool = True):
         self.group = process_group
@@ -42,6 +54,9 @@ class BucketedGradReducer:
         backend = dist.get_backend(process_group) if dist.is_initialized() else None
         self._use_avg_op = backend == "nccl"
         self.launched = 0
+        if backend == "nccl" and self.world > 1:
+            from ._lib import lib
+            lib().dllm_set_reserved_sms(RESERVED_SMS)
 
     def _make_bucket(self, plist):
         n = sum(p.numel() for p in plist)

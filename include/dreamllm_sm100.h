@@ -27,6 +27,9 @@ extern "C" {
 
 int dllm_version(void);
 const char* dllm_error_string(int code);
+/* Leave `n` SMs out of the persistent GEMM grids (for an overlapped NCCL all-reduce; data-parallel training only). */
+int dllm_set_reserved_sms(int n);
+int dllm_get_reserved_sms(void);
 
 /* Dense contraction on tcgen05 tensor cores: C[M,N] = op(A) * op(B), fp32 accumulate in TMEM.
  *   a_mn = 0: A is [M,K] row-major; a_mn = 1: A is stored [K,M] row-major (i.e. A^T, used for wgrad)
