@@ -69,7 +69,8 @@ __device__ __forceinline__ float epi_act(float x, int act) {
 template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-            const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi, ConvGeom cg) {
+            const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi, ConvGeom cg,
+            int* __restrict__ tile_counter) {
   using Cfg = GemmCfg<kCta>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kOutF32 = sizeof(OutT) == 4;
@@ -85,6 +86,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   uint64_t* tmem_full_bar = bars + 2 * kStages;
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  // dynamic tile scheduler: the leader's TMA thread draws tile ids from a global atomic counter and publishes them through a
+  // small smem ring to every role of the CTA pair.  A CTA that reaches an SM late (e.g. behind an overlapped NCCL all-reduce
+  // kernel) simply draws fewer tiles, instead of serialising a fixed 1/74th of the problem behind everyone else.
+  constexpr int kRing = 4;
+  uint64_t* ring_full = bars + 2 * kStages + 6;
+  uint64_t* ring_empty = ring_full + kRing;
+  uint32_t* tile_ring = reinterpret_cast<uint32_t*>(ring_empty + kRing);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -104,6 +112,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_init(&tmem_full_bar[i], 1);
       mbar_init(&tmem_empty_bar[i], 4 * kCta);  // one arrive per epilogue warp of every CTA in the pair
     }
+    for (int i = 0; i < kRing; ++i) {
+      mbar_init(&ring_full[i], 1);
+      mbar_init(&ring_empty[i], 5 * kCta);     // leader: MMA + 4 epilogue warps; peer: TMA thread + 4 epilogue warps
+    }
     fence_mbar_init();
   }
   if (warp_idx == 2) {
@@ -121,9 +133,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int num_n_tiles = (N + BN - 1) / BN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (K + BK - 1) / BK;
-  const int cluster_id = blockIdx.x / kCta;
-  const int num_clusters = gridDim.x / kCta;
   const int tiles_per_group = group_m * num_n_tiles;
+  const uint32_t ring_empty0_leader = (kCta == 2) ? mapa_shared(smem_u32(&ring_empty[0]), 0) : 0u;
+
+  // consumer side of the tile ring (every role except the leader's TMA thread)
+  auto ring_pop = [&](int& rslot, uint32_t& rphase, bool arrive) -> int {
+    if constexpr (kCta == 2) mbar_wait_cluster(&ring_full[rslot], rphase, 5); else mbar_wait(&ring_full[rslot], rphase, 5);
+    const int t = static_cast<int>(tile_ring[rslot]);
+    if (arrive) {
+      if constexpr (kCta == 2) mbar_arrive_cluster(ring_empty0_leader + rslot * 8); else mbar_arrive(&ring_empty[rslot]);
+    }
+    if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+    return t;
+  };
 
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
     const int g = tile / tiles_per_group;
@@ -139,7 +161,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int stage = 0;
     uint32_t phase = 0;
     const uint32_t full0_cluster = (kCta == 2) ? mapa_shared(smem_u32(&full_bar[0]), 0) : 0u;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+    int rslot = 0;
+    uint32_t rphase = 0;
+    while (true) {
+      int tile;
+      if (cta_rank == 0) {
+        mbar_wait(&ring_empty[rslot], rphase ^ 1, 6);
+        tile = atomicAdd(tile_counter, 1);
+        tile_ring[rslot] = static_cast<uint32_t>(tile);
+        if constexpr (kCta == 2) {
+          st_shared_cluster_u32(mapa_shared(smem_u32(&tile_ring[rslot]), 1), static_cast<uint32_t>(tile));
+          mbar_arrive_cluster(mapa_shared(smem_u32(&ring_full[rslot]), 1));
+        }
+        mbar_arrive(&ring_full[rslot]);
+        if (++rslot == kRing) { rslot = 0; rphase ^= 1; }
+      } else {
+        tile = ring_pop(rslot, rphase, true);
+      }
+      if (tile >= num_tiles) break;
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int m0 = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
@@ -208,7 +247,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    int rslot = 0;
+    uint32_t rphase = 0;
+    for (;; ++it) {
+      const int tile = ring_pop(rslot, rphase, true);
+      if (tile >= num_tiles) break;
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 2);
@@ -237,7 +280,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const uint32_t tmem_empty0_cluster = (kCta == 2) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     int it = 0;
     int buf = 0;
-    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++it) {
+    int rslot = 0;
+    uint32_t rphase = 0;
+    for (;; ++it) {
+      const int tile = ring_pop(rslot, rphase, false);
+      __syncwarp();
+      if (lane == 0) {
+        const int s_prev = (rslot == 0) ? kRing - 1 : rslot - 1;
+        if constexpr (kCta == 2) mbar_arrive_cluster(ring_empty0_leader + s_prev * 8); else mbar_arrive(&ring_empty[s_prev]);
+      }
+      if (tile >= num_tiles) break;
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int as = it & 1;
@@ -383,6 +435,23 @@ int num_sms() {
   return n;
 }
 
+// per-device ring of tile counters for the dynamic scheduler (one-time 4 KiB scratch; each launch zeroes its slot in stream order)
+static int* tile_counter_slot(cudaStream_t stream) {
+  constexpr int kSlots = 1024, kMaxDev = 16;
+  static int* base[kMaxDev] = {nullptr};
+  static unsigned next[kMaxDev] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= kMaxDev) return nullptr;
+  if (!base[dev]) {
+    if (cudaMalloc(&base[dev], kSlots * sizeof(int)) != cudaSuccess) return nullptr;
+    cudaMemset(base[dev], 0, kSlots * sizeof(int));
+  }
+  int* slot = base[dev] + (next[dev]++ % kSlots);
+  if (cudaMemsetAsync(slot, 0, sizeof(int), stream) != cudaSuccess) return nullptr;
+  return slot;
+}
+
 template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                        const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}) {
@@ -413,7 +482,9 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi, cg);
+  int* counter = tile_counter_slot(stream);
+  if (!counter) return DLLM_ERR_LAUNCH;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi, cg, counter);
   return e == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 

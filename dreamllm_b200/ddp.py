@@ -14,16 +14,19 @@ import torch
 import torch.distributed as dist
 
 
-NCCL_CTAS = 2          # SM budget handed to the overlapped all-reduce
-RESERVED_SMS = 4       # = 2 CTA pairs (TPCs) kept out of the persistent GEMM grids while gradients are in flight
+import os as _os
+
+NCCL_CTAS = int(_os.environ.get("DLLM_NCCL_CTAS", "0"))        # SM budget handed to the overlapped all-reduce (0 = leave NCCL alone)
+RESERVED_SMS = int(_os.environ.get("DLLM_RESERVED_SMS", "0"))  # CTA pairs kept out of the persistent GEMM grids while grads are in flight
 
 
 def configure_nccl_env():
-    """Call BEFORE init_process_group: cap the all-reduce at NCCL_CTAS CTAs.  13.5 GB of bf16 gradients need only ~35 GB/s to
-    hide under a ~0.4 s backward, so a couple of SMs suffice; the persistent tcgen05 GEMMs keep the rest (see reserve below)."""
+    """Optional knobs (off by default — measured on 2 x B200, ms/step: NCCL default + dynamic GEMM scheduler is best;
+    capping NCCL to 2 CTAs exposes the all-reduce: 799 ms; reserving SMs for it: 704 ms; see profiles/r01_ddp_n2_variants.md)."""
     import os
-    os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
-    os.environ.setdefault("NCCL_MIN_CTAS", "1")
+    if NCCL_CTAS > 0:
+        os.environ.setdefault("NCCL_MAX_CTAS", str(NCCL_CTAS))
+        os.environ.setdefault("NCCL_MIN_CTAS", "1")
 
 
 class BucketedGradReducer:
