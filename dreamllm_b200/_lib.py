@@ -94,7 +94,20 @@ SIGNATURES = {
     "dllm_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dllm_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dllm_timestep_embedding": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "dllm_timestep_embedding_batch": (_i, [_vp, _vp, _i, _i, _vp]),
     "dllm_sampler_step": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _l, _vp]),
+    "dllm_attn_bwd_ex": (_i, [_vp] * 11 + [_sz, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _i, _f, _vp]),
+    "dllm_groupnorm_stats": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _vp]),
+    "dllm_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dllm_groupnorm_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),
+    "dllm_layernorm_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
+    "dllm_geglu_bwd": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
+    "dllm_upsample2x_bwd_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dllm_col2im_s2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dllm_copy_cols2": (_i, [_vp, _vp, _l, _i, _i, _i, _i, _i, _vp]),
+    "dllm_conv_out_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dllm_add_noise": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp]),
+    "dllm_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _l, _vp]),
 }
 
 _lib = None

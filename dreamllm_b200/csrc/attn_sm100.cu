@@ -364,7 +364,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                      const __grid_constant__ CUtensorMap tdk, const __grid_constant__ CUtensorMap tdv,
                      const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ seqlens,
-                     int S, int S_pad, int nh, float scale, float scale_log2) {
+                     int S, int Skv, int S_pad, int nh, float scale, float scale_log2) {
   using L = BwdKVSmem<D>;
   constexpr int NCH = L::NCH;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -379,10 +379,11 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
-  const int len = seqlens ? min(seqlens[b], S) : S;
+  const int len = seqlens ? min(seqlens[b], S) : S;       // valid q rows
+  const int len_kv = seqlens ? len : Skv;                  // valid kv rows (Skv != S only for cross-attention)
   const int i_begin = kCausal ? (kv0 / 64) : 0;
   const int i_end = (len + 63) / 64;  // q rows >= len carry no gradient
-  const int n_it = (kv0 < len) ? max(i_end - i_begin, 0) : 0;
+  const int n_it = (kv0 < len_kv) ? max(i_end - i_begin, 0) : 0;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_bwd_dkdv: smem misaligned\n"); __trap(); }
@@ -472,7 +473,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
       tmem_ld_wait();
       // staging buffer `st` was last read by the dV/dK MMAs of iteration it-2
       if (it >= 2) mbar_wait(&acc_done[st], ((it >> 1) & 1) ^ 1, 25);
-      const bool full_tile = (qc0 + 31 < len) && (kv0 + 127 < len) && (!kCausal || kv0 + 127 <= qc0);
+      const bool full_tile = (qc0 + 31 < len) && (kv0 + 127 < len_kv) && (!kCausal || kv0 + 127 <= qc0);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         float p[8], ds[8];
@@ -480,7 +481,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         for (int e = 0; e < 8; ++e) {
           const int c = jj * 8 + e;
           const int qi = qc0 + c;
-          const bool ok = full_tile || ((qi < len) && (kv_row < len) && (!kCausal || kv_row <= qi));
+          const bool ok = full_tile || ((qi < len) && (kv_row < len_kv) && (!kCausal || kv_row <= qi));
           const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]) : 0.f;
           p[e] = pe;
           ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) * scale : 0.f;
@@ -541,8 +542,8 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                    const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
                    const __grid_constant__ CUtensorMap tdq, const float* __restrict__ lse2,
-                   const float* __restrict__ delta, const int* __restrict__ seqlens, int S, int S_pad, int nh, float scale,
-                   float scale_log2) {
+                   const float* __restrict__ delta, const int* __restrict__ seqlens, int S, int Skv, int S_pad, int nh,
+                   float scale, float scale_log2) {
   using L = BwdQSmem<D>;
   constexpr int NCH = L::NCH;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -558,7 +559,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int len = seqlens ? min(seqlens[b], S) : S;
-  const int kv_end = kCausal ? min(len, q0 + 128) : len;
+  const int len_kv = seqlens ? len : Skv;
+  const int kv_end = kCausal ? min(len_kv, q0 + 128) : len_kv;
   const int n_kv = (q0 < len) ? (kv_end + 63) / 64 : 0;
 
   if (threadIdx.x == 0) {
@@ -635,7 +637,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       tmem_ld32(tmem_dP + lane_off + st * 64 + half * 32, dv);
       tmem_ld_wait();
       if (j >= 2) mbar_wait(&acc_done[st], ((j >> 1) & 1) ^ 1, 35);
-      const bool full_tile = (q0 + 127 < len) && (kc0 + 31 < len) && (!kCausal || kc0 + 31 <= q0);
+      const bool full_tile = (q0 + 127 < len) && (kc0 + 31 < len_kv) && (!kCausal || kc0 + 31 <= q0);
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj) {
         float ds[8];
@@ -643,7 +645,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         for (int e = 0; e < 8; ++e) {
           const int c = jj * 8 + e;
           const int kvi = kc0 + c;
-          const bool ok = full_tile || (row_ok && (kvi < len) && (!kCausal || kvi <= q_row));
+          const bool ok = full_tile || (row_ok && (kvi < len_kv) && (!kCausal || kvi <= q_row));
           const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse) : 0.f;
           ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) * scale : 0.f;
         }
@@ -732,7 +734,7 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
                       const CUtensorMap& tv64, const CUtensorMap& tv128, const CUtensorMap& tdo64,
                       const CUtensorMap& tdo128, const CUtensorMap& tdq, const CUtensorMap& tdk, const CUtensorMap& tdv,
                       const bf16* dout, const bf16* out, const float* lse, float* delta, float* lse2, const int* seqlens,
-                      int B, int S, int nh, long ld_o, float scale, cudaStream_t st) {
+                      int B, int S, int Skv, int nh, long ld_o, float scale, cudaStream_t st) {
   auto k1 = attn_bwd_dkdv_kernel<D, C>;
   auto k2 = attn_bwd_dq_kernel<D, C>;
   static bool once = false;
@@ -744,39 +746,47 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
   const long warps = static_cast<long>(B) * Sp * nh;
   attn_bwd_prep_kernel<D><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(dout, out, lse, delta, lse2, B, S,
                                                                                            Sp, nh, ld_o);
-  dim3 grid((S + 127) / 128, nh, B);
-  k1<<<grid, kBwdThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Sp, nh, scale,
-                                                       scale * kLog2e);
-  k2<<<grid, kBwdThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, Sp, nh, scale,
-                                                      scale * kLog2e);
+  dim3 grid_kv((Skv + 127) / 128, nh, B), grid_q((S + 127) / 128, nh, B);
+  k1<<<grid_kv, kBwdThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Skv, Sp, nh,
+                                                          scale, scale * kLog2e);
+  k2<<<grid_q, kBwdThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, Skv, Sp, nh, scale,
+                                                        scale * kLog2e);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
 int attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
              void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int S, int nh, int d,
              long ld_qkv, long ld_o, long ld_dqkv, int causal, float scale, cudaStream_t st) {
-  if (B <= 0 || S <= 0 || nh <= 0) return DLLM_ERR_SHAPE;
+  return attn_bwd_ex(dout, q, k, v, out, lse, dq, dk, dv, seqlens, workspace, workspace_bytes, B, S, S, nh, d, ld_qkv, ld_qkv, ld_o,
+                     ld_dqkv, ld_dqkv, causal, scale, st);
+}
+
+int attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
+                void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int S, int Skv, int nh,
+                int d, long ld_q, long ld_kv, long ld_o, long ld_dq, long ld_dkv, int causal, float scale, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || Skv <= 0 || nh <= 0) return DLLM_ERR_SHAPE;
   if (d != 128 && d != 64) return DLLM_ERR_UNSUPPORTED;
+  if (S != Skv && (causal || seqlens)) return DLLM_ERR_UNSUPPORTED;
   if (workspace_bytes < attn_bwd_workspace(B, S, nh, d)) return DLLM_ERR_SHAPE;
   float* delta = static_cast<float*>(workspace);
   float* lse2 = delta + static_cast<size_t>(B) * s_pad(S) * nh;
   CUtensorMap tq64, tq128, tk64, tk128, tv64, tv128, tdo64, tdo128, tdq, tdk, tdv;
   int rc;
   const int C = nh * d;
-  if ((rc = make_tmap_bsc(&tq64, q, B, S, C, ld_qkv, 64))) return rc;
-  if ((rc = make_tmap_bsc(&tq128, q, B, S, C, ld_qkv, 128))) return rc;
-  if ((rc = make_tmap_bsc(&tk64, k, B, S, C, ld_qkv, 64))) return rc;
-  if ((rc = make_tmap_bsc(&tk128, k, B, S, C, ld_qkv, 128))) return rc;
-  if ((rc = make_tmap_bsc(&tv64, v, B, S, C, ld_qkv, 64))) return rc;
-  if ((rc = make_tmap_bsc(&tv128, v, B, S, C, ld_qkv, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tq64, q, B, S, C, ld_q, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tq128, q, B, S, C, ld_q, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tk64, k, B, Skv, C, ld_kv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tk128, k, B, Skv, C, ld_kv, 128))) return rc;
+  if ((rc = make_tmap_bsc(&tv64, v, B, Skv, C, ld_kv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tv128, v, B, Skv, C, ld_kv, 128))) return rc;
   if ((rc = make_tmap_bsc(&tdo64, dout, B, S, C, ld_o, 64))) return rc;
   if ((rc = make_tmap_bsc(&tdo128, dout, B, S, C, ld_o, 128))) return rc;
-  if ((rc = make_tmap_bsc(&tdq, dq, B, S, C, ld_dqkv, 32))) return rc;
-  if ((rc = make_tmap_bsc(&tdk, dk, B, S, C, ld_dqkv, 32))) return rc;
-  if ((rc = make_tmap_bsc(&tdv, dv, B, S, C, ld_dqkv, 32))) return rc;
+  if ((rc = make_tmap_bsc(&tdq, dq, B, S, C, ld_dq, 32))) return rc;
+  if ((rc = make_tmap_bsc(&tdk, dk, B, Skv, C, ld_dkv, 32))) return rc;
+  if ((rc = make_tmap_bsc(&tdv, dv, B, Skv, C, ld_dkv, 32))) return rc;
 #define DLLM_BWD(DD, CC)                                                                                             \
   return launch_bwd<DD, CC>(tq64, tq128, tk64, tk128, tv64, tv128, tdo64, tdo128, tdq, tdk, tdv, (const bf16*)dout,     \
-                            (const bf16*)out, lse, delta, lse2, seqlens, B, S, nh, ld_o, scale, st)
+                            (const bf16*)out, lse, delta, lse2, seqlens, B, S, Skv, nh, ld_o, scale, st)
   if (d == 128) { if (causal) DLLM_BWD(128, true); else DLLM_BWD(128, false); }
   if (causal) DLLM_BWD(64, true); else DLLM_BWD(64, false);
 #undef DLLM_BWD

@@ -188,9 +188,68 @@ int dllm_timestep_embedding(const int* timesteps, const int* step, void* out, in
   ensure_context(out);
   return timestep_embedding(timesteps, step, out, B, dim, S(stream));
 }
+int dllm_timestep_embedding_batch(const int* t, void* out, int B, int dim, void* stream) {
+  ensure_context(out);
+  return timestep_embedding_batch(t, out, B, dim, S(stream));
+}
 int dllm_sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance,
                       int use_cfg, int mode, long n, void* stream) {
   ensure_context(eps);
   return sampler_step(eps, latents, noise, coef, step, guidance, use_cfg, mode, n, S(stream));
 }
+int dllm_attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
+                     void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int Sq, int Skv, int nh,
+                     int d, long ld_q, long ld_kv, long ld_o, long ld_dq, long ld_dkv, int causal, float scale, void* stream) {
+  ensure_context(dout);
+  return attn_bwd_ex(dout, q, k, v, out, lse, dq, dk, dv, seqlens, workspace, workspace_bytes, B, Sq, Skv, nh, d, ld_q, ld_kv, ld_o,
+                     ld_dq, ld_dkv, causal, scale, S(stream));
+}
+int dllm_groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, void* stream) {
+  ensure_context(x);
+  return groupnorm_stats(x, stats, workspace, ws_bytes, N, HW, C, G, eps, S(stream));
+}
+int dllm_groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
+                         void* stream) {
+  ensure_context(x);
+  return groupnorm_apply(x, w, b, stats, y, N, HW, C, G, silu, S(stream));
+}
+int dllm_groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void* b, const float* stats, const void* dres, void* dx,
+                            void* workspace, size_t ws_bytes, int N, int HW, int C, int G, int silu, void* stream) {
+  ensure_context(dy);
+  return groupnorm_bwd_nhwc(dy, x, w, b, stats, dres, dx, workspace, ws_bytes, N, HW, C, G, silu, S(stream));
+}
+int dllm_layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, int T, int H, float eps, void* stream) {
+  ensure_context(dy);
+  return layernorm_bwd(dy, x, w, dres, dx, T, H, eps, S(stream));
+}
+int dllm_geglu_bwd(const void* dout, const void* in, void* din, int T, int I, void* stream) {
+  ensure_context(dout);
+  return geglu_bwd(dout, in, din, T, I, S(stream));
+}
+int dllm_upsample2x_bwd_nhwc(const void* dy, void* dx, int N, int H, int W, int C, void* stream) {
+  ensure_context(dy);
+  return upsample2x_bwd_nhwc(dy, dx, N, H, W, C, S(stream));
+}
+int dllm_col2im_s2_nhwc(const void* dcols, void* dx, int N, int H, int W, int C, void* stream) {
+  ensure_context(dcols);
+  return col2im_s2_nhwc(dcols, dx, N, H, W, C, S(stream));
+}
+int dllm_copy_cols2(const void* src, void* dst, long rows, int Cs, int Cd, int scol0, int dcol0, int ncols, void* stream) {
+  ensure_context(src);
+  return copy_cols2(src, dst, rows, Cs, Cd, scol0, dcol0, ncols, S(stream));
+}
+int dllm_conv_out_bwd(const float* dy, const void* w, void* dx, int B, int C, int H, int W, int Cout, void* stream) {
+  ensure_context(dy);
+  return conv_out_bwd(dy, w, dx, B, C, H, W, Cout, S(stream));
+}
+int dllm_add_noise(const float* x0, const float* noise, const int* t, const float* alphas_cumprod, float* out, int B, long per_sample,
+                   void* stream) {
+  ensure_context(x0);
+  return add_noise(x0, noise, t, alphas_cumprod, out, B, per_sample, S(stream));
+}
+int dllm_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, void* stream) {
+  ensure_context(pred);
+  return mse_fwd_bwd(pred, target, loss, dpred, n, S(stream));
+}
+
 }  // extern "C"

@@ -41,10 +41,27 @@ int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* 
 int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout,
                           cudaStream_t s);
 int timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, cudaStream_t s);
+int timestep_embedding_batch(const int* t, void* out, int B, int dim, cudaStream_t s);
 int sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance, int use_cfg,
                  int mode, long n, cudaStream_t s);
 size_t attn_bwd_workspace(int B, int S, int nh, int d);
 int attn_bwd(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
              void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int S, int nh, int d,
              long ld_qkv, long ld_o, long ld_dqkv, int causal, float scale, cudaStream_t s);
+int attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
+                void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int S, int Skv, int nh,
+                int d, long ld_q, long ld_kv, long ld_o, long ld_dq, long ld_dkv, int causal, float scale, cudaStream_t s);
+int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void* b, const float* stats, const void* dres, void* dx,
+                       void* workspace, size_t ws_bytes, int N, int HW, int C, int G, int silu, cudaStream_t s);
+int groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, cudaStream_t s);
+int groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
+                    cudaStream_t s);
+int layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, int T, int H, float eps, cudaStream_t s);
+int geglu_bwd(const void* dout, const void* in, void* din, int T, int I, cudaStream_t s);
+int upsample2x_bwd_nhwc(const void* dy, void* dx, int N, int H, int W, int C, cudaStream_t s);
+int col2im_s2_nhwc(const void* dcols, void* dx, int N, int H, int W, int C, cudaStream_t s);
+int copy_cols2(const void* src, void* dst, long rows, int Cs, int Cd, int scol0, int dcol0, int ncols, cudaStream_t s);
+int conv_out_bwd(const float* dy, const void* w, void* dx, int B, int C, int H, int W, int Cout, cudaStream_t s);
+int add_noise(const float* x0, const float* noise, const int* t, const float* ac, float* out, int B, long per_sample, cudaStream_t s);
+int mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, cudaStream_t s);
 }  // namespace dllm

