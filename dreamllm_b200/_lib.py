@@ -89,7 +89,7 @@ SIGNATURES = {
     "dllm_groupnorm_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _i, _vp]),
     "dllm_geglu": (_i, [_vp, _vp, _i, _i, _vp]),
     "dllm_upsample2x_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
-    "dllm_im2col_s2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
+    "dllm_im2col_s2_nhwc": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dllm_copy_cols": (_i, [_vp, _vp, _l, _i, _i, _i, _vp]),
     "dllm_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dllm_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
@@ -108,6 +108,8 @@ SIGNATURES = {
     "dllm_conv_out_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dllm_add_noise": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp]),
     "dllm_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _l, _vp]),
+    "dllm_softmax_rows": (_i, [_vp, _l, _i, _f, _vp]),
+    "dllm_vae_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _l, _f, _vp]),
 }
 
 _lib = None

@@ -167,9 +167,9 @@ int dllm_upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, voi
   ensure_context(x);
   return upsample2x_nhwc(x, y, N, H, W, C, S(stream));
 }
-int dllm_im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, void* stream) {
+int dllm_im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, int pad, void* stream) {
   ensure_context(x);
-  return im2col_s2_nhwc(x, out, N, H, W, C, S(stream));
+  return im2col_s2_nhwc(x, out, N, H, W, C, pad, S(stream));
 }
 int dllm_copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, void* stream) {
   ensure_context(src);
@@ -250,6 +250,16 @@ int dllm_add_noise(const float* x0, const float* noise, const int* t, const floa
 int dllm_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, void* stream) {
   ensure_context(pred);
   return mse_fwd_bwd(pred, target, loss, dpred, n, S(stream));
+}
+
+int dllm_softmax_rows(void* x, long rows, int cols, float scale, void* stream) {
+  ensure_context(x);
+  return softmax_rows(x, rows, cols, scale, S(stream));
+}
+int dllm_vae_sample(const float* h, const void* wq, const void* bq, const float* z, float* out, int B, int L, long plane, float scaling,
+                    void* stream) {
+  ensure_context(h);
+  return vae_sample(h, wq, bq, z, out, B, L, plane, scaling, S(stream));
 }
 
 }  // extern "C"

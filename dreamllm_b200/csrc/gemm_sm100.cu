@@ -195,8 +195,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           cv_c = (kb - tap * cg.cpt) * BK;
           const int r = tap / 3, sx = tap - 3 * r;
           cv_n = m0 / cg.HW;
-          cv_h = (m0 - cv_n * cg.HW) / cg.W + r - 1;
-          cv_w = sx - 1;
+          const int rem = m0 - cv_n * cg.HW;
+          const int h0 = rem / cg.W;
+          cv_h = h0 + r - 1;
+          cv_w = (rem - h0 * cg.W) + sx - 1;   // non-zero only for planes wider than one 128-pixel tile
         }
         if constexpr (kCta == 1) {
           mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
@@ -552,9 +554,10 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int Nimg, int H, in
 // y[n,h,w,:] = conv3x3(x, w) + bias + rowbias[n] (+ residual);  x NHWC [Nimg,H,W,Cin], w [Cout, 3,3,Cin] (K-major), y NHWC
 int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, const void* bias,
                  const void* rowbias, const void* residual, cudaStream_t stream) {
-  if (Nimg <= 0 || Cin % 64 || Cout % 8 || W > 128 || (128 % W)) return DLLM_ERR_SHAPE;
+  if (Nimg <= 0 || Cin % 64 || Cout % 8) return DLLM_ERR_SHAPE;
+  if (W > 128 ? (W % 128) : (128 % W)) return DLLM_ERR_SHAPE;
   const int HW = H * W;
-  int Wb = W, Hb = 128 / W, Nb = 1;
+  int Wb = W > 128 ? 128 : W, Hb = W > 128 ? 1 : 128 / W, Nb = 1;
   if (Hb > H) {  // small planes: the 128-pixel tile spans several whole images
     if (Hb % H) return DLLM_ERR_SHAPE;
     Nb = Hb / H;

@@ -34,7 +34,7 @@ int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* w
                    int G, float eps, int silu, cudaStream_t s);
 int geglu(const void* in, void* out, int T, int I, cudaStream_t s);
 int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStream_t s);
-int im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
+int im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, int pad, cudaStream_t s);
 int copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, cudaStream_t s);
 int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* y, int B, int Bsrc, int Cin, int H, int W,
                          int Cout, cudaStream_t s);
@@ -64,4 +64,7 @@ int copy_cols2(const void* src, void* dst, long rows, int Cs, int Cd, int scol0,
 int conv_out_bwd(const float* dy, const void* w, void* dx, int B, int C, int H, int W, int Cout, cudaStream_t s);
 int add_noise(const float* x0, const float* noise, const int* t, const float* ac, float* out, int B, long per_sample, cudaStream_t s);
 int mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, cudaStream_t s);
+int softmax_rows(void* x, long rows, int cols, float scale, cudaStream_t s);
+int vae_sample(const float* h, const void* wq, const void* bq, const float* z, float* out, int B, int L, long plane, float scaling,
+               cudaStream_t s);
 }  // namespace dllm

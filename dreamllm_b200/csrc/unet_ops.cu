@@ -175,7 +175,7 @@ __global__ void upsample2x_kernel(const bf16* __restrict__ x, bf16* __restrict__
   reinterpret_cast<uint4*>(y)[gid] = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + ho / 2) * W + wo / 2) * C)[v];
 }
 // im2col for the stride-2 3x3 pad-1 Downsample2D conv: out [N*Ho*Wo, 9*C], k = (r, s, c)
-__global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C) {
+__global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ out, int N, int H, int W, int C, int pad) {
   const int nvec = C >> 3;
   const int Ho = H / 2, Wo = W / 2;
   const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -187,7 +187,8 @@ __global__ void im2col_s2_kernel(const bf16* __restrict__ x, bf16* __restrict__ 
   const int wo = static_cast<int>(p % Wo); p /= Wo;
   const int ho = static_cast<int>(p % Ho);
   const int n = static_cast<int>(p / Ho);
-  const int h = 2 * ho + tap / 3 - 1, w = 2 * wo + tap % 3 - 1;
+  // pad = 1: UNet Downsample2D (symmetric padding 1); pad = 0: VAE downsample (F.pad (0,1,0,1) then padding 0)
+  const int h = 2 * ho + tap / 3 - pad, w = 2 * wo + tap % 3 - pad;
   uint4 val = make_uint4(0, 0, 0, 0);
   if (h >= 0 && h < H && w >= 0 && w < W) val = reinterpret_cast<const uint4*>(x + ((static_cast<size_t>(n) * H + h) * W + w) * C)[v];
   reinterpret_cast<uint4*>(out)[gid] = val;
@@ -207,10 +208,10 @@ int upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, cudaStre
   upsample2x_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)x, (bf16*)y, N, H, W, C);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
-int im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s) {
+int im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, int pad, cudaStream_t s) {
   if (C % 8 || H % 2 || W % 2) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(N) * (H / 2) * (W / 2) * 9 * (C / 8);
-  im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)x, (bf16*)out, N, H, W, C);
+  im2col_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)x, (bf16*)out, N, H, W, C, pad);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, cudaStream_t s) {
@@ -302,9 +303,12 @@ int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* 
 }
 int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout,
                           cudaStream_t s) {
-  if (Cout != 4) return DLLM_ERR_UNSUPPORTED;
+  if (Cout != 4 && Cout != 8) return DLLM_ERR_UNSUPPORTED;
   const long warps = static_cast<long>(B) * H * W;
-  conv_out_kernel<4><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, y, B, C, H, W);
+  if (Cout == 4)
+    conv_out_kernel<4><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, y, B, C, H, W);
+  else
+    conv_out_kernel<8><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, y, B, C, H, W);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
@@ -770,6 +774,84 @@ __global__ void mse_fwd_bwd_kernel(const float* __restrict__ pred, const float* 
 }
 int mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, cudaStream_t s) {
   mse_fwd_bwd_kernel<<<1, 1024, 0, s>>>(pred, target, loss, dpred, n);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+
+// ================================================================================================ VAE encoder helpers
+// AutoencoderKL mid-block attention is ONE head of dim 512: run as GEMM -> row softmax -> GEMM.
+// In-place row softmax of bf16 scores with fp32 math: p = softmax(x * scale).
+__global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ x, int cols, float scale) {
+  __shared__ float red[8];
+  bf16* row = x + static_cast<size_t>(blockIdx.x) * cols;
+  const int nvec = cols >> 3;
+  float m = -INFINITY;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    float f[8];
+    up8(reinterpret_cast<const V8*>(row)[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m = fmaxf(m, f[j]);
+  }
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = red[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+  __syncthreads();
+  float sum = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    float f[8];
+    up8(reinterpret_cast<const V8*>(row)[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sum += expf((f[j] - m) * scale);
+  }
+  sum = warp_sum(sum);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sum += red[i];
+  const float inv = 1.f / sum;
+  for (int v = threadIdx.x; v < nvec; v += 256) {
+    float f[8];
+    up8(reinterpret_cast<const V8*>(row)[v], f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = expf((f[j] - m) * scale) * inv;
+    reinterpret_cast<V8*>(row)[v] = pk8(f);
+  }
+}
+int softmax_rows(void* x, long rows, int cols, float scale, cudaStream_t s) {
+  if (cols % 8 || rows <= 0) return DLLM_ERR_SHAPE;
+  softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, s>>>((bf16*)x, cols, scale);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+// quant_conv (1x1, 2L -> 2L) + DiagonalGaussianDistribution.sample() + scaling_factor (modeling_plugins.py:511-512):
+//   moments = Wq h + bq; mean, logvar = chunk(moments); latents = (mean + exp(0.5 * clamp(logvar, -30, 20)) * z) * scaling
+__global__ void vae_sample_kernel(const float* __restrict__ h, const bf16* __restrict__ wq, const bf16* __restrict__ bq,
+                                  const float* __restrict__ z, float* __restrict__ out, int B, int L, long plane, float scaling) {
+  const long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= static_cast<long>(B) * plane) return;
+  const int n = static_cast<int>(i / plane);
+  const long p = i - n * plane;
+  float hv[16];
+  for (int c = 0; c < 2 * L; ++c) hv[c] = h[(static_cast<size_t>(n) * 2 * L + c) * plane + p];
+  for (int o = 0; o < L; ++o) {
+    float mean = __bfloat162float(bq[o]), logvar = __bfloat162float(bq[L + o]);
+    for (int c = 0; c < 2 * L; ++c) {
+      mean += __bfloat162float(wq[o * 2 * L + c]) * hv[c];
+      logvar += __bfloat162float(wq[(L + o) * 2 * L + c]) * hv[c];
+    }
+    mean = r16(mean);
+    logvar = fminf(fmaxf(r16(logvar), -30.f), 20.f);
+    out[(static_cast<size_t>(n) * L + o) * plane + p] = (mean + expf(0.5f * logvar) * z[(static_cast<size_t>(n) * L + o) * plane + p]) * scaling;
+  }
+}
+int vae_sample(const float* h, const void* wq, const void* bq, const float* z, float* out, int B, int L, long plane, float scaling,
+               cudaStream_t s) {
+  if (L > 8) return DLLM_ERR_UNSUPPORTED;
+  const long total = static_cast<long>(B) * plane;
+  vae_sample_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(h, (const bf16*)wq, (const bf16*)bq, z, out, B, L, plane, scaling);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 

@@ -594,7 +594,7 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
     def forward(self, input_ids=None, images=None, images_dm=None, attention_mask=None, position_ids=None,
                 past_key_values=None, inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None, attention_mask_has_padding=None, input_ids_cpu=None,
-                splice_plan=None, **kwargs):
+                splice_plan=None, sd_kwargs=None, **kwargs):
         """reference :1353-1509.  Comprehension path (images -> CLIP -> splice -> LM loss) is complete; the creation
         path returns the gathered dream-query conditioning in `additional_log_info["dream_conditioning"]` — the
         StableDiffusionHead (UNet) that consumes it (:1441) is the next §8 row."""
@@ -616,9 +616,16 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
         else:
             logits = ops.linear(h2, self.lm_head.weight).view(B, S, -1).float()
         info = {"lm_loss": lm_loss}
+        vm_loss = 0.0
         if images_dm is not None:
             from .modeling_plugins import gather_rows
             plan = self.model._last_splice_plan
             Q = self.model.dream_embedding.embed_len
-            info["dream_conditioning"] = gather_rows(hidden, plan.cond_rows).view(plan.n_dreams, Q, H)   # (:1401-1418)
+            enc_h = gather_rows(hidden, plan.cond_rows).view(plan.n_dreams, Q, H)                        # (:1401-1418)
+            info["dream_conditioning"] = enc_h
+            head = getattr(self, "stable_diffusion_head", None)
+            if head is not None and self.training:
+                vm_loss = head(images_dm[: plan.n_dreams], enc_h, **(sd_kwargs or {}))                   # (:1441)
+                loss = vm_loss * self.loss_weight_vm + (loss if loss is not None else 0.0)               # (:1486-1488)
+        info["vm_loss"] = vm_loss
         return CausalLMOutputWithPast(loss=loss, logits=logits, hidden_states=out.hidden_states, additional_log_info=info)

@@ -373,14 +373,41 @@ def gather_rows(x, rows):
 
 
 # ------------------------------------------------------------------------------------------------ StableDiffusionHead
+class _DiffusionLossFn(torch.autograd.Function):
+    """loss = mse(unet(noisy, t, cond), target).  The UNet is frozen, so the only gradient is d(loss)/d(cond); it is computed eagerly
+    (forward tape -> dgrad-only backward) so the UNet activations are freed before the LLM backward starts."""
+
+    @staticmethod
+    def forward(ctx, cond, unet, noisy, t32, target):
+        need = cond.requires_grad and torch.is_grad_enabled()
+        with torch.no_grad():
+            if need:
+                eps, tape = unet.forward_train(noisy, t32, cond)
+                loss, deps = ops.mse_fwd_bwd(eps, target)
+                dcond = unet.backward_cond(deps, tape).to(cond.dtype)
+                del tape
+                ctx.save_for_backward(dcond)
+            else:
+                eps, _ = unet.forward_train(noisy, t32, cond)
+                loss, _ = ops.mse_fwd_bwd(eps, target)
+        ctx.has_grad = need
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        if not ctx.has_grad:
+            return None, None, None, None, None
+        (dcond,) = ctx.saved_tensors
+        return dcond * g.to(dcond.dtype), None, None, None, None
+
+
 class StableDiffusionHead(MultimodalHead):
     """Mirror of reference `StableDiffusionHead` (modeling_plugins.py:335-850): same constructor arguments, `projector` /
     `unet` attribute names (state-dict keys `projector.projector.weight`, `unet.*`), `pipeline(...)` signature.
 
-    Built this round: the sampler (`pipeline`, :672-850) on the native UNet with a CUDA-graph loop, `output_type="latent"`.
-    Not built yet: the training `forward` (:493-577: VAE encode + add_noise + UNet fwd + dgrad-only
-    backward + MSE) and VAE decode for `output_type != "latent"` — both raise NotImplementedError instead of silently
-    falling back to anything.
+    Built: the training `forward` (:493-577: VAE encode -> add_noise -> UNet fwd + dgrad-only backward -> MSE) and the sampler
+    (`pipeline`, :672-850) on the native UNet with a CUDA-graph loop, `output_type="latent"`.
+    Not built yet: VAE *decode* for `output_type != "latent"` (raises NotImplementedError — no silent fallback).
     `diffusion_name_or_path` may be a dict of UNet config overrides for random init (no checkpoints exist in the sandbox);
     a checkpoint directory is loaded through safetensors into the native module (identical key names).
     """
@@ -392,6 +419,7 @@ class StableDiffusionHead(MultimodalHead):
                  freeze_vae: bool = True, freeze_unet: bool = True, freeze_projector: bool = False, local_files_only: bool = False):
         super().__init__()
         from .unet import UNet2DConditionModel
+        from .vae import AutoencoderKLEncoder
         self.save_model_name = "stable_diffusion_head"
         self.diffusion_name_or_path = diffusion_name_or_path
         self.projector_type, self.projector_depth = projector_type, projector_depth
@@ -412,7 +440,17 @@ class StableDiffusionHead(MultimodalHead):
             from safetensors.torch import load_file
             self.unet.load_state_dict(load_file(files[0]))
         else:
-            self.unet = UNet2DConditionModel(diffusion_name_or_path)
+            cfgd = dict(diffusion_name_or_path or {})
+            vae_cfg = cfgd.pop("vae", None)
+            self.unet = UNet2DConditionModel(cfgd)
+        self.vae = AutoencoderKLEncoder(vae_cfg if not isinstance(diffusion_name_or_path, str) else None)
+        if isinstance(diffusion_name_or_path, str):
+            import glob
+            from safetensors.torch import load_file
+            vf = glob.glob(os.path.join(diffusion_name_or_path, "vae", "*.safetensors"))
+            if vf:
+                self.vae.load_state_dict(load_file(vf[0]), strict=False)      # decoder.* / post_quant_conv.* are not part of this path
+        self.vae.requires_grad_(False)
         projector_cfg = dict(projector=projector_type, freeze_projector=freeze_projector, depth=projector_depth,
                              save_model_name=self.save_model_name, model_name_or_path=None)
         self.projector = build_projector(projector_cfg, in_hidden_size=embed_hidden_size,
@@ -447,9 +485,39 @@ class StableDiffusionHead(MultimodalHead):
         if os.path.isfile(f):
             self.load_state_dict(torch.load(f, map_location="cpu"), strict=False)
 
-    def forward(self, images, encoder_hidden_states, u_encoder_hidden_states=None, dream_embeddings=None):
-        raise NotImplementedError("StableDiffusionHead.forward (VAE encode + UNet fwd/dgrad + MSE, reference :493-577) is the next "
-                                  "§8 row; this build has the sampler (`pipeline`) only")
+    def _alphas_cumprod(self, device):
+        if getattr(self, "_ac", None) is None or self._ac.device != device:
+            betas = torch.linspace(0.00085 ** 0.5, 0.012 ** 0.5, 1000, dtype=torch.float32) ** 2     # scaled_linear
+            self._ac = torch.cumprod(1.0 - betas, dim=0).to(device)
+        return self._ac
+
+    def forward(self, images=None, encoder_hidden_states=None, u_encoder_hidden_states=None, dream_embeddings=None, *,
+                latents=None, noise=None, timesteps=None, vae_noise=None):
+        """Diffusion loss, reference :493-577: VAE encode (:511-512) -> noise / timestep draw (:520-531) -> add_noise (:536) -> projector
+        (:546) -> UNet eps-prediction (:556) -> MSE in fp32 (:559).  Gradients flow through the frozen UNet into the conditioning.
+        `latents` / `noise` / `timesteps` / `vae_noise` let tests inject the random draws (the reference uses the global generator).
+        `images=None` (the reference's DDP dummy branch, :500-508) is not needed by our reducer and returns None."""
+        if images is None and latents is None:
+            return None
+        if self.noise_offset or self.input_perturbation or self.snr_gamma is not None:
+            raise NotImplementedError("noise_offset / input_perturbation / snr_gamma are 0/None in every shipped config; not built")
+        if u_encoder_hidden_states is not None and self.drop_prob is not None:
+            raise NotImplementedError("CFG-dropout training (drop_prob) is None in every shipped config; not built")
+        dev = encoder_hidden_states.device
+        if latents is None:
+            latents = self.vae.encode_sample(images, z=vae_noise)
+        latents = latents.float().contiguous()
+        assert encoder_hidden_states.shape[0] == latents.shape[0], \
+            f"encoder_hidden_states.shape[0]: {encoder_hidden_states.shape[0]} != latents.shape[0]: {latents.shape[0]}"
+        bsz = latents.shape[0]
+        if noise is None:
+            noise = torch.randn_like(latents)
+        if timesteps is None:
+            timesteps = torch.randint(0, 1000, (bsz,), device=dev)
+        t32 = timesteps.to(torch.int32).contiguous()
+        noisy = ops.add_noise(latents, noise.float().contiguous(), t32, self._alphas_cumprod(dev))
+        cond = self.projector(encoder_hidden_states)[-1]
+        return _DiffusionLossFn.apply(cond, self.unet, noisy, t32, noise.float().contiguous())      # epsilon prediction (:548-549)
 
     @torch.no_grad()
     def pipeline(self, height: int | None = None, width: int | None = None, num_inference_steps: int = 50, guidance_scale: float = 7.5,

@@ -525,10 +525,10 @@ def upsample2x(x_nhwc):
     return y
 
 
-def im2col_s2(x_nhwc):
+def im2col_s2(x_nhwc, pad=1):
     N, H, W, C = x_nhwc.shape
     out = torch.empty((N * (H // 2) * (W // 2), 9 * C), device=x_nhwc.device, dtype=BF16)
-    check(lib().dllm_im2col_s2_nhwc(_p(x_nhwc), _p(out), N, H, W, C, _stream()), "dllm_im2col_s2_nhwc")
+    check(lib().dllm_im2col_s2_nhwc(_p(x_nhwc), _p(out), N, H, W, C, int(pad), _stream()), "dllm_im2col_s2_nhwc")
     LAUNCHES.add(1)
     return out
 
@@ -575,3 +575,20 @@ def sampler_step_(eps_f32, latents_f32, coef_f32, step_i32, guidance, use_cfg, m
                                   int(mode), n, _stream()), "dllm_sampler_step")
     LAUNCHES.add(2)
     return latents_f32
+
+
+def softmax_rows_(x2d, scale):
+    _chk_cuda(x2d)
+    assert x2d.is_contiguous() and x2d.dtype == BF16
+    check(lib().dllm_softmax_rows(_p(x2d), x2d.shape[0], x2d.shape[1], float(scale), _stream()), "dllm_softmax_rows")
+    LAUNCHES.add(1)
+    return x2d
+
+
+def vae_sample(h_nchw_f32, wq, bq, z_f32, scaling):
+    B, C2, H, W = h_nchw_f32.shape
+    L = C2 // 2
+    out = torch.empty((B, L, H, W), device=h_nchw_f32.device, dtype=torch.float32)
+    check(lib().dllm_vae_sample(_p(h_nchw_f32), _p(wq), _p(bq), _p(z_f32), _p(out), B, L, H * W, float(scaling), _stream()), "dllm_vae_sample")
+    LAUNCHES.add(1)
+    return out

@@ -121,7 +121,8 @@ int dllm_groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, vo
                         int C, int G, float eps, int silu, void* stream);
 int dllm_geglu(const void* in, void* out, int T, int I, void* stream);
 int dllm_upsample2x_nhwc(const void* x, void* y, int N, int H, int W, int C, void* stream);
-int dllm_im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, void* stream);
+/* pad = 1: UNet Downsample2D; pad = 0: VAE downsample (F.pad (0,1,0,1) + padding-0 conv) */
+int dllm_im2col_s2_nhwc(const void* x, void* out, int N, int H, int W, int C, int pad, void* stream);
 int dllm_copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int col0, void* stream);
 /* latents x_nchw [Bsrc,Cin,H,W] fp32 -> y_nhwc [B,H,W,Cout]; image n reads latents[n % Bsrc] (CFG duplication, plugins:811) */
 int dllm_conv_in(const float* x_nchw, const void* w, const void* bias, void* y_nhwc, int B, int Bsrc, int Cin, int H, int W, int Cout,
@@ -154,6 +155,11 @@ int dllm_conv_out_bwd(const float* dy_nchw, const void* w, void* dx_nhwc, int B,
 int dllm_add_noise(const float* x0, const float* noise, const int* t, const float* alphas_cumprod, float* out, int B, long per_sample,
                    void* stream);
 int dllm_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, void* stream);
+
+/* ---- VAE encoder helpers (AutoencoderKL.encode(...).latent_dist.sample() * scaling_factor, modeling_plugins.py:511-512) ---- */
+int dllm_softmax_rows(void* x, long rows, int cols, float scale, void* stream);
+int dllm_vae_sample(const float* h, const void* wq, const void* bq, const float* z, float* out, int B, int L, long plane, float scaling,
+                    void* stream);
 
 #ifdef __cplusplus
 }

@@ -46,17 +46,29 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_bucketed_reducer_matches_single_process():
+def _run_two_ranks():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=120) for _ in range(2)]
-    for p in procs:
-        p.join(timeout=60)
-        assert p.exitcode == 0
+    try:
+        res = [q.get(timeout=240) for _ in range(2)]
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
+    return res
+
+
+def test_bucketed_reducer_matches_single_process():
+    try:
+        res = _run_two_ranks()
+    except Exception:            # rendezvous port race / a loaded build box: one retry on a fresh port
+        res = _run_two_ranks()
     torch.manual_seed(0)
     net = Net()
     g = torch.Generator().manual_seed(1)
