@@ -379,7 +379,7 @@ class _DiffusionLossFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, cond, unet, noisy, t32, target):
-        need = cond.requires_grad and torch.is_grad_enabled()
+        need = ctx.needs_input_grad[0]          # (grad mode is off inside Function.forward; ask autograd instead)
         with torch.no_grad():
             if need:
                 eps, tape = unet.forward_train(noisy, t32, cond)
