@@ -93,6 +93,16 @@ def measured_peaks():
     return 1400.0, 6650.0, "fallback"
 
 
+def gemm_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/*_gemm_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_gemm_traffic.json")))
+    if not files:
+        return None, "no ncu --set full capture committed"
+    d = json.load(open(files[-1]))
+    return d["dram_bytes_per_launch"], d["note"]
+
+
 # ---------------------------------------------------------------------------------------------- CPU reference arm
 def cpu_reference(seq, layers_sample=1, iters=1, warm=1):
     """Reference algorithm (oracle port of modeling_dreamllm.py:599-654 + :1452-1470) on the host cores, bf16 (the config's
@@ -287,7 +297,8 @@ def main():
         "gpu_launches": launches, "clocks": clocks,
         "roofline": {"bound": "tensor", "kernel": "dllm::gemm_kernel<2,*,*,bf16> (tcgen05 GEMM, all fwd/dgrad/wgrad launches)",
                      "achieved": gemm_stats["tflops"], "peak": peak_tf, "unit": "TFLOP/s",
-                     "frac": gemm_stats["tflops"] / peak_tf if gemm_stats["tflops"] else None, "traffic": None,
+                     "frac": gemm_stats["tflops"] / peak_tf if gemm_stats["tflops"] else None, "traffic": gemm_traffic()[0],
+                     "traffic_note": gemm_traffic()[1],
                      "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({how})", "launches_timed": gemm_stats["n"],
                      "gemm_share_of_step": gemm_stats["ms"] / total_ms if total_ms else None},
         "step_roofline": {"algorithmic_tflop_per_step_per_gpu": fl / 1e12, "achieved_tflops_per_gpu": fl / 1e12 / (ms_per_step / 1e3),

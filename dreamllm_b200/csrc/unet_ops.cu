@@ -117,8 +117,15 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restri
   reinterpret_cast<V8*>(y)[gid] = pk8(f);
 }
 
+// pixel rows per partial-sum CTA: 64 for the UNet planes, more for the VAE's 512x512 planes so that the finalize pass never
+// walks more than 128 partials (it took 35 us per GroupNorm with 4096 of them — profiles/r01_stage1_launch_list_summary.md)
+static inline int gn_rows(int HW) {
+  int rows = 64;
+  while ((HW + rows - 1) / rows > 128) rows *= 2;
+  return rows;
+}
 size_t groupnorm_workspace(int N, int HW, int G) {
-  const int rows = 64;
+  const int rows = gn_rows(HW);
   const int nchunks = (HW + rows - 1) / rows;
   return (static_cast<size_t>(N) * nchunks * G * 2 + static_cast<size_t>(N) * G * 2) * sizeof(float);
 }
@@ -126,7 +133,7 @@ int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* w
                    int G, float eps, int silu, cudaStream_t s) {
   if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
   if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
-  const int rows = 64;
+  const int rows = gn_rows(HW);
   const int nchunks = (HW + rows - 1) / rows;
   float* partial = static_cast<float*>(workspace);
   float* stats = partial + static_cast<size_t>(N) * nchunks * G * 2;
@@ -490,7 +497,7 @@ int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void*
                        void* workspace, size_t ws_bytes, int N, int HW, int C, int G, int silu, cudaStream_t s) {
   if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
   if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
-  const int rows = 64;
+  const int rows = gn_rows(HW);
   const int nchunks = (HW + rows - 1) / rows;
   float* partial = static_cast<float*>(workspace);
   float* sums = partial + static_cast<size_t>(N) * nchunks * G * 2;
@@ -507,7 +514,7 @@ int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void*
 int groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, cudaStream_t s) {
   if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
   if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
-  const int rows = 64;
+  const int rows = gn_rows(HW);
   const int nchunks = (HW + rows - 1) / rows;
   float* partial = static_cast<float*>(workspace);
   gn_partial_kernel<<<dim3(nchunks, N), kGnThreads, 2 * C * sizeof(float), s>>>((const bf16*)x, partial, HW, C, G, rows);
