@@ -375,8 +375,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
   uint64_t* sdp_full = bars + 5;   // [2]
   uint64_t* pds_full = bars + 7;   // [2] (indexed i & 1: row warps may run one iteration ahead of the MMA warp)
   uint64_t* acc_done = bars + 9;   // [2]: dV/dK MMAs of iteration i retired (indexed i & 1)
-  uint64_t* final_done = bars + 11;  // every MMA of this CTA retired
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -391,9 +390,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
-      mbar_init(&pds_full[i], 128);   // one row-warp GROUP (4 warps) owns iteration parity i
+      mbar_init(&pds_full[i], 256);
     }
-    mbar_init(final_done, 1);
     fence_mbar_init();
   }
   if (warp == 9) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
@@ -448,54 +446,48 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
       umma_commit(&qdo_empty[st]);
       umma_commit(&acc_done[st]);
     }
-    umma_commit(final_done);
   } else if (warp < 8) {
-    // Two row-warp groups ping-pong on alternate q tiles: group g owns iterations it == g (mod 2) (TMEM S/dP buffer g, staging
-    // buffer g), so the tmem-load -> exp2 -> smem-store -> barrier chain of iteration it+1 overlaps the chain of iteration it.
     const int wq = warp & 3, half = warp >> 2;
     const int row = wq * 32 + lane;  // kv row within tile
     const int kv_row = kv0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     const float* lse_bh = lse2 + (static_cast<size_t>(b) * nh + h) * S_pad;
     const float* del_bh = delta + (static_cast<size_t>(b) * nh + h) * S_pad;
-    for (int it = half; it < n_it; it += 2) {
-      const int st = half;
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const int qc0 = (i_begin + it) * 64 + half * 32;  // first q index of my 32 columns
+      // my 32 columns' lse / delta: 16 broadcast float4 loads (all lanes read the same addresses)
+      float lq[32], dq_[32];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(lse_bh + qc0) + i);
+        const float4 c = __ldg(reinterpret_cast<const float4*>(del_bh + qc0) + i);
+        lq[4 * i] = a.x; lq[4 * i + 1] = a.y; lq[4 * i + 2] = a.z; lq[4 * i + 3] = a.w;
+        dq_[4 * i] = c.x; dq_[4 * i + 1] = c.y; dq_[4 * i + 2] = c.z; dq_[4 * i + 3] = c.w;
+      }
       mbar_wait(&sdp_full[st], (it >> 1) & 1, 24);
       tc_fence_after();
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tmem_St + lane_off + st * 64 + half * 32, sv);
+      tmem_ld32(tmem_dPt + lane_off + st * 64 + half * 32, dv);
+      tmem_ld_wait();
       // staging buffer `st` was last read by the dV/dK MMAs of iteration it-2
       if (it >= 2) mbar_wait(&acc_done[st], ((it >> 1) & 1) ^ 1, 25);
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        const int qc0 = (i_begin + it) * 64 + hh * 32;  // first q index of these 32 columns
-        // lse / delta of the 32 columns: 16 broadcast float4 loads (all lanes read the same addresses)
-        float lq[32], dq_[32];
+      const bool full_tile = (qc0 + 31 < len) && (kv0 + 127 < len_kv) && (!kCausal || kv0 + 127 <= qc0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(lse_bh + qc0) + i);
-          const float4 c = __ldg(reinterpret_cast<const float4*>(del_bh + qc0) + i);
-          lq[4 * i] = a.x; lq[4 * i + 1] = a.y; lq[4 * i + 2] = a.z; lq[4 * i + 3] = a.w;
-          dq_[4 * i] = c.x; dq_[4 * i + 1] = c.y; dq_[4 * i + 2] = c.z; dq_[4 * i + 3] = c.w;
+      for (int jj = 0; jj < 4; ++jj) {
+        float p[8], ds[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int c = jj * 8 + e;
+          const int qi = qc0 + c;
+          const bool ok = full_tile || ((qi < len) && (kv_row < len_kv) && (!kCausal || kv_row <= qi));
+          const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]) : 0.f;
+          p[e] = pe;
+          ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) * scale : 0.f;
         }
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_St + lane_off + st * 64 + hh * 32, sv);
-        tmem_ld32(tmem_dPt + lane_off + st * 64 + hh * 32, dv);
-        tmem_ld_wait();
-        const bool full_tile = (qc0 + 31 < len) && (kv0 + 127 < len_kv) && (!kCausal || kv0 + 127 <= qc0);
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float p[8], ds[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = jj * 8 + e;
-            const int qi = qc0 + c;
-            const bool ok = full_tile || ((qi < len) && (kv_row < len_kv) && (!kCausal || kv_row <= qi));
-            const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]) : 0.f;
-            p[e] = pe;
-            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) * scale : 0.f;
-          }
-          store_row_chunk(smem + L::oP + st * 16384, row, hh * 4 + jj, p);
-          store_row_chunk(smem + L::oDS + st * 16384, row, hh * 4 + jj, ds);
-        }
+        store_row_chunk(smem + L::oP + st * 16384, row, half * 4 + jj, p);
+        store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -504,7 +496,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
     const bool my_store = (D == 128) || (half == 0);
     const int cb = (D == 128) ? half : 0, ce = (D == 128) ? half + 1 : 1;
     if (n_it > 0) {
-      mbar_wait(final_done, 0, 26);
+      mbar_wait(&acc_done[(n_it - 1) & 1], ((n_it - 1) >> 1) & 1, 26);
       tc_fence_after();
       if (my_store) {
         store_acc_tile<D>(tmem_dV, smem + L::oV, 1.f, &tdv, h * D, kv0, b, wq, lane, cb, ce);
@@ -562,8 +554,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   uint64_t* sdp_full = bars + 5;  // [2]
   uint64_t* ds_full = bars + 7;   // [2]
   uint64_t* acc_done = bars + 9;  // [2]
-  uint64_t* final_done = bars + 11;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 12);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -577,9 +568,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     mbar_init(q_full, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
-      mbar_init(&ds_full[i], 128);
+      mbar_init(&ds_full[i], 256);
     }
-    mbar_init(final_done, 1);
     fence_mbar_init();
   }
   if (warp == 9) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
@@ -629,9 +619,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       umma_commit(&kv_empty[st]);
       umma_commit(&acc_done[st]);
     }
-    umma_commit(final_done);
   } else if (warp < 8) {
-    // row-warp group g owns kv tiles j == g (mod 2) (ping-pong, see attn_bwd_dkdv_kernel)
     const int wq = warp & 3, half = warp >> 2;
     const int row = wq * 32 + lane;
     const int q_row = q0 + row;
@@ -639,32 +627,29 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const size_t sidx = (static_cast<size_t>(b) * nh + h) * S_pad + min(q_row, S_pad - 1);
     const float my_lse = lse2[sidx], my_delta = delta[sidx];
     const bool row_ok = q_row < len;
-    for (int j = half; j < n_kv; j += 2) {
-      const int st = half;
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const int kc0 = j * 64 + half * 32;
       mbar_wait(&sdp_full[st], (j >> 1) & 1, 34);
       tc_fence_after();
+      uint32_t sv[32], dv[32];
+      tmem_ld32(tmem_S + lane_off + st * 64 + half * 32, sv);
+      tmem_ld32(tmem_dP + lane_off + st * 64 + half * 32, dv);
+      tmem_ld_wait();
       if (j >= 2) mbar_wait(&acc_done[st], ((j >> 1) & 1) ^ 1, 35);
-#pragma unroll 1
-      for (int hh = 0; hh < 2; ++hh) {
-        const int kc0 = j * 64 + hh * 32;
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tmem_S + lane_off + st * 64 + hh * 32, sv);
-        tmem_ld32(tmem_dP + lane_off + st * 64 + hh * 32, dv);
-        tmem_ld_wait();
-        const bool full_tile = (q0 + 127 < len) && (kc0 + 31 < len_kv) && (!kCausal || kc0 + 31 <= q0);
+      const bool full_tile = (q0 + 127 < len) && (kc0 + 31 < len_kv) && (!kCausal || kc0 + 31 <= q0);
 #pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-          float ds[8];
+      for (int jj = 0; jj < 4; ++jj) {
+        float ds[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int c = jj * 8 + e;
-            const int kvi = kc0 + c;
-            const bool ok = full_tile || (row_ok && (kvi < len_kv) && (!kCausal || kvi <= q_row));
-            const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse) : 0.f;
-            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) * scale : 0.f;
-          }
-          store_row_chunk(smem + L::oDS + st * 16384, row, hh * 4 + jj, ds);
+        for (int e = 0; e < 8; ++e) {
+          const int c = jj * 8 + e;
+          const int kvi = kc0 + c;
+          const bool ok = full_tile || (row_ok && (kvi < len_kv) && (!kCausal || kvi <= q_row));
+          const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse) : 0.f;
+          ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) * scale : 0.f;
         }
+        store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -673,7 +658,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     const bool my_store = (D == 128) || (half == 0);
     const int cb = (D == 128) ? half : 0, ce = (D == 128) ? half + 1 : 1;
     if (n_kv > 0) {
-      mbar_wait(final_done, 0, 36);
+      mbar_wait(&acc_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1, 36);
       tc_fence_after();
       if (my_store) store_acc_tile<D>(tmem_dQ, smem + L::oQ, 1.f, &tdq, h * D, q0, b, wq, lane, cb, ce);
     } else if (my_store) {
