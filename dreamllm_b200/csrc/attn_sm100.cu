@@ -474,20 +474,36 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
       // staging buffer `st` was last read by the dV/dK MMAs of iteration it-2
       if (it >= 2) mbar_wait(&acc_done[st], ((it >> 1) & 1) ^ 1, 25);
       const bool full_tile = (qc0 + 31 < len) && (kv0 + 127 < len_kv) && (!kCausal || kv0 + 127 <= qc0);
+      if (full_tile) {  // interior tile (the common case): no per-element predicates
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        float p[8], ds[8];
+        for (int jj = 0; jj < 4; ++jj) {
+          float p[8], ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = jj * 8 + e;
-          const int qi = qc0 + c;
-          const bool ok = full_tile || ((qi < len) && (kv_row < len_kv) && (!kCausal || kv_row <= qi));
-          const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]) : 0.f;
-          p[e] = pe;
-          ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) * scale : 0.f;
+          for (int e = 0; e < 8; ++e) {
+            const int c = jj * 8 + e;
+            const float pe = exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]);
+            p[e] = pe;
+            ds[e] = pe * (__uint_as_float(dv[c]) - dq_[c]) * scale;
+          }
+          store_row_chunk(smem + L::oP + st * 16384, row, half * 4 + jj, p);
+          store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
         }
-        store_row_chunk(smem + L::oP + st * 16384, row, half * 4 + jj, p);
-        store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float p[8], ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = jj * 8 + e;
+            const int qi = qc0 + c;
+            const bool ok = (qi < len) && (kv_row < len_kv) && (!kCausal || kv_row <= qi);
+            const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]) : 0.f;
+            p[e] = pe;
+            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) * scale : 0.f;
+          }
+          store_row_chunk(smem + L::oP + st * 16384, row, half * 4 + jj, p);
+          store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -638,18 +654,32 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       tmem_ld_wait();
       if (j >= 2) mbar_wait(&acc_done[st], ((j >> 1) & 1) ^ 1, 35);
       const bool full_tile = (q0 + 127 < len) && (kc0 + 31 < len_kv) && (!kCausal || kc0 + 31 <= q0);
+      if (full_tile) {
 #pragma unroll
-      for (int jj = 0; jj < 4; ++jj) {
-        float ds[8];
+        for (int jj = 0; jj < 4; ++jj) {
+          float ds[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int c = jj * 8 + e;
-          const int kvi = kc0 + c;
-          const bool ok = full_tile || (row_ok && (kvi < len_kv) && (!kCausal || kvi <= q_row));
-          const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse) : 0.f;
-          ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) * scale : 0.f;
+          for (int e = 0; e < 8; ++e) {
+            const int c = jj * 8 + e;
+            const float pe = exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse);
+            ds[e] = pe * (__uint_as_float(dv[c]) - my_delta) * scale;
+          }
+          store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
         }
-        store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+          float ds[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const int c = jj * 8 + e;
+            const int kvi = kc0 + c;
+            const bool ok = row_ok && (kvi < len_kv) && (!kCausal || kvi <= q_row);
+            const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse) : 0.f;
+            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) * scale : 0.f;
+          }
+          store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
+        }
       }
       fence_proxy_async_smem();
       tc_fence_before();
