@@ -483,7 +483,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
             const int c = jj * 8 + e;
             const float pe = exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]);
             p[e] = pe;
-            ds[e] = pe * (__uint_as_float(dv[c]) - dq_[c]) * scale;
+            ds[e] = pe * (__uint_as_float(dv[c]) - dq_[c]);   // softmax scale is applied once, to the dK accumulator
           }
           store_row_chunk(smem + L::oP + st * 16384, row, half * 4 + jj, p);
           store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
@@ -499,7 +499,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
             const bool ok = (qi < len) && (kv_row < len_kv) && (!kCausal || kv_row <= qi);
             const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - lq[c]) : 0.f;
             p[e] = pe;
-            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) * scale : 0.f;
+            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - dq_[c]) : 0.f;
           }
           store_row_chunk(smem + L::oP + st * 16384, row, half * 4 + jj, p);
           store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
@@ -516,7 +516,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
       tc_fence_after();
       if (my_store) {
         store_acc_tile<D>(tmem_dV, smem + L::oV, 1.f, &tdv, h * D, kv0, b, wq, lane, cb, ce);
-        store_acc_tile<D>(tmem_dK, smem + L::oK, 1.f, &tdk, h * D, kv0, b, wq, lane, cb, ce);
+        store_acc_tile<D>(tmem_dK, smem + L::oK, scale, &tdk, h * D, kv0, b, wq, lane, cb, ce);
       }
     } else if (my_store) {
       for (int c = cb; c < ce; ++c)
@@ -662,7 +662,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
           for (int e = 0; e < 8; ++e) {
             const int c = jj * 8 + e;
             const float pe = exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse);
-            ds[e] = pe * (__uint_as_float(dv[c]) - my_delta) * scale;
+            ds[e] = pe * (__uint_as_float(dv[c]) - my_delta);   // scale applied to the dQ accumulator
           }
           store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
         }
@@ -676,7 +676,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
             const int kvi = kc0 + c;
             const bool ok = row_ok && (kvi < len_kv) && (!kCausal || kvi <= q_row);
             const float pe = ok ? exp2f(__uint_as_float(sv[c]) * scale_log2 - my_lse) : 0.f;
-            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) * scale : 0.f;
+            ds[e] = ok ? pe * (__uint_as_float(dv[c]) - my_delta) : 0.f;
           }
           store_row_chunk(smem + L::oDS + st * 16384, row, half * 4 + jj, ds);
         }
@@ -690,7 +690,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
     if (n_kv > 0) {
       mbar_wait(&acc_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1, 36);
       tc_fence_after();
-      if (my_store) store_acc_tile<D>(tmem_dQ, smem + L::oQ, 1.f, &tdq, h * D, q0, b, wq, lane, cb, ce);
+      if (my_store) store_acc_tile<D>(tmem_dQ, smem + L::oQ, scale, &tdq, h * D, q0, b, wq, lane, cb, ce);
     } else if (my_store) {
       for (int c = cb; c < ce; ++c)
         for (int jj = 0; jj < 8; ++jj) {
