@@ -110,6 +110,9 @@ __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, float* __restrict__ lse,
                 const int* __restrict__ seqlens, int S, int Skv, int nh, float scale_log2) {
+  // causal with Skv > S = kv-cache decode / continuation (reference :344-355, :444-449): query i sits at absolute position
+  // (Skv - S) + i, i.e. the mask is bottom-right aligned:  kv <= q + coff
+  const int coff = kCausal ? (Skv - S) : 0;
   using L = FwdSmem<D>;
   constexpr int NCH = L::NCH;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -128,7 +131,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int kv_len = seqlens ? min(seqlens[b], Skv) : Skv;   // Skv != S only for cross-attention (non-causal)
   const int q_len = seqlens ? kv_len : S;                    // right-padded self-attention: rows >= len are padding
-  const int kv_end = kCausal ? min(kv_len, q0 + 128) : kv_len;
+  const int kv_end = kCausal ? min(kv_len, q0 + 128 + coff) : kv_len;
   const int n_kv = (kv_end + 63) / 64;
 
   if (threadIdx.x == 0) {
@@ -206,13 +209,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       tmem_ld32(tmem_S + lane_off + (j & 1) * 64 + 32, sv + 32);
       tmem_ld_wait();
       const int kv0 = j * 64;
-      const bool need_mask = (kCausal && kv0 + 63 > q0 + warp * 32) || (kv0 + 64 > kv_len);
+      const bool need_mask = (kCausal && kv0 + 63 > q0 + warp * 32 + coff) || (kv0 + 64 > kv_len);
       float mx = -INFINITY;
       if (need_mask) {
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
           const int kvi = kv0 + c;
-          const bool ok = (kvi < kv_len) && (!kCausal || kvi <= q_row);
+          const bool ok = (kvi < kv_len) && (!kCausal || kvi <= q_row + coff);
           float s = ok ? __uint_as_float(sv[c]) : -INFINITY;
           sv[c] = __float_as_uint(s);
           mx = fmaxf(mx, s);
@@ -740,14 +743,22 @@ int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse,
 // q: [B, S, nh, d] (token stride ld_q); k, v: [B, Skv, nh, d] (token stride ld_kv).  Skv != S = cross-attention.
 int attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int Skv,
                 int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, cudaStream_t st) {
-  if (B <= 0 || S <= 0 || Skv <= 0 || nh <= 0) return DLLM_ERR_SHAPE;
+  return attn_fwd_cache(q, k, v, out, lse, seqlens, B, S, Skv, Skv, nh, d, ld_q, ld_kv, ld_o, causal, scale, st);
+}
+
+// kv_rows = rows allocated per batch entry in the k/v buffers (>= Skv): lets a preallocated kv-cache [B, max_len, nh*d] be read in
+// place with Skv valid rows.  causal with Skv > S uses the bottom-right aligned mask (decode / continuation).
+int attn_fwd_cache(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int Skv,
+                   int kv_rows, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, cudaStream_t st) {
+  if (B <= 0 || S <= 0 || Skv <= 0 || nh <= 0 || kv_rows < Skv) return DLLM_ERR_SHAPE;
   if (d != 128 && d != 64) return DLLM_ERR_UNSUPPORTED;
-  if (S != Skv && (causal || seqlens)) return DLLM_ERR_UNSUPPORTED;
+  if (S != Skv && seqlens) return DLLM_ERR_UNSUPPORTED;
+  if (causal && Skv < S) return DLLM_ERR_SHAPE;
   CUtensorMap tq, tk, tv, to;
   int rc;
   if ((rc = make_tmap_bsc(&tq, q, B, S, nh * d, ld_q, 128))) return rc;
-  if ((rc = make_tmap_bsc(&tk, k, B, Skv, nh * d, ld_kv, 64))) return rc;
-  if ((rc = make_tmap_bsc(&tv, v, B, Skv, nh * d, ld_kv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tk, k, B, kv_rows, nh * d, ld_kv, 64))) return rc;
+  if ((rc = make_tmap_bsc(&tv, v, B, kv_rows, nh * d, ld_kv, 64))) return rc;
   if ((rc = make_tmap_bsc(&to, out, B, S, nh * d, ld_o, 32))) return rc;
   const float sl2 = scale * kLog2e;
   if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st)

@@ -296,8 +296,7 @@ class _DecoderLayerFn(torch.autograd.Function):
         h2, rstd2, xmid = ops.rmsnorm_fwd(x2, w_post, meta.eps, add=o)    # xmid = x + o
         gu = ops.linear(h2, meta.wgu)                                     # [T, 2I]
         act = ops.swiglu_fwd(gu, I)
-        dn = ops.linear(act, wd)
-        y = ops.add(xmid, dn)
+        y = ops.linear(act, wd, residual=xmid)                            # down_proj + residual add fused in the GEMM epilogue
         ctx.save_for_backward(x2, w_in, rstd1, h1, qkv, ao2, lse, wo, xmid, w_post, rstd2, h2, gu, act, wd)
         ctx.meta = meta
         return y.view(B, S, H)
@@ -342,6 +341,20 @@ class _DecoderLayerFn(torch.autograd.Function):
         return (dx.view(B, S, H) if need[0] else None, dw_in, dwq, dwk, dwv, dwo, dw_post, dwg, dwu, dwd, None)
 
 
+class KVCache:
+    """Preallocated per-layer K/V buffers [B, max_len, nh, d] (token-major, read in place by the attention kernel).  Replaces the
+    reference's per-layer `torch.cat([past, new], dim=2)` tuples (:444-449); opaque to callers, passed as `past_key_values`."""
+
+    def __init__(self, num_layers, batch, max_len, num_heads, head_dim, device, dtype=BF16):
+        self.k = [torch.empty((batch, max_len, num_heads, head_dim), device=device, dtype=dtype) for _ in range(num_layers)]
+        self.v = [torch.empty((batch, max_len, num_heads, head_dim), device=device, dtype=dtype) for _ in range(num_layers)]
+        self.len = 0
+        self.max_len = max_len
+
+    def get_seq_length(self):
+        return self.len
+
+
 class DreamLLMDecoderLayer(nn.Module):
     def __init__(self, config):
         super().__init__()
@@ -361,7 +374,7 @@ class DreamLLMDecoderLayer(nn.Module):
         if hidden_states.dtype != BF16:
             raise ValueError("dreamllm_b200 computes in bf16: cast the model and inputs with .to(torch.bfloat16)")
         if past_key_value is not None:
-            raise NotImplementedError("kv-cache decode is SURVEY §8(f) row 2 (next), not built yet")
+            return self._forward_cached(hidden_states, position_ids, past_key_value)
         if output_attentions:
             raise ValueError("output_attentions=True needs the materialised eager path, which this build does not have")
         B, S, H = hidden_states.shape
@@ -387,8 +400,40 @@ class DreamLLMDecoderLayer(nn.Module):
                                   self.mlp.gate_proj.weight, self.mlp.up_proj.weight, self.mlp.down_proj.weight, meta)
         outputs = (y,)
         if use_cache:
-            raise NotImplementedError("use_cache=True (kv-cache) is SURVEY §8(f) row 2 (next), not built yet")
+            raise ValueError("use_cache=True needs a cache: pass past_key_value=(KVCache, layer_idx) (DreamLLMModel does this)")
         return outputs
+
+    @torch.no_grad()
+    def _forward_cached(self, hidden_states, position_ids, past_key_value):
+        """Inference with a kv-cache (prefill or decode; reference :344-355 / :444-449): new keys/values are appended to
+        `cache.k/v[layer]` at rows [cache.len, cache.len + S) and attention runs causally (bottom-right aligned) over all of them."""
+        cache, li = past_key_value
+        B, S, H = hidden_states.shape
+        att, mlp = self.self_attn, self.mlp
+        nh, d, I = att.num_heads, att.head_dim, mlp.intermediate_size
+        start = cache.len
+        if start + S > cache.max_len:
+            raise ValueError(f"kv-cache overflow: {start} + {S} > {cache.max_len}")
+        dev = hidden_states.device
+        if position_ids is None:
+            pos = torch.arange(start, start + S, device=dev, dtype=torch.int32).repeat(B)
+        else:
+            pos = position_ids.to(torch.int32).expand(B, S).reshape(-1).contiguous()
+        cos, sin = att.rotary_emb.tables(max(start + S, att.max_position_embeddings), dev)
+        eps = self.input_layernorm.variance_epsilon
+        x2 = hidden_states.reshape(B * S, H).contiguous()
+        h1, _, _ = ops.rmsnorm_fwd(x2, self.input_layernorm.weight, eps)
+        qkv = ops.linear(h1, _fuse_rows([att.q_proj.weight, att.k_proj.weight, att.v_proj.weight]))
+        ops.rope_(qkv, cos, sin, pos, 2 * nh, d)
+        q4 = qkv.view(B, S, 3, nh, d)
+        cache.k[li][:, start:start + S].copy_(q4[:, :, 1])
+        cache.v[li][:, start:start + S].copy_(q4[:, :, 2])
+        ao = ops.attn_fwd_cache(q4[:, :, 0], cache.k[li], cache.v[li], start + S, causal=True)
+        o = ops.linear(ao.view(B * S, H), att.o_proj.weight)
+        h2, _, xmid = ops.rmsnorm_fwd(x2, self.post_attention_layernorm.weight, eps, add=o)
+        gu = ops.linear(h2, _fuse_rows([mlp.gate_proj.weight, mlp.up_proj.weight]))
+        y = ops.linear(ops.swiglu_fwd(gu, I), mlp.down_proj.weight, residual=xmid)
+        return (y.view(B, S, H), (cache, li))
 
 
 # ------------------------------------------------------------------------------------------------ model
@@ -504,14 +549,30 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
             attention_mask = None
         hidden_states = inputs_embeds
         all_hidden = () if output_hidden_states else None
-        for layer in self.layers:
+        cache = None
+        if use_cache or past_key_values is not None:
+            if torch.is_grad_enabled() and hidden_states.requires_grad:
+                raise ValueError("kv-cache inference runs under torch.no_grad()")
+            if attention_mask is not None and attention_mask_has_padding is not False and not bool(attention_mask.all()):
+                raise NotImplementedError("kv-cache path does not support padded batches (pad positions inside the cache); "
+                                          "run prompts of different lengths one at a time")
+            B, S, _ = hidden_states.shape
+            att = self.layers[0].self_attn
+            cache = past_key_values if past_key_values is not None else KVCache(
+                len(self.layers), B, self.config.max_position_embeddings, att.num_heads, att.head_dim, hidden_states.device)
+        for li, layer in enumerate(self.layers):
             if output_hidden_states:
                 all_hidden += (hidden_states,)
-            hidden_states = layer(hidden_states, attention_mask=attention_mask, position_ids=position_ids)[0]
+            if cache is not None:
+                hidden_states = layer(hidden_states, position_ids=position_ids, past_key_value=(cache, li), use_cache=True)[0]
+            else:
+                hidden_states = layer(hidden_states, attention_mask=attention_mask, position_ids=position_ids)[0]
+        if cache is not None:
+            cache.len += hidden_states.shape[1]
         hidden_states = self.norm(hidden_states)
         if output_hidden_states:
             all_hidden += (hidden_states,)
-        return BaseModelOutputWithPast(last_hidden_state=hidden_states, hidden_states=all_hidden)
+        return BaseModelOutputWithPast(last_hidden_state=hidden_states, past_key_values=cache, hidden_states=all_hidden)
 
     # ---- plugins (reference :822-831 `init_plugin_modules` instantiates them from config; here they are attached) ----
     def attach_plugins(self, clip_vision_embedding=None, dream_embedding=None, image_start_id=None, dream_start_id=None):
@@ -525,6 +586,8 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
             image_start_id = st["additional_special_tokens"]["<im_start>"] if image_start_id is None else image_start_id
             dream_start_id = st["additional_special_tokens"]["<dream_start>"] if dream_start_id is None else dream_start_id
         self.image_start_id, self.dream_start_id = image_start_id, dream_start_id
+        self.dream_end_id = (st["additional_special_tokens"]["<dream_end>"] if st is not None else
+                             (None if dream_start_id is None else dream_start_id + 1))      # token order: tokenization_dreamllm.py:78-94
 
     def forward(self, input_ids=None, images=None, images_dm=None, attention_mask=None, position_ids=None,
                 past_key_values=None, inputs_embeds=None, use_cache=None, output_attentions=None, output_hidden_states=None,
@@ -533,10 +596,14 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
         `input_ids_cpu` (the collator's host copy) lets the index maps be built without a device->host sync;
         `splice_plan` lets the caller pass prebuilt maps."""
         need_splice = (images is not None) or (images_dm is not None)
+        if past_key_values is not None and images is not None and input_ids is not None and \
+                not bool((input_ids == getattr(self, "image_start_id", -1)).any()):
+            images = None          # decode steps: do not re-extract CLIP features (reference :1072-1079)
+            need_splice = images_dm is not None
         if not need_splice:
             return self._forward(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
-                                 inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states,
-                                 attention_mask_has_padding=attention_mask_has_padding)
+                                 past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
+                                 output_hidden_states=output_hidden_states, attention_mask_has_padding=attention_mask_has_padding)
         from .modeling_plugins import build_splice_plan, splice_embeddings
         if input_ids is None:
             raise ValueError("image / dream splicing needs input_ids")
@@ -557,7 +624,15 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
             image_features = image_features.to(inputs_embeds.dtype)
         inputs_embeds = splice_embeddings(inputs_embeds, image_features, dq, splice_plan)
         return self._forward(attention_mask=attention_mask, position_ids=position_ids, inputs_embeds=inputs_embeds,
-                             output_hidden_states=output_hidden_states, attention_mask_has_padding=attention_mask_has_padding)
+                             past_key_values=past_key_values, use_cache=use_cache, output_hidden_states=output_hidden_states,
+                             attention_mask_has_padding=attention_mask_has_padding)
+
+    def prepare_dream_queries_with_special_token(self, batch_size: int = 1):
+        """reference :1161-1169: embeds of [<dream_start>, dream queries, <dream_end>]."""
+        ids = torch.tensor([[self.dream_start_id, self.dream_end_id]], device=self.embed_tokens.weight.device)
+        sp = ops.embedding_fwd(ids, self.embed_tokens.weight)
+        dq = torch.cat([sp[:, :1], self.dream_embedding().to(sp.dtype), sp[:, 1:]], 1)
+        return dq.repeat(batch_size, 1, 1)
 
 
 class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
@@ -599,7 +674,8 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
         path returns the gathered dream-query conditioning in `additional_log_info["dream_conditioning"]` — the
         StableDiffusionHead (UNet) that consumes it (:1441) is the next §8 row."""
         out = self.model(input_ids=input_ids, images=images, images_dm=images_dm, attention_mask=attention_mask,
-                         position_ids=position_ids, inputs_embeds=inputs_embeds, output_hidden_states=output_hidden_states,
+                         position_ids=position_ids, past_key_values=past_key_values, inputs_embeds=inputs_embeds,
+                         use_cache=use_cache, output_hidden_states=output_hidden_states,
                          attention_mask_has_padding=attention_mask_has_padding, input_ids_cpu=input_ids_cpu,
                          splice_plan=splice_plan)
         hidden = out.last_hidden_state
@@ -613,6 +689,8 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
             shifted[:, :-1] = labels[:, 1:]
             lm_loss = _LMHeadLossFn.apply(h2, self.lm_head.weight, shifted.reshape(-1).contiguous())
             loss = lm_loss * self.loss_weight_lm
+        elif kwargs.get("last_token_logits_only", False):
+            logits = ops.linear(hidden[:, -1].contiguous(), self.lm_head.weight).view(B, 1, -1).float()
         else:
             logits = ops.linear(h2, self.lm_head.weight).view(B, S, -1).float()
         info = {"lm_loss": lm_loss}
@@ -628,4 +706,46 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
                 vm_loss = head(images_dm[: plan.n_dreams], enc_h, **(sd_kwargs or {}))                   # (:1441)
                 loss = vm_loss * self.loss_weight_vm + (loss if loss is not None else 0.0)               # (:1486-1488)
         info["vm_loss"] = vm_loss
-        return CausalLMOutputWithPast(loss=loss, logits=logits, hidden_states=out.hidden_states, additional_log_info=info)
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=out.past_key_values, hidden_states=out.hidden_states,
+                                      additional_log_info=info)
+
+    # ---------------------------------------------------------------------------------------------- inference entry points
+    @torch.no_grad()
+    def generate_greedy(self, input_ids, max_new_tokens=16, images=None, eos_token_id=None):
+        """Greedy decoding with the kv-cache (the path HF `generate(do_sample=False)` takes through the reference,
+        omni/eval/vqa/vqa_inference.py:112-130).  Token-id / argmax path: bit-exact w.r.t. a full re-forward."""
+        out = self(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True)
+        cache = out.past_key_values
+        tokens = [out.logits[:, -1].argmax(-1)]
+        for _ in range(max_new_tokens - 1):
+            out = self(input_ids=tokens[-1][:, None], past_key_values=cache, use_cache=True, last_token_logits_only=True)
+            tokens.append(out.logits[:, -1].argmax(-1))
+            if eos_token_id is not None and bool((tokens[-1] == eos_token_id).all()):
+                break
+        return torch.cat([input_ids, torch.stack(tokens, 1)], 1)
+
+    @torch.no_grad()
+    def get_prompt_embeds(self, input_ids, images=None):
+        """reference :1598-1673 (token ids in; the tokenizer is out of scope): LLM pass 1 over the prompt with use_cache, pass 2 over
+        [<dream_start>, dream queries, <dream_end>] against the cache; returns last hidden states [:, 1:-1] = [B, Q, H]."""
+        text_out = self(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True)
+        dq = self.model.prepare_dream_queries_with_special_token(batch_size=input_ids.shape[0])
+        out = self(inputs_embeds=dq, past_key_values=text_out.past_key_values, use_cache=True, output_hidden_states=True,
+                   last_token_logits_only=True)
+        return out.hidden_states[-1][:, 1:-1, :]
+
+    @torch.no_grad()
+    def stable_diffusion_pipeline(self, input_ids, negative_input_ids=None, images=None, guidance_scale=7.5, num_inference_steps=50,
+                                  height=None, width=None, latents=None, generator=None, output_type="latent", scheduler="ddpm",
+                                  use_cuda_graph=True):
+        """reference :1765-1889: encode_prompt (two kv-cache LLM passes, also for the negative prompt) -> StableDiffusionHead.pipeline."""
+        prompt_embeds = self.get_prompt_embeds(input_ids, images)
+        negative = None
+        if guidance_scale > 1.0:
+            if negative_input_ids is None:
+                raise ValueError("classifier-free guidance needs negative_input_ids (the reference's default negative prompt is text)")
+            negative = self.get_prompt_embeds(negative_input_ids)
+        return self.stable_diffusion_head.pipeline(height=height, width=width, num_inference_steps=num_inference_steps,
+                                                   guidance_scale=guidance_scale, generator=generator, latents=latents,
+                                                   prompt_embeds=prompt_embeds, negative_prompt_embeds=negative, output_type=output_type,
+                                                   scheduler=scheduler, use_cuda_graph=use_cuda_graph)

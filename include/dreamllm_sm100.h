@@ -112,6 +112,10 @@ int dllm_zero_rows(void* dst, const int* idx, int R, int H, void* stream);
 /* attention with separate kv length (UNet cross-attention on the dream-query conditioning: Skv = 64 / 77). */
 int dllm_attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int Sq,
                      int Skv, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, void* stream);
+/* kv-cache attention (reference :344-355, :444-449 concat past k/v): k/v live in a preallocated [B, kv_rows, nh*d] cache with Skv valid
+ * rows; causal uses the bottom-right aligned mask (query i is at absolute position Skv - Sq + i). */
+int dllm_attn_fwd_cache(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Skv, int kv_rows, int nh,
+                        int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, void* stream);
 /* ResnetBlock2D / Upsample2D conv: implicit-GEMM 3x3 stride-1 pad-1 on tcgen05 (4-D TMA im2col, zero-fill padding).
  * y = conv(x, w) + bias[c] + rowbias[n, c] (+ residual);  w is [Cout, 3, 3, Cin]. */
 int dllm_conv3x3_nhwc(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, const void* bias,

@@ -1,0 +1,69 @@
+"""kv-cache inference path: prefill + decode == full re-forward; two-pass dream-query prompt embedding == single
+pass over the concatenated sequence (reference get_prompt_embeds, modeling_dreamllm.py:1598-1673); text -> latents pipeline runs."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _model(layers=2):
+    from dreamllm_b200.modeling_dreamllm import DreamLLMConfig, DreamLLMForCausalMLM
+    torch.manual_seed(0)
+    cfg = DreamLLMConfig(vocab_size=32008, hidden_size=256, intermediate_size=512, num_hidden_layers=layers, num_attention_heads=2,
+                         max_position_embeddings=512)
+    return DreamLLMForCausalMLM(cfg)
+
+
+def test_incremental_decode_matches_full_forward():
+    m = _model().to(device="cuda", dtype=BF).eval()
+    ids = torch.randint(0, 32000, (2, 70), device="cuda")
+    with torch.no_grad():
+        full = m(input_ids=ids).logits                       # [B, S, V]
+        out = m(input_ids=ids[:, :50], use_cache=True)       # prefill 50
+        cache = out.past_key_values
+        torch.testing.assert_close(out.logits, full[:, :50], rtol=2e-2, atol=2e-2)
+        steps = [m(input_ids=ids[:, 50:64], past_key_values=cache, use_cache=True).logits]     # continuation of 14 tokens
+        for t in range(64, 70):                                                                # then 1 token at a time
+            steps.append(m(input_ids=ids[:, t:t + 1], past_key_values=cache, use_cache=True).logits)
+    inc = torch.cat(steps, 1)
+    assert cache.len == 70
+    torch.testing.assert_close(inc, full[:, 50:], rtol=2e-2, atol=3e-2)
+    assert float((inc.argmax(-1) == full[:, 50:].argmax(-1)).float().mean()) > 0.97
+
+
+def test_greedy_generate_token_ids_match_recompute():
+    m = _model().to(device="cuda", dtype=BF).eval()
+    ids = torch.randint(0, 32000, (2, 33), device="cuda")
+    gen = m.generate_greedy(ids, max_new_tokens=6)
+    assert gen.shape == (2, 39) and torch.equal(gen[:, :33], ids)
+    with torch.no_grad():
+        for t in range(33, 39):        # every generated token is the argmax of a full re-forward over its prefix
+            ref = m(input_ids=gen[:, :t]).logits[:, -1]
+            top2 = ref.topk(2).values
+            sure = (top2[:, 0] - top2[:, 1]) > 0.05         # ignore near-ties (bf16)
+            assert bool(((ref.argmax(-1) == gen[:, t]) | ~sure).all())
+
+
+def test_prompt_embeds_two_pass_equals_single_pass_and_pipeline_runs():
+    from dreamllm_b200.modeling_plugins import DreamEmbedding, StableDiffusionHead
+    m = _model()
+    Q = 8
+    dream = DreamEmbedding(num_dream_queries=Q, embed_hidden_size=256)
+    m.stable_diffusion_head = StableDiffusionHead(dict(block_out_channels=(64, 128, 256, 256), attention_head_dim=(1, 2, 4, 4),
+                                                       cross_attention_dim=128, vae=dict(block_out_channels=(64, 128, 128, 128))),
+                                                  embed_hidden_size=256)
+    m.model.attach_plugins(None, dream, image_start_id=32003, dream_start_id=32006)
+    m = m.to(device="cuda", dtype=BF).eval()
+    ids = torch.randint(3, 32000, (2, 21), device="cuda")
+    pe = m.get_prompt_embeds(ids)
+    assert pe.shape == (2, Q, 256)
+    # single pass: [text, <dream_start>, Q x <im_patch>, <dream_end>] with the dream-query splice (training layout)
+    full_ids = torch.cat([ids, torch.tensor([[32006] + [32002] * Q + [32007]] * 2, device="cuda")], 1)
+    with torch.no_grad():
+        out = m.model(input_ids=full_ids, images_dm=torch.zeros(2, 1), output_hidden_states=True)
+    want = out.hidden_states[-1][:, 22:22 + Q]
+    torch.testing.assert_close(pe.float(), want.float(), rtol=3e-2, atol=3e-2)
+    neg = torch.randint(3, 32000, (2, 5), device="cuda")
+    lat = m.stable_diffusion_pipeline(ids, neg, guidance_scale=3.0, num_inference_steps=3, height=128, width=128, scheduler="ddim")
+    assert lat.shape == (2, 4, 16, 16) and torch.isfinite(lat).all()
