@@ -310,9 +310,11 @@ int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* 
 }
 int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout,
                           cudaStream_t s) {
-  if (Cout != 4 && Cout != 8) return DLLM_ERR_UNSUPPORTED;
+  if (Cout != 4 && Cout != 8 && Cout != 3) return DLLM_ERR_UNSUPPORTED;
   const long warps = static_cast<long>(B) * H * W;
-  if (Cout == 4)
+  if (Cout == 3)
+    conv_out_kernel<3><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, y, B, C, H, W);
+  else if (Cout == 4)
     conv_out_kernel<4><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, y, B, C, H, W);
   else
     conv_out_kernel<8><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)bias, y, B, C, H, W);

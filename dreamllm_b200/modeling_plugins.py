@@ -407,7 +407,7 @@ class StableDiffusionHead(MultimodalHead):
 
     Built: the training `forward` (:493-577: VAE encode -> add_noise -> UNet fwd + dgrad-only backward -> MSE) and the sampler
     (`pipeline`, :672-850) on the native UNet with a CUDA-graph loop, `output_type="latent"`.
-    Not built yet: VAE *decode* for `output_type != "latent"` (raises NotImplementedError — no silent fallback).
+    `output_type` "latent" | "pt" | "np" (VAE decode on the native decoder); PIL conversion is host glue and not provided.
     `diffusion_name_or_path` may be a dict of UNet config overrides for random init (no checkpoints exist in the sandbox);
     a checkpoint directory is loaded through safetensors into the native module (identical key names).
     """
@@ -419,7 +419,7 @@ class StableDiffusionHead(MultimodalHead):
                  freeze_vae: bool = True, freeze_unet: bool = True, freeze_projector: bool = False, local_files_only: bool = False):
         super().__init__()
         from .unet import UNet2DConditionModel
-        from .vae import AutoencoderKLEncoder
+        from .vae import AutoencoderKLDecoder, AutoencoderKLEncoder
         self.save_model_name = "stable_diffusion_head"
         self.diffusion_name_or_path = diffusion_name_or_path
         self.projector_type, self.projector_depth = projector_type, projector_depth
@@ -450,6 +450,11 @@ class StableDiffusionHead(MultimodalHead):
             vf = glob.glob(os.path.join(diffusion_name_or_path, "vae", "*.safetensors"))
             if vf:
                 self.vae.load_state_dict(load_file(vf[0]), strict=False)      # decoder.* / post_quant_conv.* are not part of this path
+        # decode half of the same AutoencoderKL (separate module so its keys stay `decoder.*` / `post_quant_conv.*`)
+        self.vae_decoder = AutoencoderKLDecoder(vae_cfg if not isinstance(diffusion_name_or_path, str) else None)
+        if isinstance(diffusion_name_or_path, str) and vf:
+            self.vae_decoder.load_state_dict(load_file(vf[0]), strict=False)
+        self.vae_decoder.requires_grad_(False)
         self.vae.requires_grad_(False)
         projector_cfg = dict(projector=projector_type, freeze_projector=freeze_projector, depth=projector_depth,
                              save_model_name=self.save_model_name, model_name_or_path=None)
@@ -534,12 +539,17 @@ class StableDiffusionHead(MultimodalHead):
         assert prompt_embeds is not None, "`prompt_embeds` must be provided by LLM."
         if guidance_rescale > 0.0 or callback is not None or (num_images_per_prompt or 1) != 1:
             raise NotImplementedError("guidance_rescale / callback / num_images_per_prompt>1 are not built")
-        if output_type != "latent":
-            raise NotImplementedError("VAE decode is SURVEY §8(f) row 1 (next); use output_type='latent'")
+        if output_type not in ("latent", "pt", "np"):
+            raise NotImplementedError("output_type must be 'latent', 'pt' or 'np' (PIL conversion is host-side glue)")
         cond = self.projector(prompt_embeds)[-1]
         if guidance_scale > 1.0:
             assert negative_prompt_embeds is not None, "When using classifier free guidance, `negative_prompt_embeds` must be provided by LLM."
             cond = torch.cat([self.projector(negative_prompt_embeds)[-1], cond])
         loop = DenoiseLoop(self.unet, cond, num_inference_steps, guidance_scale, scheduler, latents=latents, height=height, width=width,
                            use_cuda_graph=use_cuda_graph, generator=generator)
-        return loop.run()
+        lat = loop.run()
+        if output_type == "latent":
+            return lat
+        image = self.vae_decoder.decode(lat)                                  # vae.decode(latents / scaling_factor), :842
+        image = (image / 2 + 0.5).clamp(0, 1)                                 # VaeImageProcessor.postprocess denormalize
+        return image if output_type == "pt" else image.permute(0, 2, 3, 1).cpu().numpy()

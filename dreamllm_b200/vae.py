@@ -138,3 +138,70 @@ class AutoencoderKLEncoder(nn.Module):
             z = torch.randn((B, L, h.shape[2], h.shape[3]), device=h.device, dtype=torch.float32, generator=generator)
         wq = self.quant_conv.weight.view(2 * L, 2 * L)
         return ops.vae_sample(h, wq, self.quant_conv.bias, z.float().contiguous(), self.cfg["scaling_factor"])
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+
+class Decoder(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        ch, G, L = c["block_out_channels"], c["norm_num_groups"], c["layers_per_block"]
+        rev = list(reversed(ch))
+        self.conv_in = nn.Conv2d(c["latent_channels"], rev[0], 3, padding=1)
+        self.mid_block = _B()
+        self.mid_block.resnets = nn.ModuleList([ResnetBlock2D(rev[0], rev[0], G), ResnetBlock2D(rev[0], rev[0], G)])
+        self.mid_block.attentions = nn.ModuleList([Attention(rev[0], G)])
+        self.up_blocks = nn.ModuleList()
+        out = rev[0]
+        for i, co in enumerate(rev):
+            b = _B()
+            cin, out = out, co
+            b.resnets = nn.ModuleList([ResnetBlock2D(cin if j == 0 else out, out, G) for j in range(L + 1)])
+            if i < len(ch) - 1:
+                b.upsamplers = nn.ModuleList([Upsample2D(out)])
+            self.up_blocks.append(b)
+        self.conv_norm_out = nn.GroupNorm(G, ch[0], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[0], c["in_channels"], 3, padding=1)
+
+
+class AutoencoderKLDecoder(AutoencoderKLEncoder):
+    """`vae.decode(latents / scaling_factor)` (modeling_plugins.py:842; 2 514.5 GFLOP per 512x512 image) on the same
+    kernels as the encoder.  Keys: `decoder.*`, `post_quant_conv.*` (diffusers)."""
+
+    def __init__(self, cfg=None):
+        nn.Module.__init__(self)
+        c = dict(SDVAE)
+        c.update(cfg or {})
+        self.cfg = c
+        self.decoder = Decoder(c)
+        self.post_quant_conv = nn.Conv2d(c["latent_channels"], c["latent_channels"], 1)
+        self._wcache = {}
+
+    @torch.no_grad()
+    def decode(self, latents):
+        """latents [B,4,h,w] fp32 (scaled) -> images [B,3,8h,8w] fp32 in roughly [-1, 1]."""
+        if not latents.is_cuda:
+            raise RuntimeError("dreamllm_b200 VAE decoder requires CUDA tensors; there is no CPU fallback")
+        d = self.decoder
+        L = self.cfg["latent_channels"]
+        z = latents.float() / self.cfg["scaling_factor"]
+        B = z.shape[0]
+        # post_quant_conv (1x1, 4 -> 4) folded into conv_in's input: tiny, done as a per-pixel 4x4 matmul on the fp32 latents
+        wq = self.post_quant_conv.weight.view(L, L).float()
+        z = torch.einsum("oc,bchw->bohw", wq, z) + self.post_quant_conv.bias.float().view(1, L, 1, 1)
+        x = ops.conv_in(z.contiguous(), d.conv_in.weight, d.conv_in.bias, B)
+        x = self._resnet(d.mid_block.resnets[0], x)
+        x = self._attention(d.mid_block.attentions[0], x)
+        x = self._resnet(d.mid_block.resnets[1], x)
+        for b in d.up_blocks:
+            for r in b.resnets:
+                x = self._resnet(r, x)
+            if hasattr(b, "upsamplers"):
+                conv = b.upsamplers[0].conv
+                x = ops.conv3x3(ops.upsample2x(x), self._conv_w(conv), bias=conv.bias)
+        x = ops.groupnorm(x, d.conv_norm_out.weight, d.conv_norm_out.bias, self.cfg["norm_num_groups"], d.conv_norm_out.eps, silu=True)
+        return ops.conv_out(x, d.conv_out.weight, d.conv_out.bias)

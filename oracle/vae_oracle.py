@@ -106,3 +106,62 @@ class AutoencoderKLEncoder(nn.Module):
         mean, logvar = moments.chunk(2, dim=1)
         logvar = torch.clamp(logvar, -30.0, 20.0)
         return (mean + torch.exp(0.5 * logvar) * z) * self.cfg["scaling_factor"]
+
+
+class Upsample2D(nn.Module):
+    def __init__(self, c):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+    def forward(self, x):
+        return self.conv(F.interpolate(x, scale_factor=2.0, mode="nearest"))
+
+
+class Decoder(nn.Module):
+    """diffusers vae.Decoder: conv_in -> mid (res, attn, res) -> 4 UpDecoderBlock2D (layers_per_block + 1 resnets each) -> GN/SiLU/conv_out."""
+
+    def __init__(self, c):
+        super().__init__()
+        ch, G, L = c["block_out_channels"], c["norm_num_groups"], c["layers_per_block"]
+        rev = list(reversed(ch))
+        self.conv_in = nn.Conv2d(c["latent_channels"], rev[0], 3, padding=1)
+        self.mid_block = _B()
+        self.mid_block.resnets = nn.ModuleList([ResnetBlock2D(rev[0], rev[0], G), ResnetBlock2D(rev[0], rev[0], G)])
+        self.mid_block.attentions = nn.ModuleList([Attention(rev[0], G)])
+        self.up_blocks = nn.ModuleList()
+        out = rev[0]
+        for i, co in enumerate(rev):
+            b = _B()
+            cin, out = out, co
+            b.resnets = nn.ModuleList([ResnetBlock2D(cin if j == 0 else out, out, G) for j in range(L + 1)])
+            if i < len(ch) - 1:
+                b.upsamplers = nn.ModuleList([Upsample2D(out)])
+            self.up_blocks.append(b)
+        self.conv_norm_out = nn.GroupNorm(G, ch[0], eps=1e-6)
+        self.conv_out = nn.Conv2d(ch[0], c["in_channels"], 3, padding=1)
+
+    def forward(self, z):
+        x = self.conv_in(z)
+        x = self.mid_block.resnets[0](x)
+        x = self.mid_block.attentions[0](x)
+        x = self.mid_block.resnets[1](x)
+        for b in self.up_blocks:
+            for r in b.resnets:
+                x = r(x)
+            if hasattr(b, "upsamplers"):
+                x = b.upsamplers[0](x)
+        return self.conv_out(F.silu(self.conv_norm_out(x)))
+
+
+class AutoencoderKLDecoder(nn.Module):
+    def __init__(self, cfg=None):
+        super().__init__()
+        c = dict(SDVAE)
+        c.update(cfg or {})
+        self.cfg = c
+        self.decoder = Decoder(c)
+        self.post_quant_conv = nn.Conv2d(c["latent_channels"], c["latent_channels"], 1)
+
+    def decode(self, latents):
+        """`self.vae.decode(latents / scaling_factor)` (modeling_plugins.py:842)."""
+        return self.decoder(self.post_quant_conv(latents / self.cfg["scaling_factor"]))

@@ -67,3 +67,6 @@ def test_prompt_embeds_two_pass_equals_single_pass_and_pipeline_runs():
     neg = torch.randint(3, 32000, (2, 5), device="cuda")
     lat = m.stable_diffusion_pipeline(ids, neg, guidance_scale=3.0, num_inference_steps=3, height=128, width=128, scheduler="ddim")
     assert lat.shape == (2, 4, 16, 16) and torch.isfinite(lat).all()
+    img = m.stable_diffusion_pipeline(ids, neg, guidance_scale=3.0, num_inference_steps=2, height=128, width=128, scheduler="ddim",
+                                      output_type="pt")
+    assert img.shape == (2, 3, 128, 128) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0

@@ -121,3 +121,24 @@ def test_creation_step_end_to_end():
     assert gq is not None and torch.isfinite(gq.float()).all() and float(gq.float().abs().sum()) > 0
     assert m.stable_diffusion_head.projector.projector.weight.grad is not None
     assert m.model.layers[0].mlp.down_proj.weight.grad is None                    # frozen LLM: dgrad only
+
+
+@pytest.mark.parametrize("cfg,B,R", [(SMALL_VAE, 2, 8), (None, 1, 32)])
+def test_vae_decode_vs_oracle(cfg, B, R):
+    from dreamllm_b200.vae import AutoencoderKLDecoder
+    torch.manual_seed(4)
+    ref = VO.AutoencoderKLDecoder(cfg).eval()
+    for n, p in ref.named_parameters():
+        if p.dim() == 1:
+            p.data.add_(0.05 * torch.randn_like(p))
+    ours = AutoencoderKLDecoder(cfg)
+    assert list(ours.state_dict().keys()) == list(ref.state_dict().keys())
+    ours.load_state_dict(ref.state_dict())
+    ours = ours.to(device="cuda", dtype=BF)
+    lat = torch.randn(B, 4, R, R, generator=torch.Generator().manual_seed(5)) * 0.18215
+    with torch.no_grad():
+        want = ref.decode(lat)
+    got = ours.decode(lat.cuda()).cpu()
+    e = _rel(got, want)
+    print(f"vae decode rel err {e:.4f}")
+    assert got.shape == want.shape == (B, 3, 8 * R, 8 * R) and e < 5e-2, e
