@@ -26,15 +26,20 @@ constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 256;
 constexpr int kEpiWarp0 = 4;
 
+#ifndef DLLM_EPI_BUFS
+#define DLLM_EPI_BUFS 2   // staging buffers per epilogue warp (TMA stores in flight per warp)
+#endif
+
 template <int kCta>
 struct GemmCfg {
   static constexpr int kBRows = BN / kCta;  // rows of B each CTA loads
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (kCta == 1) ? 4 : 6;
+  static constexpr int kEpiBufs = DLLM_EPI_BUFS;
+  static constexpr int kStages = (kCta == 1) ? (kEpiBufs <= 2 ? 4 : 3) : (kEpiBufs <= 2 ? 6 : 5);
   static constexpr int kEpiBufBytes = 32 * 128;                // 32 rows x 128 B per warp-store
-  static constexpr int kEpiBytes = 4 * 2 * kEpiBufBytes;       // 4 warps x double buffer
+  static constexpr int kEpiBytes = 4 * kEpiBufs * kEpiBufBytes;
   static constexpr int kBarBytes = 1024;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024 /*align slack*/;
 };
@@ -66,7 +71,10 @@ __device__ __forceinline__ float epi_act(float x, int act) {
   return x;
 }
 
-template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false>
+// kEpi: 0 = plain store, 1 = + bias / row-group bias / residual, 2 = 1 + activation.  Compile-time so that the plain and the
+// bias-only epilogues carry none of the (inlined expf / erff) activation code: with a runtime switch every element paid ~78 issue
+// slots of predicated-off instructions and bias GEMMs with small K ran at 200 TF/s (profiles/r01_gemm_smallk_epilogue.md).
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi, ConvGeom cg,
@@ -278,7 +286,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else if (warp_idx >= kEpiWarp0) {
     // ======================= epilogue warps =======================
     const int wq = warp_idx - kEpiWarp0;  // TMEM lane quarter: this warp may touch lanes [32*wq, 32*wq+32)
-    uint8_t* my_epi = epi_smem + wq * 2 * Cfg::kEpiBufBytes;
+    uint8_t* my_epi = epi_smem + wq * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
     const uint32_t tmem_empty0_cluster = (kCta == 2) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     int it = 0;
     int buf = 0;
@@ -307,44 +315,58 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         tmem_ld32(taddr0 + c * CH, v);
         if constexpr (!kOutF32) tmem_ld32(taddr0 + c * CH + 32, v + 32);
         tmem_ld_wait();
-        if (epi.bias != nullptr || epi.act != 0 || epi.residual != nullptr || epi.rowbias != nullptr) {
+        if constexpr (kEpi > 0) {
           const int gcol = col0 + c * CH;
           const int grow = row0 + lane;
 #pragma unroll
           for (int j = 0; j < CH / 8; ++j) {
             const int cj = gcol + j * 8;
-            float bsv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            float rsv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
             const bool col_ok = cj + 8 <= N;
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = __uint_as_float(v[j * 8 + e]);
             if (epi.bias != nullptr && col_ok) {
               const uint4 q = __ldg(reinterpret_cast<const uint4*>(epi.bias + cj));
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); bsv[2 * e] = f.x; bsv[2 * e + 1] = f.y; }
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); x[2 * e] += f.x; x[2 * e + 1] += f.y; }
             }
             if (epi.rowbias != nullptr && col_ok && grow < M) {
               const uint4 q = __ldg(reinterpret_cast<const uint4*>(epi.rowbias + static_cast<size_t>(grow / epi.rows_per_group) * N + cj));
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); bsv[2 * e] += f.x; bsv[2 * e + 1] += f.y; }
+              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); x[2 * e] += f.x; x[2 * e + 1] += f.y; }
+            }
+            if constexpr (kEpi == 2) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = __bfloat162float(__float2bfloat16_rn(x[e]));
+              if (epi.act == 1) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = x[e] / (1.f + __expf(-1.702f * x[e]));
+              } else if (epi.act == 2) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = 0.5f * x[e] * (1.f + erff(x[e] * 0.70710678118654752f));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x[e] = x[e] / (1.f + __expf(-x[e]));
+              }
             }
             if (epi.residual != nullptr && col_ok && grow < M) {
               const uint4 q = *reinterpret_cast<const uint4*>(epi.residual + static_cast<size_t>(grow) * epi.ldr + cj);
               const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-              for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); rsv[2 * e] = f.x; rsv[2 * e + 1] = f.y; }
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __bfloat1622float2(h2[e]);
+                x[2 * e] = __bfloat162float(__float2bfloat16_rn(x[2 * e])) + f.x;
+                x[2 * e + 1] = __bfloat162float(__float2bfloat16_rn(x[2 * e + 1])) + f.y;
+              }
             }
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-              float x = __uint_as_float(v[j * 8 + e]) + bsv[e];
-              if (epi.act != 0) x = epi_act(__bfloat162float(__float2bfloat16_rn(x)), epi.act);
-              if (epi.residual != nullptr) x = __bfloat162float(__float2bfloat16_rn(x)) + rsv[e];
-              v[j * 8 + e] = __float_as_uint(x);
-            }
+            for (int e = 0; e < 8; ++e) v[j * 8 + e] = __float_as_uint(x[e]);
           }
         }
         // the staging buffer we are about to overwrite was handed to TMA two stores ago
-        if (lane == 0) tma_store_wait_read<1>();
+        if (lane == 0) tma_store_wait_read<Cfg::kEpiBufs - 1>();
         __syncwarp();
         uint8_t* dst = my_epi + buf * Cfg::kEpiBufBytes + lane * 128;
 #pragma unroll
@@ -367,7 +389,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             tma_store_2d(&tma_c, my_epi + buf * Cfg::kEpiBufBytes, col0 + c * CH, row0);
           tma_store_commit();
         }
-        buf ^= 1;
+        buf = (buf + 1 == Cfg::kEpiBufs) ? 0 : buf + 1;
       }
       // all TMEM reads of this accumulator are complete -> hand it back to the MMA warp
       tc_fence_before();
@@ -454,11 +476,11 @@ static int* tile_counter_slot(cudaStream_t stream) {
   return slot;
 }
 
-template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false>
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                        const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}) {
   using Cfg = GemmCfg<kCta>;
-  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv>;
+  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv, kEpi>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
@@ -518,6 +540,15 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   rc = make_tmap_2d(&tc, C, out_fp32 ? 4 : 2, M, N, ldc, 32, out_fp32 ? 32 : 64);
   if (rc) return rc;
 
+  const int emode = (act != 0) ? 2 : ((bias || residual) ? 1 : 0);
+  if (emode != 0) {
+    // fused epilogues exist for the forward (NT, bf16 out) contraction only
+    if (a_mn || b_mn || out_fp32) return DLLM_ERR_UNSUPPORTED;
+    if (kcta == 2) return emode == 2 ? launch_gemm<2, false, false, bf16, false, 2>(ta, tb, tc, M, N, K, epi, stream)
+                                     : launch_gemm<2, false, false, bf16, false, 1>(ta, tb, tc, M, N, K, epi, stream);
+    return emode == 2 ? launch_gemm<1, false, false, bf16, false, 2>(ta, tb, tc, M, N, K, epi, stream)
+                      : launch_gemm<1, false, false, bf16, false, 1>(ta, tb, tc, M, N, K, epi, stream);
+  }
 #define DLLM_GEMM_CASE(CTA, AMN, BMN)                                                                 \
   if (kcta == CTA && (a_mn != 0) == AMN && (b_mn != 0) == BMN) {                                      \
     return out_fp32 ? launch_gemm<CTA, AMN, BMN, float>(ta, tb, tc, M, N, K, epi, stream)             \
@@ -574,8 +605,11 @@ int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, 
   if ((rc = make_tmap_2d(&tc, y, 2, M, Cout, Cout, 32, 64))) return rc;
   GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), Cout, 0, static_cast<const bf16*>(rowbias), HW};
   ConvGeom cg{Cin / 64, W, H, HW};
-  if (kcta == 2) return launch_gemm<2, false, false, bf16, true>(ta, tb, tc, M, Cout, K, epi, stream, cg);
-  return launch_gemm<1, false, false, bf16, true>(ta, tb, tc, M, Cout, K, epi, stream, cg);
+  const bool any_epi = bias || rowbias || residual;
+  if (kcta == 2) return any_epi ? launch_gemm<2, false, false, bf16, true, 1>(ta, tb, tc, M, Cout, K, epi, stream, cg)
+                                : launch_gemm<2, false, false, bf16, true, 0>(ta, tb, tc, M, Cout, K, epi, stream, cg);
+  return any_epi ? launch_gemm<1, false, false, bf16, true, 1>(ta, tb, tc, M, Cout, K, epi, stream, cg)
+                 : launch_gemm<1, false, false, bf16, true, 0>(ta, tb, tc, M, Cout, K, epi, stream, cg);
 }
 
 }  // namespace dllm
