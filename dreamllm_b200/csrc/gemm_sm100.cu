@@ -23,7 +23,8 @@ constexpr int BM = 128;  // A rows per CTA == TMEM lanes
 constexpr int BN = 256;  // UMMA N
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle line
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 256;
+constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, each draining half of the tile's columns
+constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
 constexpr int kEpiWarp0 = 4;
 
 #ifndef DLLM_EPI_BUFS
@@ -37,9 +38,9 @@ struct GemmCfg {
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBufs = DLLM_EPI_BUFS;
-  static constexpr int kStages = (kCta == 1) ? (kEpiBufs <= 2 ? 4 : 3) : (kEpiBufs <= 2 ? 6 : 5);
+  static constexpr int kStages = (kCta == 1) ? 3 : 5;          // 144 / 160 KB of operand stages + 64 KB of store staging
   static constexpr int kEpiBufBytes = 32 * 128;                // 32 rows x 128 B per warp-store
-  static constexpr int kEpiBytes = 4 * kEpiBufs * kEpiBufBytes;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiBufBytes;
   static constexpr int kBarBytes = 1024;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024 /*align slack*/;
 };
@@ -118,11 +119,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4 * kCta);  // one arrive per epilogue warp of every CTA in the pair
+      mbar_init(&tmem_empty_bar[i], kEpiWarps * kCta);  // one arrive per epilogue warp of every CTA in the pair
     }
     for (int i = 0; i < kRing; ++i) {
       mbar_init(&ring_full[i], 1);
-      mbar_init(&ring_empty[i], 5 * kCta);     // leader: MMA + 4 epilogue warps; peer: TMA thread + 4 epilogue warps
+      mbar_init(&ring_empty[i], (kEpiWarps + 1) * kCta);  // leader: MMA + epilogue warps; peer: TMA thread + epilogue warps
     }
     fence_mbar_init();
   }
@@ -285,8 +286,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp_idx >= kEpiWarp0) {
     // ======================= epilogue warps =======================
-    const int wq = warp_idx - kEpiWarp0;  // TMEM lane quarter: this warp may touch lanes [32*wq, 32*wq+32)
-    uint8_t* my_epi = epi_smem + wq * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
+    const int ew = warp_idx - kEpiWarp0;  // 0..7
+    const int wq = ew & 3;                // TMEM lane quarter: this warp may touch lanes [32*wq, 32*wq+32)
+    const int chalf = ew >> 2;            // which half of the tile's column chunks this warp drains
+    uint8_t* my_epi = epi_smem + ew * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
     const uint32_t tmem_empty0_cluster = (kCta == 2) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     int it = 0;
     int buf = 0;
@@ -310,7 +313,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
+      for (int c = chalf * (kChunks / 2); c < (chalf + 1) * (kChunks / 2); ++c) {
         uint32_t v[kOutF32 ? 32 : 64];
         tmem_ld32(taddr0 + c * CH, v);
         if constexpr (!kOutF32) tmem_ld32(taddr0 + c * CH + 32, v + 32);
