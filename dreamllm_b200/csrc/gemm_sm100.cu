@@ -23,22 +23,23 @@ constexpr int BM = 128;  // A rows per CTA == TMEM lanes
 constexpr int BN = 256;  // UMMA N
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle line
 constexpr int UMMA_K = 16;
-constexpr int kEpiWarps = 8;    // two warps per TMEM lane quarter, each draining half of the tile's columns
-constexpr int kGemmThreads = 128 + 32 * kEpiWarps;
+// epilogue warps: 4 (one per TMEM lane quarter; 6/4 operand stages) for mainloop-bound shapes, 8 (two per quarter, each draining half
+// of the tile's columns; 5/3 stages) for epilogue-bound ones (small K, fused epilogues).  Same-box A/B: profiles/r01_gemm_smallk_epilogue.md
+constexpr int gemm_threads(int ew) { return 128 + 32 * ew; }
 constexpr int kEpiWarp0 = 4;
 
 #ifndef DLLM_EPI_BUFS
 #define DLLM_EPI_BUFS 2   // staging buffers per epilogue warp (TMA stores in flight per warp)
 #endif
 
-template <int kCta>
+template <int kCta, int kEpiWarps = 4>
 struct GemmCfg {
   static constexpr int kBRows = BN / kCta;  // rows of B each CTA loads
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBufs = DLLM_EPI_BUFS;
-  static constexpr int kStages = (kCta == 1) ? 3 : 5;          // 144 / 160 KB of operand stages + 64 KB of store staging
+  static constexpr int kStages = (kEpiWarps == 8) ? ((kCta == 1) ? 3 : 5) : ((kCta == 1) ? 4 : 6);  // operand stages + store staging <= 227 KB
   static constexpr int kEpiBufBytes = 32 * 128;                // 32 rows x 128 B per warp-store
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiBufBytes;
   static constexpr int kBarBytes = 1024;
@@ -75,12 +76,12 @@ __device__ __forceinline__ float epi_act(float x, int act) {
 // kEpi: 0 = plain store, 1 = + bias / row-group bias / residual, 2 = 1 + activation.  Compile-time so that the plain and the
 // bias-only epilogues carry none of the (inlined expf / erff) activation code: with a runtime switch every element paid ~78 issue
 // slots of predicated-off instructions and bias GEMMs with small K ran at 200 TF/s (profiles/r01_gemm_smallk_epilogue.md).
-template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEpiWarps = 4>
+__global__ void __launch_bounds__(gemm_threads(kEpiWarps), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi, ConvGeom cg,
             int* __restrict__ tile_counter) {
-  using Cfg = GemmCfg<kCta>;
+  using Cfg = GemmCfg<kCta, kEpiWarps>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kOutF32 = sizeof(OutT) == 4;
   constexpr int CH = kOutF32 ? 32 : 64;  // output columns per 128-byte store line
@@ -288,7 +289,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // ======================= epilogue warps =======================
     const int ew = warp_idx - kEpiWarp0;  // 0..7
     const int wq = ew & 3;                // TMEM lane quarter: this warp may touch lanes [32*wq, 32*wq+32)
-    const int chalf = ew >> 2;            // which half of the tile's column chunks this warp drains
+    const int chalf = ew >> 2;            // which part of the tile's column chunks this warp drains
+    constexpr int kParts = kEpiWarps / 4;
     uint8_t* my_epi = epi_smem + ew * Cfg::kEpiBufs * Cfg::kEpiBufBytes;
     const uint32_t tmem_empty0_cluster = (kCta == 2) ? mapa_shared(smem_u32(&tmem_empty_bar[0]), 0) : 0u;
     int it = 0;
@@ -313,7 +315,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c = chalf * (kChunks / 2); c < (chalf + 1) * (kChunks / 2); ++c) {
+      for (int c = chalf * (kChunks / kParts); c < (chalf + 1) * (kChunks / kParts); ++c) {
         uint32_t v[kOutF32 ? 32 : 64];
         tmem_ld32(taddr0 + c * CH, v);
         if constexpr (!kOutF32) tmem_ld32(taddr0 + c * CH + 32, v + 32);
@@ -479,11 +481,11 @@ static int* tile_counter_slot(cudaStream_t stream) {
   return slot;
 }
 
-template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0>
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEW = 4>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
                        const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}) {
-  using Cfg = GemmCfg<kCta>;
-  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv, kEpi>;
+  using Cfg = GemmCfg<kCta, kEW>;
+  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
@@ -499,7 +501,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   const int group_m = (kCta == 2) ? 8 : 16;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(clusters * kCta);
-  cfg.blockDim = dim3(kGemmThreads);
+  cfg.blockDim = dim3(gemm_threads(kEW));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -547,10 +549,14 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   if (emode != 0) {
     // fused epilogues exist for the forward (NT, bf16 out) contraction only
     if (a_mn || b_mn || out_fp32) return DLLM_ERR_UNSUPPORTED;
-    if (kcta == 2) return emode == 2 ? launch_gemm<2, false, false, bf16, false, 2>(ta, tb, tc, M, N, K, epi, stream)
-                                     : launch_gemm<2, false, false, bf16, false, 1>(ta, tb, tc, M, N, K, epi, stream);
-    return emode == 2 ? launch_gemm<1, false, false, bf16, false, 2>(ta, tb, tc, M, N, K, epi, stream)
-                      : launch_gemm<1, false, false, bf16, false, 1>(ta, tb, tc, M, N, K, epi, stream);
+    if (kcta == 2) return emode == 2 ? launch_gemm<2, false, false, bf16, false, 2, 8>(ta, tb, tc, M, N, K, epi, stream)
+                                     : launch_gemm<2, false, false, bf16, false, 1, 8>(ta, tb, tc, M, N, K, epi, stream);
+    return emode == 2 ? launch_gemm<1, false, false, bf16, false, 2, 8>(ta, tb, tc, M, N, K, epi, stream)
+                      : launch_gemm<1, false, false, bf16, false, 1, 8>(ta, tb, tc, M, N, K, epi, stream);
+  }
+  if (!a_mn && !b_mn && !out_fp32 && K <= 2048) {   // epilogue-bound plain forward GEMMs (UNet / CLIP projections)
+    if (kcta == 2) return launch_gemm<2, false, false, bf16, false, 0, 8>(ta, tb, tc, M, N, K, epi, stream);
+    return launch_gemm<1, false, false, bf16, false, 0, 8>(ta, tb, tc, M, N, K, epi, stream);
   }
 #define DLLM_GEMM_CASE(CTA, AMN, BMN)                                                                 \
   if (kcta == CTA && (a_mn != 0) == AMN && (b_mn != 0) == BMN) {                                      \
@@ -609,10 +615,10 @@ int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, 
   GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), Cout, 0, static_cast<const bf16*>(rowbias), HW};
   ConvGeom cg{Cin / 64, W, H, HW};
   const bool any_epi = bias || rowbias || residual;
-  if (kcta == 2) return any_epi ? launch_gemm<2, false, false, bf16, true, 1>(ta, tb, tc, M, Cout, K, epi, stream, cg)
-                                : launch_gemm<2, false, false, bf16, true, 0>(ta, tb, tc, M, Cout, K, epi, stream, cg);
-  return any_epi ? launch_gemm<1, false, false, bf16, true, 1>(ta, tb, tc, M, Cout, K, epi, stream, cg)
-                 : launch_gemm<1, false, false, bf16, true, 0>(ta, tb, tc, M, Cout, K, epi, stream, cg);
+  if (kcta == 2) return any_epi ? launch_gemm<2, false, false, bf16, true, 1, 8>(ta, tb, tc, M, Cout, K, epi, stream, cg)
+                                : launch_gemm<2, false, false, bf16, true, 0, 4>(ta, tb, tc, M, Cout, K, epi, stream, cg);
+  return any_epi ? launch_gemm<1, false, false, bf16, true, 1, 8>(ta, tb, tc, M, Cout, K, epi, stream, cg)
+                 : launch_gemm<1, false, false, bf16, true, 0, 4>(ta, tb, tc, M, Cout, K, epi, stream, cg);
 }
 
 }  // namespace dllm
