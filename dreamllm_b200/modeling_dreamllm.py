@@ -346,8 +346,10 @@ class KVCache:
     reference's per-layer `torch.cat([past, new], dim=2)` tuples (:444-449); opaque to callers, passed as `past_key_values`."""
 
     def __init__(self, num_layers, batch, max_len, num_heads, head_dim, device, dtype=BF16):
-        self.k = [torch.empty((batch, max_len, num_heads, head_dim), device=device, dtype=dtype) for _ in range(num_layers)]
-        self.v = [torch.empty((batch, max_len, num_heads, head_dim), device=device, dtype=dtype) for _ in range(num_layers)]
+        # zero-filled: the attention kernel reads whole 64-row tiles; rows past the valid length are masked in the softmax (p = 0) but
+        # still multiply into P.V, so they must be finite (0 * NaN from recycled allocator memory poisoned the output otherwise)
+        self.k = [torch.zeros((batch, max_len, num_heads, head_dim), device=device, dtype=dtype) for _ in range(num_layers)]
+        self.v = [torch.zeros((batch, max_len, num_heads, head_dim), device=device, dtype=dtype) for _ in range(num_layers)]
         self.len = 0
         self.max_len = max_len
 
