@@ -109,6 +109,7 @@ SIGNATURES = {
     "dllm_conv_out_bwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dllm_add_noise": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _l, _vp]),
     "dllm_mse_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _l, _vp]),
+    "dllm_mse_minsnr_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _l, _vp]),
     "dllm_softmax_rows": (_i, [_vp, _l, _i, _f, _vp]),
     "dllm_vae_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _l, _f, _vp]),
 }

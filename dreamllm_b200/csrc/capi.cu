@@ -256,6 +256,11 @@ int dllm_mse_fwd_bwd(const float* pred, const float* target, float* loss, float*
   ensure_context(pred);
   return mse_fwd_bwd(pred, target, loss, dpred, n, S(stream));
 }
+int dllm_mse_minsnr_fwd_bwd(const float* pred, const float* target, const int* t, const float* alphas_cumprod, float snr_gamma,
+                            float* loss, float* dpred, int B, long per_sample, void* stream) {
+  ensure_context(pred);
+  return mse_minsnr_fwd_bwd(pred, target, t, alphas_cumprod, snr_gamma, loss, dpred, B, per_sample, S(stream));
+}
 
 int dllm_softmax_rows(void* x, long rows, int cols, float scale, void* stream) {
   ensure_context(x);

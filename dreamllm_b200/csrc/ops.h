@@ -66,6 +66,8 @@ int copy_cols2(const void* src, void* dst, long rows, int Cs, int Cd, int scol0,
 int conv_out_bwd(const float* dy, const void* w, void* dx, int B, int C, int H, int W, int Cout, cudaStream_t s);
 int add_noise(const float* x0, const float* noise, const int* t, const float* ac, float* out, int B, long per_sample, cudaStream_t s);
 int mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, cudaStream_t s);
+int mse_minsnr_fwd_bwd(const float* pred, const float* target, const int* t, const float* ac, float gamma, float* loss, float* dpred,
+                       int B, long per_sample, cudaStream_t s);
 int softmax_rows(void* x, long rows, int cols, float scale, cudaStream_t s);
 int vae_sample(const float* h, const void* wq, const void* bq, const float* z, float* out, int B, int L, long plane, float scaling,
                cudaStream_t s);

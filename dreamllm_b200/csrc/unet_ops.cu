@@ -785,6 +785,39 @@ int mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpre
   mse_fwd_bwd_kernel<<<1, 1024, 0, s>>>(pred, target, loss, dpred, n);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
+// min-SNR weighted variant (reference modeling_plugins.py:561-572, `_compute_snr` :468-491):
+//   snr_b = (sqrt(ac[t_b]) / sqrt(1 - ac[t_b]))^2,  w_b = min(snr_b, gamma) / snr_b,
+//   loss = mean_b( w_b * mean_chw((pred - target)^2) ),  dpred = 2 w_b (pred - target) / n.
+__global__ void mse_minsnr_fwd_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, const int* __restrict__ t,
+                                          const float* __restrict__ alphas_cumprod, float gamma, float* __restrict__ loss,
+                                          float* __restrict__ dpred, long per_sample, long n) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const float inv = 1.f / static_cast<float>(n);
+  for (long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float ac = alphas_cumprod[t[i / per_sample]];
+    const float r = sqrtf(ac) / sqrtf(1.f - ac);
+    const float snr = r * r;
+    const float w = fminf(snr, gamma) / snr;
+    const float d = pred[i] - target[i];
+    acc += w * d * d;
+    dpred[i] = 2.f * w * d * inv;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) loss[0] = v * inv;
+  }
+}
+int mse_minsnr_fwd_bwd(const float* pred, const float* target, const int* t, const float* ac, float gamma, float* loss, float* dpred,
+                       int B, long per_sample, cudaStream_t s) {
+  if (B <= 0 || per_sample <= 0 || !(gamma > 0.f)) return DLLM_ERR_SHAPE;
+  mse_minsnr_fwd_bwd_kernel<<<1, 1024, 0, s>>>(pred, target, t, ac, gamma, loss, dpred, per_sample, static_cast<long>(B) * per_sample);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
 
 
 // ================================================================================================ VAE encoder helpers

@@ -672,9 +672,9 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
                 past_key_values=None, inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None, attention_mask_has_padding=None, input_ids_cpu=None,
                 splice_plan=None, sd_kwargs=None, **kwargs):
-        """reference :1353-1509.  Comprehension path (images -> CLIP -> splice -> LM loss) is complete; the creation
-        path returns the gathered dream-query conditioning in `additional_log_info["dream_conditioning"]` — the
-        StableDiffusionHead (UNet) that consumes it (:1441) is the next §8 row."""
+        """reference :1353-1509.  Comprehension path: images -> CLIP -> splice -> LM loss.  Creation path: dream-query conditioning
+        gather (:1401-1418, also returned in `additional_log_info["dream_conditioning"]`) -> optional null-prompt pass (:1420-1439) ->
+        `stable_diffusion_head` loss (:1441); `sd_kwargs` forwards injected random draws to the head (tests)."""
         out = self.model(input_ids=input_ids, images=images, images_dm=images_dm, attention_mask=attention_mask,
                          position_ids=position_ids, past_key_values=past_key_values, inputs_embeds=inputs_embeds,
                          use_cache=use_cache, output_hidden_states=output_hidden_states,
@@ -705,11 +705,33 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
             info["dream_conditioning"] = enc_h
             head = getattr(self, "stable_diffusion_head", None)
             if head is not None and self.training:
-                vm_loss = head(images_dm[: plan.n_dreams], enc_h, **(sd_kwargs or {}))                   # (:1441)
+                u_enc = None
+                if getattr(head, "drop_prob", None) is not None:                                         # (:1420-1439)
+                    u_enc = self._null_prompt_states(Q)
+                vm_loss = head(images_dm[: plan.n_dreams], enc_h, u_enc, **(sd_kwargs or {}))            # (:1441)
                 loss = vm_loss * self.loss_weight_vm + (loss if loss is not None else 0.0)               # (:1486-1488)
         info["vm_loss"] = vm_loss
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=out.past_key_values, hidden_states=out.hidden_states,
                                       additional_log_info=info)
+
+    def _null_prompt_states(self, Q):
+        """reference :1420-1439: the classifier-free-guidance "null prompt" — an LLM pass over
+        [bos, <dream_start>, Q x <im_patch>, <dream_end>, eos] (no `images_dm`, so the patch positions keep their token embeddings) whose
+        hidden states at positions [2, 2+Q) replace the conditioning of dropped samples.  Returned as [1, Q, H]; the reference's
+        `.repeat(Nd, 1, 1)` is folded into `_CfgDropFn`'s broadcast."""
+        from .modeling_plugins import gather_rows
+        m = self.model
+        st = getattr(self.config, "special_tokens2ids_dict", None)
+        if st is not None:
+            patch_id = st["additional_special_tokens"]["<im_patch>"]
+            bos_id, eos_id = st["<s>"], st["</s>"]                  # DEFAULT_BOS/EOS_TOKEN keys (:1396-1397)
+        else:                                                           # token order: tokenization_dreamllm.py:78-94
+            patch_id, bos_id, eos_id = m.dream_start_id - 4, self.config.bos_token_id, self.config.eos_token_id
+        dev = m.embed_tokens.weight.device
+        ids = torch.tensor([[bos_id, m.dream_start_id] + [patch_id] * Q + [m.dream_end_id, eos_id]], device=dev)
+        u_hidden = m(input_ids=ids, attention_mask_has_padding=False).last_hidden_state                  # [1, Q+4, H]
+        rows = torch.arange(2, 2 + Q, device=dev, dtype=torch.int32)
+        return gather_rows(u_hidden, rows).view(1, Q, u_hidden.shape[-1])
 
     # ---------------------------------------------------------------------------------------------- inference entry points
     @torch.no_grad()

@@ -374,31 +374,89 @@ def gather_rows(x, rows):
 
 # ------------------------------------------------------------------------------------------------ StableDiffusionHead
 class _DiffusionLossFn(torch.autograd.Function):
-    """loss = mse(unet(noisy, t, cond), target).  The UNet is frozen, so the only gradient is d(loss)/d(cond); it is computed eagerly
-    (forward tape -> dgrad-only backward) so the UNet activations are freed before the LLM backward starts."""
+    """loss = mse(unet(noisy, t, cond), target) — plain mean (:559) or min-SNR weighted (:561-572) when `snr` = (alphas_cumprod, gamma).
+    The UNet is frozen, so the only gradient is d(loss)/d(cond); it is computed eagerly (forward tape -> dgrad-only backward) so the
+    UNet activations are freed before the LLM backward starts."""
 
     @staticmethod
-    def forward(ctx, cond, unet, noisy, t32, target):
+    def forward(ctx, cond, unet, noisy, t32, target, snr=None):
         need = ctx.needs_input_grad[0]          # (grad mode is off inside Function.forward; ask autograd instead)
+
+        def mse(eps):
+            if snr is None:
+                return ops.mse_fwd_bwd(eps, target)
+            return ops.mse_minsnr_fwd_bwd(eps, target, t32, snr[0], snr[1])
+
         with torch.no_grad():
             if need:
                 eps, tape = unet.forward_train(noisy, t32, cond)
-                loss, deps = ops.mse_fwd_bwd(eps, target)
+                loss, deps = mse(eps)
                 dcond = unet.backward_cond(deps, tape).to(cond.dtype)
                 del tape
                 ctx.save_for_backward(dcond)
             else:
                 eps, _ = unet.forward_train(noisy, t32, cond)
-                loss, _ = ops.mse_fwd_bwd(eps, target)
+                loss, _ = mse(eps)
         ctx.has_grad = need
         return loss
 
     @staticmethod
     def backward(ctx, g):
         if not ctx.has_grad:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         (dcond,) = ctx.saved_tensors
-        return dcond * g.to(dcond.dtype), None, None, None, None
+        return dcond * g.to(dcond.dtype), None, None, None, None, None
+
+
+class _CfgDropFn(torch.autograd.Function):
+    """Classifier-free-guidance dropout of the conditioning (reference :539-543): sample b takes `u[b]` where mask[b] == 1, else
+    `enc[b]`.  The reference writes it as (1 - mask) * enc + mask * u with a {0,1} mask, which is exactly a per-sample row select, so
+    it is done with bit-exact row copies; `u` may be [1, Q, H] (the null-prompt pass before its `.repeat`, :1438-1439) or [B, Q, H].
+    Backward: enc gets dy on kept samples / 0 on dropped ones; u gets dy of the dropped samples (summed when u is broadcast)."""
+
+    @staticmethod
+    def forward(ctx, enc, u, drop_mask_cpu):
+        B, Q, H = enc.shape
+        assert u.shape[1:] == (Q, H) and u.shape[0] in (1, B), (u.shape, enc.shape)
+        dropped = [b for b in range(B) if bool(drop_mask_cpu[b])]
+        out = enc.reshape(B * Q, H).clone()
+        ctx.meta = (B, Q, H, u.shape[0], len(dropped))
+        if dropped:
+            dev = enc.device
+            q = torch.arange(Q)
+            dst = torch.cat([b * Q + q for b in dropped])
+            src = torch.cat([(b if u.shape[0] == B else 0) * Q + q for b in dropped])
+            K = len(dropped)
+            seg = torch.arange(Q + 1) * K                                                   # query-major CSR for the broadcast sum
+            rows = (torch.tensor(dropped)[None, :] * Q + q[:, None]).reshape(-1)
+            to = lambda t: t.to(torch.int32).to(dev)
+            dst, src, seg, rows = to(dst), to(src), to(seg), to(rows)
+            ops.copy_rows_(out, dst, u.reshape(-1, H).contiguous(), src)
+            ctx.save_for_backward(dst, src, seg, rows)
+        return out.view(B, Q, H)
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, Q, H, Bu, K = ctx.meta
+        dy2 = dy.reshape(B * Q, H).contiguous()
+        d_enc = d_u = None
+        if K == 0:
+            if ctx.needs_input_grad[0]:
+                d_enc = dy
+            if ctx.needs_input_grad[1]:
+                d_u = torch.zeros((Bu, Q, H), device=dy.device, dtype=dy.dtype)
+            return d_enc, d_u, None
+        dst, src, seg, rows = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            d_enc = ops.zero_rows_(dy2.clone(), dst).view(B, Q, H)
+        if ctx.needs_input_grad[1]:
+            if Bu == 1:
+                d_u = ops.segment_sum_rows(dy2, seg, rows, Q).view(1, Q, H).to(dy.dtype)
+            else:
+                d_u = torch.zeros((B * Q, H), device=dy.device, dtype=dy.dtype)
+                ops.copy_rows_(d_u, src, dy2, dst)
+                d_u = d_u.view(B, Q, H)
+        return d_enc, d_u, None
 
 
 class StableDiffusionHead(MultimodalHead):
@@ -497,17 +555,16 @@ class StableDiffusionHead(MultimodalHead):
         return self._ac
 
     def forward(self, images=None, encoder_hidden_states=None, u_encoder_hidden_states=None, dream_embeddings=None, *,
-                latents=None, noise=None, timesteps=None, vae_noise=None):
-        """Diffusion loss, reference :493-577: VAE encode (:511-512) -> noise / timestep draw (:520-531) -> add_noise (:536) -> projector
-        (:546) -> UNet eps-prediction (:556) -> MSE in fp32 (:559).  Gradients flow through the frozen UNet into the conditioning.
-        `latents` / `noise` / `timesteps` / `vae_noise` let tests inject the random draws (the reference uses the global generator).
-        `images=None` (the reference's DDP dummy branch, :500-508) is not needed by our reducer and returns None."""
+                latents=None, noise=None, timesteps=None, vae_noise=None, offset_noise=None, perturbation_noise=None, drop_mask=None):
+        """Diffusion loss, reference :493-577: VAE encode (:511-512) -> noise draw, + `noise_offset` (:521-523), `input_perturbation`
+        (:524-525, :533-534) -> timestep draw (:528) -> add_noise (:534-536) -> CFG-dropout mix when `drop_prob` is set and the null-prompt
+        states are given (:539-543) -> projector (:546) -> UNet eps-prediction (:556) -> MSE in fp32 (:559) or min-SNR weighted
+        (`snr_gamma`, :561-572).  Gradients flow through the frozen UNet into the conditioning.
+        `latents` / `noise` / `timesteps` / `vae_noise` / `offset_noise` / `perturbation_noise` / `drop_mask` let tests inject the random
+        draws (the reference uses the global generators, in this order).  `images=None` (the reference's DDP dummy branch, :500-508) is
+        not needed by our reducer and returns None."""
         if images is None and latents is None:
             return None
-        if self.noise_offset or self.input_perturbation or self.snr_gamma is not None:
-            raise NotImplementedError("noise_offset / input_perturbation / snr_gamma are 0/None in every shipped config; not built")
-        if u_encoder_hidden_states is not None and self.drop_prob is not None:
-            raise NotImplementedError("CFG-dropout training (drop_prob) is None in every shipped config; not built")
         dev = encoder_hidden_states.device
         if latents is None:
             latents = self.vae.encode_sample(images, z=vae_noise)
@@ -517,12 +574,30 @@ class StableDiffusionHead(MultimodalHead):
         bsz = latents.shape[0]
         if noise is None:
             noise = torch.randn_like(latents)
+        noise = noise.float()
+        if self.noise_offset:                                                       # RNG post-processing on [B,4,h,w] fp32 (:521-523)
+            if offset_noise is None:
+                offset_noise = torch.randn((bsz, latents.shape[1], 1, 1), device=dev)
+            noise = noise + self.noise_offset * offset_noise.float().view(bsz, latents.shape[1], 1, 1)
+        noise = noise.contiguous()
+        fwd_noise = noise
+        if self.input_perturbation:                                                 # (:524-525): perturbed noise drives x_t, target stays `noise`
+            if perturbation_noise is None:
+                perturbation_noise = torch.randn_like(noise)
+            fwd_noise = (noise + self.input_perturbation * perturbation_noise.float()).contiguous()
         if timesteps is None:
             timesteps = torch.randint(0, 1000, (bsz,), device=dev)
         t32 = timesteps.to(torch.int32).contiguous()
-        noisy = ops.add_noise(latents, noise.float().contiguous(), t32, self._alphas_cumprod(dev))
+        ac = self._alphas_cumprod(dev)
+        noisy = ops.add_noise(latents, fwd_noise, t32, ac)
+        if u_encoder_hidden_states is not None and self.drop_prob is not None:      # train with classifier-free guidance (:539-543)
+            if drop_mask is None:
+                drop_mask = torch.bernoulli(torch.zeros(bsz) + self.drop_prob)       # drawn on the host, as the reference does (:541)
+            encoder_hidden_states = _CfgDropFn.apply(encoder_hidden_states, u_encoder_hidden_states.to(encoder_hidden_states.dtype),
+                                                     drop_mask.detach().to("cpu"))
         cond = self.projector(encoder_hidden_states)[-1]
-        return _DiffusionLossFn.apply(cond, self.unet, noisy, t32, noise.float().contiguous())      # epsilon prediction (:548-549)
+        snr = None if self.snr_gamma is None else (ac, float(self.snr_gamma))
+        return _DiffusionLossFn.apply(cond, self.unet, noisy, t32, noise, snr)      # epsilon prediction (:548-549)
 
     @torch.no_grad()
     def pipeline(self, height: int | None = None, width: int | None = None, num_inference_steps: int = 50, guidance_scale: float = 7.5,

@@ -507,6 +507,17 @@ def mse_fwd_bwd(pred_f32, target_f32):
     return loss[0], dpred
 
 
+def mse_minsnr_fwd_bwd(pred_f32, target_f32, t_i32, alphas_cumprod_f32, snr_gamma: float):
+    """min-SNR weighted MSE (reference modeling_plugins.py:561-572): per-sample weight min(snr, gamma) / snr."""
+    loss = torch.empty(1, device=pred_f32.device, dtype=torch.float32)
+    dpred = torch.empty_like(pred_f32)
+    B = pred_f32.shape[0]
+    check(lib().dllm_mse_minsnr_fwd_bwd(_p(pred_f32), _p(target_f32), _p(t_i32), _p(alphas_cumprod_f32), float(snr_gamma), _p(loss),
+                                        _p(dpred), B, pred_f32.numel() // B, _stream()), "dllm_mse_minsnr_fwd_bwd")
+    LAUNCHES.add(1)
+    return loss[0], dpred
+
+
 def geglu(x2d):
     _chk_cuda(x2d)
     T, I2 = x2d.shape

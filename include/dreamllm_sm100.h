@@ -159,6 +159,9 @@ int dllm_conv_out_bwd(const float* dy_nchw, const void* w, void* dx_nhwc, int B,
 int dllm_add_noise(const float* x0, const float* noise, const int* t, const float* alphas_cumprod, float* out, int B, long per_sample,
                    void* stream);
 int dllm_mse_fwd_bwd(const float* pred, const float* target, float* loss, float* dpred, long n, void* stream);
+/* min-SNR weighted MSE (modeling_plugins.py:561-572 with `_compute_snr` :468-491): w_b = min(snr(t_b), gamma) / snr(t_b) */
+int dllm_mse_minsnr_fwd_bwd(const float* pred, const float* target, const int* t, const float* alphas_cumprod, float snr_gamma,
+                            float* loss, float* dpred, int B, long per_sample, void* stream);
 
 /* ---- VAE encoder helpers (AutoencoderKL.encode(...).latent_dist.sample() * scaling_factor, modeling_plugins.py:511-512) ---- */
 int dllm_softmax_rows(void* x, long rows, int cols, float scale, void* stream);

@@ -273,3 +273,25 @@ def ddpm_step(x_t, eps, t, ratio, ac, noise):
     mu = (a_prev.sqrt() * b_cur / (1 - a_t)) * x0 + (a_cur.sqrt() * (1 - a_prev) / (1 - a_t)) * x_t
     var = torch.clamp((1 - a_prev) / (1 - a_t) * b_cur, min=1e-20)
     return mu + (var.sqrt() * noise if t > 0 else 0.0)
+
+
+def diffusion_loss(unet, latents, cond, noise, t, ac, *, noise_offset=0.0, offset_noise=None, input_perturbation=0.0,
+                   perturbation_noise=None, snr_gamma=None):
+    """Restatement of `StableDiffusionHead.forward` after the VAE (reference modeling_plugins.py:520-572, epsilon prediction):
+    offset noise (:521-523), input perturbation (:524-525, :533-534), add_noise (:534-536), UNet (:556), plain MSE (:559) or
+    min-SNR weighted MSE (:561-572 with `_compute_snr` :468-491).  fp32 throughout; `cond` is already projected."""
+    noise = noise.clone()
+    if noise_offset:
+        noise = noise + noise_offset * offset_noise.view(noise.shape[0], noise.shape[1], 1, 1)
+    new_noise = noise + input_perturbation * perturbation_noise if input_perturbation else noise
+    noisy = add_noise(latents, new_noise, t, ac)
+    pred = unet(noisy, t, cond)
+    if snr_gamma is None:
+        return torch.nn.functional.mse_loss(pred.float(), noise.float(), reduction="mean")
+    alpha = (ac ** 0.5)[t].float()
+    sigma = ((1.0 - ac) ** 0.5)[t].float()
+    snr = (alpha / sigma) ** 2
+    w = torch.stack([snr, snr_gamma * torch.ones_like(snr)], dim=1).min(dim=1)[0] / snr
+    loss = torch.nn.functional.mse_loss(pred.float(), noise.float(), reduction="none")
+    loss = loss.mean(dim=list(range(1, len(loss.shape)))) * w
+    return loss.mean()
