@@ -11,7 +11,7 @@ import subprocess
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("DLLM_LIB_PATH") or os.path.join(_HERE, "libdreamllm_sm100.so")   # env override: A/B builds in dev scripts
-SOURCES = ["capi.cu", "gemm_sm100.cu", "elementwise.cu", "attn_sm100.cu", "unet_ops.cu"]
+SOURCES = ["capi.cu", "gemm_sm100.cu", "elementwise.cu", "attn_sm100.cu", "unet_ops.cu", "optim.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--use_fast_math", "-Xcompiler", "-fPIC", "-Xcompiler", "-O3",
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
-_vp, _i, _l, _f, _sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_size_t
+_vp, _i, _l, _f, _sz, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_size_t, ctypes.c_double
 
 # name -> (restype, argtypes); mirrors include/dreamllm_sm100.h one-to-one
 SIGNATURES = {
@@ -112,6 +112,9 @@ SIGNATURES = {
     "dllm_mse_minsnr_fwd_bwd": (_i, [_vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _l, _vp]),
     "dllm_softmax_rows": (_i, [_vp, _l, _i, _f, _vp]),
     "dllm_vae_sample": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _l, _f, _vp]),
+    "dllm_adamw_step": (_i, [_vp, _vp, _vp, _vp, _vp, _l, _i, _d, _d, _d, _d, _d, _i, _vp, _d, _vp]),
+    "dllm_sumsq_workspace_bytes": (_sz, []),
+    "dllm_sumsq_bf16": (_i, [_vp, _l, _vp, _i, _vp, _sz, _vp]),
 }
 
 _lib = None

@@ -272,4 +272,19 @@ int dllm_vae_sample(const float* h, const void* wq, const void* bq, const float*
   return vae_sample(h, wq, bq, z, out, B, L, plane, scaling, S(stream));
 }
 
+
+int dllm_adamw_step(const void* grad, void* master, void* exp_avg, void* exp_avg_sq, void* param, long n, int bf16_state, double lr,
+                    double beta1, double beta2, double eps, double weight_decay, int step, const float* grad_sumsq,
+                    double max_grad_norm,
+                    void* stream) {
+  ensure_context(grad);
+  return adamw_step(grad, master, exp_avg, exp_avg_sq, param, n, bf16_state, lr, beta1, beta2, eps, weight_decay, step, grad_sumsq,
+                    max_grad_norm, S(stream));
+}
+size_t dllm_sumsq_workspace_bytes(void) { return sumsq_workspace(); }
+int dllm_sumsq_bf16(const void* x, long n, float* out, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  ensure_context(out);
+  return sumsq_bf16(x, n, out, accumulate, workspace, workspace_bytes, S(stream));
+}
+
 }  // extern "C"

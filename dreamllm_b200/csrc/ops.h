@@ -71,4 +71,9 @@ int mse_minsnr_fwd_bwd(const float* pred, const float* target, const int* t, con
 int softmax_rows(void* x, long rows, int cols, float scale, cudaStream_t s);
 int vae_sample(const float* h, const void* wq, const void* bq, const float* z, float* out, int B, int L, long plane, float scaling,
                cudaStream_t s);
+// optim.cu — sharded AdamW + grad-norm
+int adamw_step(const void* grad, void* master, void* mom, void* var, void* param, long n, int bf16_state, double lr, double beta1,
+               double beta2, double eps, double weight_decay, int step, const float* sumsq, double max_norm, cudaStream_t s);
+size_t sumsq_workspace();
+int sumsq_bf16(const void* x, long n, float* out, int accumulate, void* workspace, size_t ws_bytes, cudaStream_t s);
 }  // namespace dllm

@@ -618,3 +618,42 @@ def attn_fwd_cache(q, k_cache, v_cache, kv_len, causal=True, scale=None):
                                     k_cache.stride(1), nh * d, int(causal), scale, _stream()), "dllm_attn_fwd_cache")
     LAUNCHES.add(1)
     return out
+
+
+# ------------------------------------------------------------------------------------------------ optimizer shard
+_SUMSQ_WS = {}
+
+
+def sumsq_bf16_(x_bf16, out_f32, accumulate: bool = True):
+    """out[0] (+)= sum(x^2) in fp32 over a flat bf16 vector (numel % 8 == 0); deterministic two-stage reduction."""
+    _chk_cuda(x_bf16, out_f32)
+    assert x_bf16.dtype == BF16 and x_bf16.is_contiguous() and out_f32.dtype == torch.float32
+    dev = x_bf16.device
+    ws = _SUMSQ_WS.get(dev)
+    if ws is None:
+        ws = _SUMSQ_WS[dev] = torch.empty(lib().dllm_sumsq_workspace_bytes(), dtype=torch.uint8, device=dev)
+    check(lib().dllm_sumsq_bf16(_p(x_bf16), x_bf16.numel(), _p(out_f32), int(accumulate), _p(ws), ws.numel(), _stream()),
+          "dllm_sumsq_bf16")
+    LAUNCHES.add(2)
+    return out_f32
+
+
+def adamw_step_(grad_bf16, param_bf16, exp_avg, exp_avg_sq, master_f32, *, lr, beta1, beta2, eps, weight_decay, step,
+                grad_sumsq=None, max_grad_norm=0.0):
+    """One fused AdamW step over a flat shard (reference: torch.optim.AdamW via HF Trainer `optim="adamw_torch"`).
+    master_f32 is None  -> bf16-state mode: param / exp_avg / exp_avg_sq are bf16, per-op bf16 rounding as the reference's optimizer.
+    master_f32 is given -> fp32 master / exp_avg / exp_avg_sq; param (bf16) is rewritten from the updated master."""
+    _chk_cuda(grad_bf16, param_bf16, exp_avg, exp_avg_sq)
+    n = grad_bf16.numel()
+    bf16_state = master_f32 is None
+    st = BF16 if bf16_state else torch.float32
+    assert grad_bf16.dtype == BF16 and param_bf16.dtype == BF16 and exp_avg.dtype == st and exp_avg_sq.dtype == st
+    assert param_bf16.numel() == n and exp_avg.numel() == n and exp_avg_sq.numel() == n
+    assert all(t.is_contiguous() for t in (grad_bf16, param_bf16, exp_avg, exp_avg_sq))
+    if not bf16_state:
+        _chk_cuda(master_f32)
+        assert master_f32.dtype == torch.float32 and master_f32.numel() == n and master_f32.is_contiguous()
+    check(lib().dllm_adamw_step(_p(grad_bf16), _p(master_f32), _p(exp_avg), _p(exp_avg_sq), _p(param_bf16), n, int(bf16_state),
+                                float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step), _p(grad_sumsq),
+                                float(max_grad_norm), _stream()), "dllm_adamw_step")
+    LAUNCHES.add(1)

@@ -168,6 +168,24 @@ int dllm_softmax_rows(void* x, long rows, int cols, float scale, void* stream);
 int dllm_vae_sample(const float* h, const void* wq, const void* bq, const float* z, float* out, int B, int L, long plane, float scaling,
                     void* stream);
 
+/* ---- data-parallel optimizer shard ----
+ * Replaces torch.optim.AdamW (`optim="adamw_torch"`, projects/dreamllm/configs/stage1/base.py:85, stage2/base.py:95) applied to this
+ * rank's shard of a flat bf16 gradient bucket under FSDP shard_grad_op (stage2/base.py:91-94), with the gradient clipping of
+ * omni/train/trainer.py:800-807 folded in: the step scales grads by min(1, max_grad_norm / (sqrt(*grad_sumsq) + 1e-6)) when
+ * grad_sumsq != NULL and max_grad_norm > 0 (grad_sumsq = global sum of squares, device pointer, read at kernel time: no host sync).
+ * n % 8 == 0, 16-byte aligned pointers.  bf16_state = 0: master / exp_avg / exp_avg_sq are fp32 shards, `param` (bf16) is written from
+ * the updated master.  bf16_state = 1: `param`, exp_avg, exp_avg_sq are bf16 and every ATen op of the reference optimizer's
+ * single-tensor path rounds to bf16 (bit-for-bit the arithmetic the reference runs on its bf16-loaded model); master is ignored.
+ * `step` is the 1-based step count used for the bias corrections.  Hyper-parameters are doubles: Python computes 1 - beta1, lr / (1 - beta1^t)
+ * ... in double before ATen narrows them to the fp32 opmath type, and the kernel's scalars are derived the same way. */
+int dllm_adamw_step(const void* grad, void* master, void* exp_avg, void* exp_avg_sq, void* param, long n, int bf16_state, double lr,
+                    double beta1, double beta2, double eps, double weight_decay, int step, const float* grad_sumsq,
+                    double max_grad_norm,
+                    void* stream);
+/* sum of squares of a bf16 vector in fp32 (deterministic two-stage reduction); *out = (accumulate ? *out : 0) + sum(x^2) */
+size_t dllm_sumsq_workspace_bytes(void);
+int dllm_sumsq_bf16(const void* x, long n, float* out, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
