@@ -385,13 +385,15 @@ class DreamLLMDecoderLayer(nn.Module):
                 f"Attention mask should be of size {(B, S)} (2-D padding mask, flash path), but is {tuple(attention_mask.size())}")
         att = self.self_attn
         dev = hidden_states.device
-        if position_ids is None:
-            pos = torch.arange(S, device=dev, dtype=torch.int32).repeat(B)
-        else:
-            pos = position_ids.to(torch.int32).expand(B, S).reshape(-1).contiguous()
+        pos = kwargs.get("pos_i32")                       # [B*S] int32, built once per forward by DreamLLMModel._forward
+        if pos is None:
+            if position_ids is None:
+                pos = torch.arange(S, device=dev, dtype=torch.int32).repeat(B)
+            else:
+                pos = position_ids.to(torch.int32).expand(B, S).reshape(-1).contiguous()
         cos, sin = att.rotary_emb.tables(max(S, att.max_position_embeddings), dev)
-        seqlens = None
-        if attention_mask is not None:
+        seqlens = kwargs.get("seqlens")                   # int32 [B] valid lengths (collator / model loop); else derived from the mask
+        if seqlens is None and attention_mask is not None:
             seqlens = attention_mask.sum(-1).to(torch.int32).contiguous()
         meta = _LayerMeta(att.num_heads, att.head_dim, self.mlp.intermediate_size, self.input_layernorm.variance_epsilon,
                           B, S, pos, cos, sin, seqlens,
@@ -537,7 +539,7 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
 
     def _forward(self, input_ids=None, attention_mask=None, position_ids=None, past_key_values=None, inputs_embeds=None,
                  use_cache=None, output_attentions=None, output_hidden_states=None, return_dict=None,
-                 attention_mask_has_padding=None):
+                 attention_mask_has_padding=None, seqlens=None):
         """reference :846-1043.  `attention_mask_has_padding` replaces the `0 in attention_mask` host sync (:962):
         pass False when the collator knows there is no padding (None = decide on the device-free path: keep the
         mask and let the kernel honour seqlens)."""
@@ -549,6 +551,7 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
             inputs_embeds = _EmbeddingFn.apply(input_ids, self.embed_tokens.weight)
         if attention_mask_has_padding is False:
             attention_mask = None
+            seqlens = None
         hidden_states = inputs_embeds
         all_hidden = () if output_hidden_states else None
         cache = None
@@ -562,13 +565,28 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
             att = self.layers[0].self_attn
             cache = past_key_values if past_key_values is not None else KVCache(
                 len(self.layers), B, self.config.max_position_embeddings, att.num_heads, att.head_dim, hidden_states.device)
+        pos_i32 = None
+        if cache is None:
+            # once per forward instead of once per layer: valid lengths for the attention kernels and the int32 RoPE positions
+            if attention_mask is not None and seqlens is None:
+                if attention_mask.dim() != 2:
+                    raise ValueError(f"Attention mask should be 2-D [batch, seq] (flash path), but is {tuple(attention_mask.size())}")
+                seqlens = attention_mask.sum(-1).to(torch.int32).contiguous()
+            elif seqlens is not None:
+                seqlens = seqlens.to(device=hidden_states.device, dtype=torch.int32).contiguous()
+            Bq, Sq = hidden_states.shape[:2]
+            if position_ids is None:
+                pos_i32 = torch.arange(Sq, device=hidden_states.device, dtype=torch.int32).repeat(Bq)
+            else:
+                pos_i32 = position_ids.to(torch.int32).expand(Bq, Sq).reshape(-1).contiguous()
         for li, layer in enumerate(self.layers):
             if output_hidden_states:
                 all_hidden += (hidden_states,)
             if cache is not None:
                 hidden_states = layer(hidden_states, position_ids=position_ids, past_key_value=(cache, li), use_cache=True)[0]
             else:
-                hidden_states = layer(hidden_states, attention_mask=attention_mask, position_ids=position_ids)[0]
+                hidden_states = layer(hidden_states, attention_mask=attention_mask, position_ids=position_ids, seqlens=seqlens,
+                                      pos_i32=pos_i32)[0]
         if cache is not None:
             cache.len += hidden_states.shape[1]
         hidden_states = self.norm(hidden_states)
@@ -593,7 +611,7 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
 
     def forward(self, input_ids=None, images=None, images_dm=None, attention_mask=None, position_ids=None,
                 past_key_values=None, inputs_embeds=None, use_cache=None, output_attentions=None, output_hidden_states=None,
-                return_dict=None, attention_mask_has_padding=None, input_ids_cpu=None, splice_plan=None):
+                return_dict=None, attention_mask_has_padding=None, input_ids_cpu=None, splice_plan=None, seqlens=None):
         """reference :1045-1158: embed_tokens -> dream-query splice -> CLIP features -> image splice -> `_forward`.
         `input_ids_cpu` (the collator's host copy) lets the index maps be built without a device->host sync;
         `splice_plan` lets the caller pass prebuilt maps."""
@@ -605,7 +623,8 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
         if not need_splice:
             return self._forward(input_ids=input_ids, attention_mask=attention_mask, position_ids=position_ids,
                                  past_key_values=past_key_values, inputs_embeds=inputs_embeds, use_cache=use_cache,
-                                 output_hidden_states=output_hidden_states, attention_mask_has_padding=attention_mask_has_padding)
+                                 output_hidden_states=output_hidden_states, attention_mask_has_padding=attention_mask_has_padding,
+                                 seqlens=seqlens)
         from .modeling_plugins import build_splice_plan, splice_embeddings
         if input_ids is None:
             raise ValueError("image / dream splicing needs input_ids")
@@ -621,13 +640,15 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
                                             self.dream_start_id if images_dm is not None else -1, P, Q,
                                             0 if images is None else images.shape[0],
                                             None if images_dm is None else images_dm.shape[0], inputs_embeds.device)
+        elif splice_plan.device != inputs_embeds.device:       # the collator's host plan: async H2D of a few int32 maps
+            splice_plan = splice_plan.to(inputs_embeds.device)
         self._last_splice_plan = splice_plan
         if image_features is not None:
             image_features = image_features.to(inputs_embeds.dtype)
         inputs_embeds = splice_embeddings(inputs_embeds, image_features, dq, splice_plan)
         return self._forward(attention_mask=attention_mask, position_ids=position_ids, inputs_embeds=inputs_embeds,
                              past_key_values=past_key_values, use_cache=use_cache, output_hidden_states=output_hidden_states,
-                             attention_mask_has_padding=attention_mask_has_padding)
+                             attention_mask_has_padding=attention_mask_has_padding, seqlens=seqlens)
 
     def prepare_dream_queries_with_special_token(self, batch_size: int = 1):
         """reference :1161-1169: embeds of [<dream_start>, dream queries, <dream_end>]."""
@@ -671,24 +692,28 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
     def forward(self, input_ids=None, images=None, images_dm=None, attention_mask=None, position_ids=None,
                 past_key_values=None, inputs_embeds=None, labels=None, use_cache=None, output_attentions=None,
                 output_hidden_states=None, return_dict=None, attention_mask_has_padding=None, input_ids_cpu=None,
-                splice_plan=None, sd_kwargs=None, **kwargs):
-        """reference :1353-1509.  Comprehension path: images -> CLIP -> splice -> LM loss.  Creation path: dream-query conditioning
+                splice_plan=None, sd_kwargs=None, seqlens=None, shifted_labels=None, **kwargs):
+        """reference :1353-1509.  `seqlens` / `shifted_labels` / `splice_plan` / `input_ids_cpu` are the collator's precomputed maps
+        (dreamllm_b200/collator.py); without them they are derived here as the reference does.  Comprehension path: images -> CLIP -> splice -> LM loss.  Creation path: dream-query conditioning
         gather (:1401-1418, also returned in `additional_log_info["dream_conditioning"]`) -> optional null-prompt pass (:1420-1439) ->
         `stable_diffusion_head` loss (:1441); `sd_kwargs` forwards injected random draws to the head (tests)."""
         out = self.model(input_ids=input_ids, images=images, images_dm=images_dm, attention_mask=attention_mask,
                          position_ids=position_ids, past_key_values=past_key_values, inputs_embeds=inputs_embeds,
                          use_cache=use_cache, output_hidden_states=output_hidden_states,
                          attention_mask_has_padding=attention_mask_has_padding, input_ids_cpu=input_ids_cpu,
-                         splice_plan=splice_plan)
+                         splice_plan=splice_plan, seqlens=seqlens)
         hidden = out.last_hidden_state
         B, S, H = hidden.shape
         h2 = hidden.reshape(B * S, H)
         loss = None
         logits = None
         lm_loss = 0.0
-        if labels is not None:
-            shifted = torch.full_like(labels, -100)
-            shifted[:, :-1] = labels[:, 1:]
+        if labels is not None or shifted_labels is not None:
+            if shifted_labels is not None:
+                shifted = shifted_labels
+            else:
+                shifted = torch.full_like(labels, -100)
+                shifted[:, :-1] = labels[:, 1:]
             lm_loss = _LMHeadLossFn.apply(h2, self.lm_head.weight, shifted.reshape(-1).contiguous())
             loss = lm_loss * self.loss_weight_lm
         elif kwargs.get("last_token_logits_only", False):

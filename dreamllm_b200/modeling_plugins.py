@@ -265,6 +265,19 @@ class SplicePlan:
     n_images_used: int
     n_dreams: int
 
+    _FIELDS = ("img_dst", "img_src", "dq_dst", "dq_src", "dq_seg", "dq_rows", "cond_rows")
+
+    def to(self, device, non_blocking: bool = True) -> "SplicePlan":
+        """Host plan (built by the collator in a dataloader worker, ideally pinned) -> device plan; async H2D, no sync."""
+        return SplicePlan(*[getattr(self, f).to(device, non_blocking=non_blocking) for f in self._FIELDS], self.n_images_used, self.n_dreams)
+
+    def pin_memory(self) -> "SplicePlan":
+        return SplicePlan(*[getattr(self, f).pin_memory() for f in self._FIELDS], self.n_images_used, self.n_dreams)
+
+    @property
+    def device(self):
+        return self.img_dst.device
+
 
 def build_splice_plan(input_ids_cpu: torch.Tensor, image_start_id: int, dream_start_id: int, P: int, Q: int, n_images: int,
                       n_dream_images: int | None, device) -> SplicePlan:
