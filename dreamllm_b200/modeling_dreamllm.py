@@ -27,43 +27,7 @@ BF16 = torch.bfloat16
 
 
 # ------------------------------------------------------------------------------------------------ config
-class DreamLLMConfig:
-    """Minimal stand-in for `configuration_dreamllm.DreamLLMConfig` (:64-278): the LLaMA hyper-parameters the
-    decoder reads.  Any object with these attributes (e.g. the reference's own config) works."""
-
-    model_type = "dreamllm"
-
-    def __init__(self, vocab_size=32000, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
-                 num_attention_heads=32, num_key_value_heads=None, hidden_act="silu", max_position_embeddings=2048,
-                 initializer_range=0.02, rms_norm_eps=1e-6, use_cache=True, pad_token_id=None, bos_token_id=1,
-                 eos_token_id=2, pretraining_tp=1, tie_word_embeddings=False, rope_theta=10000.0, rope_scaling=None,
-                 attention_bias=False, **kwargs):
-        self.vocab_size = vocab_size
-        self.hidden_size = hidden_size
-        self.intermediate_size = intermediate_size
-        self.num_hidden_layers = num_hidden_layers
-        self.num_attention_heads = num_attention_heads
-        self.num_key_value_heads = num_key_value_heads or num_attention_heads
-        self.hidden_act = hidden_act
-        self.max_position_embeddings = max_position_embeddings
-        self.initializer_range = initializer_range
-        self.rms_norm_eps = rms_norm_eps
-        self.use_cache = use_cache
-        self.pad_token_id = pad_token_id
-        self.bos_token_id = bos_token_id
-        self.eos_token_id = eos_token_id
-        self.pretraining_tp = pretraining_tp
-        self.tie_word_embeddings = tie_word_embeddings
-        self.rope_theta = rope_theta
-        self.rope_scaling = rope_scaling
-        self.attention_bias = attention_bias
-        for k, v in kwargs.items():
-            setattr(self, k, v)
-
-    @classmethod
-    def vicuna_7b(cls, **kw):
-        return cls(vocab_size=32008, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32,
-                   num_attention_heads=32, **kw)
+from .configuration_dreamllm import DreamLLMConfig, deep_instantiate  # noqa: E402  (re-exported: the reference keeps it next door too)
 
 
 def _check_supported(config):
@@ -498,11 +462,142 @@ class CausalLMOutputWithPast:
     additional_log_info: dict | None = None
 
 
+WEIGHTS_NAME, WEIGHTS_INDEX_NAME = "pytorch_model.bin", "pytorch_model.bin.index.json"
+SAFE_WEIGHTS_NAME, SAFE_WEIGHTS_INDEX_NAME = "model.safetensors", "model.safetensors.index.json"
+
+
 class DreamLLMPreTrainedModel(nn.Module):
+    """The slice of `PreTrainedModel` the reference relies on (modeling_dreamllm.py:657-757): class attributes, `_init_weights`,
+    `device` / `dtype`, `save_pretrained` / weight loading in the HF on-disk layout (config.json + [sharded] safetensors or .bin), and
+    `resize_token_embeddings`.  Not a transformers subclass: the pinned 4.35 API and the installed 5.x one differ, the file format does not."""
+    config_class = DreamLLMConfig
     base_model_prefix = "model"
     supports_gradient_checkpointing = True
     _no_split_modules = ["DreamLLMDecoderLayer"]
+    _skip_keys_device_placement = "past_key_values"
     _supports_flash_attn_2 = True
+
+    def __init__(self, config=None):
+        super().__init__()
+        self.config = config
+        self._keys_to_ignore_on_save = []           # per instance (the reference's class-level list, :669, is shared between models)
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    # ---- HF on-disk layout -------------------------------------------------------------------------------------------------------
+    def save_pretrained(self, save_directory: str, max_shard_size: int = 5 * 1024 ** 3, safe_serialization: bool = True):
+        """config.json + model weights without the plugin keys (`_keys_to_ignore_on_save`, :826-831, :1230-1235); plugins write their own
+        `<save_model_name>.bin` next to them, as DreamLLMTrainer.save_model does (omni/train/dreamllm_trainer.py:104-112)."""
+        import json
+        import os
+        os.makedirs(save_directory, exist_ok=True)
+        self.config.save_pretrained(save_directory)
+        ignore = set(self._keys_to_ignore_on_save)
+        for m in self.modules():
+            if m is not self and isinstance(m, DreamLLMPreTrainedModel):
+                ignore.update(m._keys_to_ignore_on_save)
+        # q|k|v and gate|up are row blocks of one storage: clone so every saved tensor owns its memory
+        sd = {k: v.detach().to("cpu").clone().contiguous() for k, v in self.state_dict().items() if k not in ignore}
+        shards, cur, cur_bytes = [], {}, 0
+        for k, v in sd.items():
+            nb = v.numel() * v.element_size()
+            if cur and cur_bytes + nb > max_shard_size:
+                shards.append(cur)
+                cur, cur_bytes = {}, 0
+            cur[k] = v
+            cur_bytes += nb
+        shards.append(cur)
+        base, index_name = (SAFE_WEIGHTS_NAME, SAFE_WEIGHTS_INDEX_NAME) if safe_serialization else (WEIGHTS_NAME, WEIGHTS_INDEX_NAME)
+
+        def _write(tensors, fname):
+            if safe_serialization:
+                from safetensors.torch import save_file
+                save_file(tensors, os.path.join(save_directory, fname), metadata={"format": "pt"})
+            else:
+                torch.save(tensors, os.path.join(save_directory, fname))
+
+        if len(shards) == 1:
+            _write(shards[0], base)
+        else:
+            stem, ext = base.rsplit(".", 1)
+            weight_map = {}
+            for i, sh in enumerate(shards):
+                fname = f"{stem}-{i + 1:05d}-of-{len(shards):05d}.{ext}"
+                _write(sh, fname)
+                weight_map.update({k: fname for k in sh})
+            total = sum(v.numel() * v.element_size() for v in sd.values())
+            with open(os.path.join(save_directory, index_name), "w") as f:
+                json.dump({"metadata": {"total_size": total}, "weight_map": weight_map}, f, indent=2)
+        for _, plugin in self.named_plugins():
+            plugin.save_model(save_directory)
+
+    def named_plugins(self):
+        cfg = self.config
+        out = []
+        for name in getattr(cfg, "plugins_init_kwargs", {}) or {}:
+            owner = self.model if (cfg.plugins_type[name] == "embedding" and hasattr(self, "model")) else self
+            if hasattr(owner, name):
+                out.append((name, getattr(owner, name)))
+        return out
+
+    @staticmethod
+    def _read_checkpoint(path: str) -> dict:
+        import json
+        import os
+
+        def _load(f):
+            if f.endswith(".safetensors"):
+                from safetensors.torch import load_file
+                return load_file(f)
+            return torch.load(f, map_location="cpu", weights_only=True)
+
+        for single, index in ((SAFE_WEIGHTS_NAME, SAFE_WEIGHTS_INDEX_NAME), (WEIGHTS_NAME, WEIGHTS_INDEX_NAME)):
+            if os.path.isfile(os.path.join(path, single)):
+                return _load(os.path.join(path, single))
+            if os.path.isfile(os.path.join(path, index)):
+                with open(os.path.join(path, index)) as f:
+                    files = sorted(set(json.load(f)["weight_map"].values()))
+                sd = {}
+                for fn in files:
+                    sd.update(_load(os.path.join(path, fn)))
+                return sd
+        raise OSError(f"no {SAFE_WEIGHTS_NAME} / {WEIGHTS_NAME} (or sharded index) under {path!r}")
+
+    def resize_token_embeddings(self, new_num_tokens: int):
+        """PreTrainedModel.resize_token_embeddings as the reference uses it (:1310-1316): grow (or shrink) embed_tokens and lm_head, new
+        rows initialised like `_init_weights`."""
+        old = self.get_input_embeddings()
+        if new_num_tokens == old.weight.shape[0]:
+            return old
+
+        def _resized(w, is_embedding):
+            new = torch.empty(new_num_tokens, w.shape[1], dtype=w.dtype, device=w.device)
+            new.normal_(mean=0.0, std=self.config.initializer_range)
+            n = min(new_num_tokens, w.shape[0])
+            new[:n] = w.data[:n]
+            return new
+
+        emb = nn.Embedding(new_num_tokens, old.weight.shape[1], old.padding_idx, device=old.weight.device, dtype=old.weight.dtype)
+        emb.weight.data = _resized(old.weight, True)
+        emb.weight.requires_grad_(old.weight.requires_grad)
+        self.set_input_embeddings(emb)
+        head = self.get_output_embeddings() if hasattr(self, "get_output_embeddings") else None
+        if head is not None:
+            new_head = nn.Linear(head.weight.shape[1], new_num_tokens, bias=False, device=head.weight.device, dtype=head.weight.dtype)
+            new_head.weight.data = _resized(head.weight, False)
+            new_head.weight.requires_grad_(head.weight.requires_grad)
+            self.set_output_embeddings(new_head)
+        self.config.vocab_size = new_num_tokens
+        self.vocab_size = new_num_tokens
+        if hasattr(self, "model"):
+            self.model.vocab_size = new_num_tokens
+        return self.get_input_embeddings()
 
     def _init_weights(self, module):
         std = self.config.initializer_range
@@ -521,15 +616,31 @@ class DreamLLMPreTrainedModel(nn.Module):
 
 class DreamLLMModel(DreamLLMPreTrainedModel):
     def __init__(self, config):
-        super().__init__()
+        super().__init__(config)
         _check_supported(config)
-        self.config = config
         self.padding_idx = config.pad_token_id
         self.vocab_size = config.vocab_size
         self.embed_tokens = nn.Embedding(config.vocab_size, config.hidden_size, self.padding_idx)
         self.layers = nn.ModuleList([DreamLLMDecoderLayer(config) for _ in range(config.num_hidden_layers)])
         self.norm = DreamLLMRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self.gradient_checkpointing = False
+
+    def init_plugin_modules(self):
+        """reference :822-831: instantiate every "embedding" plugin of `config.plugins_init_kwargs` from its `_target_` string, move it to
+        the model's device / dtype, attach it under its registered name, keep its keys out of the LLM checkpoint."""
+        for name, init_kwargs in self.config.plugins_init_kwargs.items():
+            if self.config.plugins_type[name] == "embedding":
+                setattr(self, name, deep_instantiate(init_kwargs).to(self.device, dtype=self.dtype))
+                self._keys_to_ignore_on_save.extend(f"model.{name}.{key}" for key in getattr(self, name).state_dict().keys())
+        self.attach_plugins()
+
+    def fsdp_ignored_modules(self) -> list:
+        """reference :833-838."""
+        ignored_modules = []
+        for name, _ in self.config.plugins_init_kwargs.items():
+            if self.config.plugins_type[name] == "embedding":
+                ignored_modules += getattr(self, name).fsdp_ignored_modules()
+        return ignored_modules
 
     def get_input_embeddings(self):
         return self.embed_tokens
@@ -601,7 +712,7 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
             self.clip_vision_embedding = clip_vision_embedding
         if dream_embedding is not None:
             self.dream_embedding = dream_embedding
-        st = getattr(self.config, "special_tokens2ids_dict", None)
+        st = getattr(self.config, "special_tokens2ids_dict", None) or None     # {} (the config default) = not populated
         if st is not None:
             image_start_id = st["additional_special_tokens"]["<im_start>"] if image_start_id is None else image_start_id
             dream_start_id = st["additional_special_tokens"]["<dream_start>"] if dream_start_id is None else dream_start_id
@@ -662,14 +773,95 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
     _tied_weights_keys = {"lm_head.weight": "model.embed_tokens.weight"}
 
     def __init__(self, config):
-        super().__init__()
-        self.config = config
+        super().__init__(config)
         self.model = DreamLLMModel(config)
         self.vocab_size = config.vocab_size
         self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
         self.loss_weight_lm = getattr(config, "loss_weight_lm", 1.0)
-        self.loss_weight_vm = getattr(config, "loss_weight_vm", 1.0)
+        self.loss_weight_vm = getattr(config, "loss_weight_vm", 10.0)      # configuration_dreamllm.py:196 default
         self.post_init()
+
+    def init_plugin_modules(self):
+        """reference :1224-1235."""
+        self.model.init_plugin_modules()
+        for name, init_kwargs in self.config.plugins_init_kwargs.items():
+            if self.config.plugins_type[name] == "head":
+                setattr(self, name, deep_instantiate(init_kwargs).to(self.device, dtype=self.dtype))
+                self._keys_to_ignore_on_save.extend(f"{name}.{key}" for key in getattr(self, name).state_dict().keys())
+
+    def fsdp_ignored_modules(self) -> list:
+        """reference :1237-1242."""
+        ignored_modules = self.model.fsdp_ignored_modules()
+        for name, _ in self.config.plugins_init_kwargs.items():
+            if self.config.plugins_type[name] == "head":
+                ignored_modules += getattr(self, name).fsdp_ignored_modules()
+        return ignored_modules
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, tokenizer=None, *model_args, config=None, torch_dtype=None,
+                        device=None, reset_plugin_model_name_or_path: bool = False, strict: bool = True, **kwargs):
+        """reference :1244-1332: config -> LLM weights -> vocabulary check against the tokenizer -> plugins.  Local directories only (no
+        network): HF layout written by `save_pretrained` here, by the reference, or a plain LLaMA / Vicuna export."""
+        assert tokenizer is not None, "tokenizer should not be None"
+        if not isinstance(config, DreamLLMConfig):
+            config_path = config if config is not None else pretrained_model_name_or_path
+            config = cls.config_class.from_pretrained(config_path)
+        model = cls(config, *model_args)
+        sd = cls._read_checkpoint(pretrained_model_name_or_path)
+        res = model.load_state_dict(sd, strict=False)
+        missing = [k for k in res.missing_keys if not k.endswith("rotary_emb.inv_freq")]      # recomputed buffer (newer LLaMA exports drop it)
+        plugin_prefixes = tuple(f"model.{n}." if config.plugins_type[n] == "embedding" else f"{n}." for n in config.plugins_init_kwargs)
+        unexpected = [k for k in res.unexpected_keys if not (plugin_prefixes and k.startswith(plugin_prefixes))]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"checkpoint does not match the model: missing {missing[:8]}, unexpected {unexpected[:8]}")
+        if torch_dtype is not None or device is not None:
+            model.to(device=device, dtype=torch_dtype)
+        if reset_plugin_model_name_or_path:
+            config.reset_plugins_init_kwargs()
+        if len(tokenizer) > model.config.vocab_size:                                            # :1310-1316
+            model.resize_token_embeddings(len(tokenizer))
+        for _, init_kwargs in config.plugins_init_kwargs.items():                               # :1325-1328
+            if init_kwargs.get("pretrained_model_name_or_path", None) is None:
+                init_kwargs["pretrained_model_name_or_path"] = pretrained_model_name_or_path
+        model.init_plugin_modules()                                                             # :1330-1331 (after resize: see the BUG note there)
+        return model
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, inputs_embeds=None, **kwargs):
+        """reference :1511-1547 (the cache is a `KVCache`; a legacy tuple-of-tuples is measured the reference's way)."""
+        if past_key_values is not None:
+            past_length = past_key_values.get_seq_length() if hasattr(past_key_values, "get_seq_length") else past_key_values[0][0].shape[2]
+            if input_ids.shape[1] > past_length:
+                remove_prefix_length = past_length
+            else:
+                remove_prefix_length = input_ids.shape[1] - 1
+            input_ids = input_ids[:, remove_prefix_length:]
+        position_ids = kwargs.get("position_ids", None)
+        if attention_mask is not None and position_ids is None:
+            position_ids = attention_mask.long().cumsum(-1) - 1
+            position_ids.masked_fill_(attention_mask == 0, 1)
+            if past_key_values:
+                position_ids = position_ids[:, -input_ids.shape[1]:]
+        if inputs_embeds is not None and past_key_values is None:
+            model_inputs = {"inputs_embeds": inputs_embeds}
+        else:
+            model_inputs = {"input_ids": input_ids}
+        model_inputs.update({"position_ids": position_ids, "past_key_values": past_key_values, "use_cache": kwargs.get("use_cache"),
+                             "attention_mask": attention_mask, "images": kwargs.pop("images", None)})
+        return model_inputs
+
+    @staticmethod
+    def _reorder_cache(past_key_values, beam_idx):
+        """reference :1549-1554; a `KVCache` is reordered in place along its batch dimension."""
+        if isinstance(past_key_values, KVCache):
+            for li in range(len(past_key_values.k)):
+                idx = beam_idx.to(past_key_values.k[li].device)
+                past_key_values.k[li] = past_key_values.k[li].index_select(0, idx)
+                past_key_values.v[li] = past_key_values.v[li].index_select(0, idx)
+            return past_key_values
+        reordered_past = ()
+        for layer_past in past_key_values:
+            reordered_past += (tuple(past_state.index_select(0, beam_idx.to(past_state.device)) for past_state in layer_past),)
+        return reordered_past
 
     def get_input_embeddings(self):
         return self.model.embed_tokens
@@ -746,7 +938,7 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
         `.repeat(Nd, 1, 1)` is folded into `_CfgDropFn`'s broadcast."""
         from .modeling_plugins import gather_rows
         m = self.model
-        st = getattr(self.config, "special_tokens2ids_dict", None)
+        st = getattr(self.config, "special_tokens2ids_dict", None) or None     # {} (the config default) = not populated
         if st is not None:
             patch_id = st["additional_special_tokens"]["<im_patch>"]
             bos_id, eos_id = st["<s>"], st["</s>"]                  # DEFAULT_BOS/EOS_TOKEN keys (:1396-1397)
