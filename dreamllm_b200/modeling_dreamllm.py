@@ -952,18 +952,21 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
 
     # ---------------------------------------------------------------------------------------------- inference entry points
     @torch.no_grad()
+    def generate(self, input_ids, images=None, max_new_tokens=16, do_sample=False, temperature=1.0, top_k=0, top_p=1.0,
+                 repetition_penalty=1.0, eos_token_id=None, pad_token_id=None, generator=None, attention_mask=None, **kwargs):
+        """Decoding with the kv-cache (what HF `generate` does through the reference: omni/eval/vqa/vqa_inference.py:112-130): greedy or
+        temperature / top-k / top-p sampling with HF's processor semantics (dreamllm_b200/generation.py).  Beam search is not built."""
+        if kwargs.get("num_beams", 1) != 1:
+            raise NotImplementedError("beam search is not built (num_beams must be 1)")
+        from .generation import generate
+        return generate(self, input_ids, images=images, max_new_tokens=max_new_tokens, do_sample=do_sample, temperature=temperature,
+                        top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty, eos_token_id=eos_token_id,
+                        pad_token_id=pad_token_id, generator=generator, attention_mask=attention_mask)
+
+    @torch.no_grad()
     def generate_greedy(self, input_ids, max_new_tokens=16, images=None, eos_token_id=None):
-        """Greedy decoding with the kv-cache (the path HF `generate(do_sample=False)` takes through the reference,
-        omni/eval/vqa/vqa_inference.py:112-130).  Token-id / argmax path: bit-exact w.r.t. a full re-forward."""
-        out = self(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True)
-        cache = out.past_key_values
-        tokens = [out.logits[:, -1].argmax(-1)]
-        for _ in range(max_new_tokens - 1):
-            out = self(input_ids=tokens[-1][:, None], past_key_values=cache, use_cache=True, last_token_logits_only=True)
-            tokens.append(out.logits[:, -1].argmax(-1))
-            if eos_token_id is not None and bool((tokens[-1] == eos_token_id).all()):
-                break
-        return torch.cat([input_ids, torch.stack(tokens, 1)], 1)
+        """Greedy decoding (`do_sample=False`): token-id / argmax path, bit-exact w.r.t. a full re-forward."""
+        return self.generate(input_ids, images=images, max_new_tokens=max_new_tokens, do_sample=False, eos_token_id=eos_token_id)
 
     @torch.no_grad()
     def get_prompt_embeds(self, input_ids, images=None):

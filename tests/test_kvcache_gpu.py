@@ -70,3 +70,27 @@ def test_prompt_embeds_two_pass_equals_single_pass_and_pipeline_runs():
     img = m.stable_diffusion_pipeline(ids, neg, guidance_scale=3.0, num_inference_steps=2, height=128, width=128, scheduler="ddim",
                                       output_type="pt")
     assert img.shape == (2, 3, 128, 128) and float(img.min()) >= 0.0 and float(img.max()) <= 1.0
+
+
+def test_sampling_generate_and_eos_padding():
+    """`generate`: top_k=1 sampling is greedy; sampled tokens come from the top-k of a full re-forward; rows that hit EOS emit pad."""
+    m = _model().to(device="cuda", dtype=BF).eval()
+    ids = torch.randint(0, 32000, (2, 20), device="cuda")
+    greedy = m.generate(ids, max_new_tokens=5)
+    assert torch.equal(greedy, m.generate_greedy(ids, max_new_tokens=5))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    assert torch.equal(m.generate(ids, max_new_tokens=5, do_sample=True, top_k=1, generator=g), greedy)
+    samp = m.generate(ids, max_new_tokens=4, do_sample=True, top_k=8, temperature=1.5, generator=g)
+    assert samp.shape == (2, 24) and torch.equal(samp[:, :20], ids)
+    with torch.no_grad():
+        for t in range(20, 24):
+            ref = m(input_ids=samp[:, :t]).logits[:, -1]
+            top = ref.topk(12).indices                       # top-8 of the cached step, with slack for bf16 near-ties
+            assert bool((top == samp[:, t, None]).any(-1).all())
+    eos = int(greedy[0, 20])                                 # row 0's first generated token -> that row finishes at once
+    out = m.generate(ids, max_new_tokens=5, eos_token_id=eos, pad_token_id=0)
+    assert int(out[0, 20]) == eos and bool((out[0, 21:] == 0).all())
+    if eos not in greedy[1, 20:].tolist():
+        assert torch.equal(out[1], greedy[1])                # the other row is unaffected
+    with pytest.raises(NotImplementedError):
+        m.generate(ids, attention_mask=torch.tensor([[1] * 20, [1] * 19 + [0]], device="cuda"))
