@@ -928,6 +928,10 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
                 vm_loss = head(images_dm[: plan.n_dreams], enc_h, u_enc, **(sd_kwargs or {}))            # (:1441)
                 loss = vm_loss * self.loss_weight_vm + (loss if loss is not None else 0.0)               # (:1486-1488)
         info["vm_loss"] = vm_loss
+        sched = getattr(self.config, "loss_scale_schedule", "none")                                   # (:1472-1477, :1489)
+        if loss is not None and sched in ("l1_norm", "l2_norm"):
+            loss = loss / (self.loss_weight_lm + self.loss_weight_vm if sched == "l1_norm" else
+                           math.sqrt(self.loss_weight_lm ** 2 + self.loss_weight_vm ** 2))
         return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=out.past_key_values, hidden_states=out.hidden_states,
                                       additional_log_info=info)
 
