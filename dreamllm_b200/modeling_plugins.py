@@ -139,7 +139,7 @@ class DreamEmbedding(MultimodalEmbedding):
     def load_model(self, output_dir: str):
         f = os.path.join(output_dir, f"{self.save_model_name}.bin")
         if os.path.isfile(f):
-            self.load_state_dict(torch.load(f, map_location="cpu"))
+            self.load_state_dict(torch.load(f, map_location="cpu", weights_only=True))
 
     def forward(self, batch_size: int = 1):
         return self.dream_queries.repeat(batch_size, 1, 1)
@@ -236,7 +236,7 @@ class CLIPVisionEmbedding(MultimodalEmbedding):
     def load_model(self, output_dir: str):
         f = os.path.join(output_dir, f"{self.save_model_name}.bin")
         if os.path.isfile(f):
-            self.load_state_dict(torch.load(f, map_location="cpu"))
+            self.load_state_dict(torch.load(f, map_location="cpu", weights_only=True))
 
     def forward(self, images: torch.Tensor | None = None):
         """[Ni,3,R,R] -> [Ni,P,H].  `images=None` returns None: the reference's dummy CLIP pass on a zero image (:316-319,
@@ -559,7 +559,7 @@ class StableDiffusionHead(MultimodalHead):
     def load_model(self, output_dir: str):
         f = os.path.join(output_dir, f"{self.save_model_name}.bin")
         if os.path.isfile(f):
-            self.load_state_dict(torch.load(f, map_location="cpu"), strict=False)
+            self.load_state_dict(torch.load(f, map_location="cpu", weights_only=True), strict=False)
 
     def _alphas_cumprod(self, device):
         if getattr(self, "_ac", None) is None or self._ac.device != device:

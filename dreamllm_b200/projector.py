@@ -68,7 +68,7 @@ class BaseProjector(nn.Module):
             for suffix, whole in ((".bin", True), (".pt", False)):
                 f = os.path.join(model_name_or_path, f"{self.save_model_name}{suffix}") if os.path.isdir(model_name_or_path) else model_name_or_path
                 if os.path.isfile(f) and f.endswith(suffix):
-                    sd = torch.load(f, map_location="cpu")
+                    sd = torch.load(f, map_location="cpu", weights_only=True)
                     (self if whole else self.projector).load_state_dict(sd)
                     return True
         return False
