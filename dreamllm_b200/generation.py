@@ -53,9 +53,11 @@ def pick_next_token(logits: torch.Tensor, input_ids: torch.Tensor | None = None,
 @torch.no_grad()
 def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample: bool = False, temperature: float = 1.0, top_k: int = 0,
              top_p: float = 1.0, repetition_penalty: float = 1.0, eos_token_id=None, pad_token_id=None, generator=None,
-             attention_mask=None):
+             attention_mask=None, stopping_criteria=None):
     """Prefill once with the kv-cache, then one cached decode step per token.  Finished rows keep emitting `pad_token_id` (HF semantics);
-    stops when every row has produced an EOS.  Returns [B, S + n_generated] ids (prompt included, like HF for decoder-only models)."""
+    stops when every row has produced an EOS or a `stopping_criteria` callable `(input_ids, scores) -> bool | BoolTensor[B]` fires for it
+    (HF `StoppingCriteria` semantics; the reference's VQA eval passes a keyword criterion, omni/eval/vqa/vqa_inference.py:105-106).
+    Returns [B, S + n_generated] ids (prompt included, like HF for decoder-only models)."""
     if attention_mask is not None and not bool(attention_mask.all()):
         raise NotImplementedError("padded prompt batches are not supported by the kv-cache path; generate prompts of different lengths one at a time")
     eos = None
@@ -63,6 +65,8 @@ def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample:
         eos = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=input_ids.device)
         if pad_token_id is None:
             pad_token_id = int(eos[0])
+    if stopping_criteria and pad_token_id is None:
+        pad_token_id = 0
     warp = dict(temperature=temperature, top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty)
     seq = input_ids
     unfinished = torch.ones(input_ids.shape[0], dtype=torch.bool, device=input_ids.device)
@@ -70,11 +74,16 @@ def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample:
     cache = out.past_key_values
     for i in range(max_new_tokens):
         nxt = pick_next_token(out.logits[:, -1], seq, do_sample=do_sample, generator=generator, **warp)
+        if pad_token_id is not None:
+            nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_token_id))       # finished rows keep emitting pad
         if eos is not None:
-            nxt = torch.where(unfinished, nxt, torch.full_like(nxt, pad_token_id))
             unfinished = unfinished & ~torch.isin(nxt, eos)
         seq = torch.cat([seq, nxt[:, None]], 1)
-        if i + 1 == max_new_tokens or (eos is not None and not bool(unfinished.any())):
+        for crit in (stopping_criteria or ()):
+            done = crit(seq, out.logits[:, -1])
+            done = torch.as_tensor(done, device=seq.device, dtype=torch.bool)
+            unfinished = unfinished & ~(done.expand_as(unfinished))
+        if i + 1 == max_new_tokens or ((eos is not None or stopping_criteria) and not bool(unfinished.any())):
             break
         out = model(input_ids=nxt[:, None], past_key_values=cache, use_cache=True, last_token_logits_only=True)
     return seq

@@ -20,6 +20,7 @@ from dataclasses import dataclass
 
 import torch
 import torch.nn as nn
+import torch.utils.checkpoint
 
 from . import ops
 
@@ -490,6 +491,21 @@ class DreamLLMPreTrainedModel(nn.Module):
     def dtype(self):
         return next(self.parameters()).dtype
 
+    def gradient_checkpointing_enable(self, gradient_checkpointing_kwargs=None):
+        """PreTrainedModel API used by HF Trainer when `gradient_checkpointing=True` (projects/dreamllm/configs/stage1/base.py:90)."""
+        for m in self.modules():
+            if hasattr(m, "gradient_checkpointing"):
+                m.gradient_checkpointing = True
+
+    def gradient_checkpointing_disable(self):
+        for m in self.modules():
+            if hasattr(m, "gradient_checkpointing"):
+                m.gradient_checkpointing = False
+
+    @property
+    def is_gradient_checkpointing(self) -> bool:
+        return any(getattr(m, "gradient_checkpointing", False) for m in self.modules())
+
     # ---- HF on-disk layout -------------------------------------------------------------------------------------------------------
     def save_pretrained(self, save_directory: str, max_shard_size: int = 5 * 1024 ** 3, safe_serialization: bool = True):
         """config.json + model weights without the plugin keys (`_keys_to_ignore_on_save`, :826-831, :1230-1235); plugins write their own
@@ -695,6 +711,12 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
                 all_hidden += (hidden_states,)
             if cache is not None:
                 hidden_states = layer(hidden_states, position_ids=position_ids, past_key_value=(cache, li), use_cache=True)[0]
+            elif self.gradient_checkpointing and self.training and torch.is_grad_enabled():
+                # reference :994-1003.  Saves only the layer input and re-runs the (deterministic) layer forward inside backward: ~2.15 GB
+                # -> 0.27 GB of saved activations per layer at C2 shapes, for one extra forward (+33 % layer FLOPs).  Off by default:
+                # 180 GB holds the whole C2 step without recompute.
+                hidden_states = torch.utils.checkpoint.checkpoint(layer, hidden_states, attention_mask, position_ids, use_reentrant=False,
+                                                                  seqlens=seqlens, pos_i32=pos_i32)[0]
             else:
                 hidden_states = layer(hidden_states, attention_mask=attention_mask, position_ids=position_ids, seqlens=seqlens,
                                       pos_i32=pos_i32)[0]
@@ -957,7 +979,8 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
     # ---------------------------------------------------------------------------------------------- inference entry points
     @torch.no_grad()
     def generate(self, input_ids, images=None, max_new_tokens=16, do_sample=False, temperature=1.0, top_k=0, top_p=1.0,
-                 repetition_penalty=1.0, eos_token_id=None, pad_token_id=None, generator=None, attention_mask=None, **kwargs):
+                 repetition_penalty=1.0, eos_token_id=None, pad_token_id=None, generator=None, attention_mask=None,
+                 stopping_criteria=None, **kwargs):
         """Decoding with the kv-cache (what HF `generate` does through the reference: omni/eval/vqa/vqa_inference.py:112-130): greedy or
         temperature / top-k / top-p sampling with HF's processor semantics (dreamllm_b200/generation.py).  Beam search is not built."""
         if kwargs.get("num_beams", 1) != 1:
@@ -965,7 +988,8 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
         from .generation import generate
         return generate(self, input_ids, images=images, max_new_tokens=max_new_tokens, do_sample=do_sample, temperature=temperature,
                         top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty, eos_token_id=eos_token_id,
-                        pad_token_id=pad_token_id, generator=generator, attention_mask=attention_mask)
+                        pad_token_id=pad_token_id, generator=generator, attention_mask=attention_mask,
+                        stopping_criteria=stopping_criteria)
 
     @torch.no_grad()
     def generate_greedy(self, input_ids, max_new_tokens=16, images=None, eos_token_id=None):

@@ -47,3 +47,59 @@ def test_pick_next_token():
     assert torch.equal(a, b)                                                                           # seeded sampling is reproducible
     with pytest.raises(ValueError):
         warp_logits(scores, temperature=0.0)
+
+
+# ------------------------------------------------------------------------------------------------ decode loop on a scripted model
+class _Scripted:
+    """Stands in for DreamLLMForCausalMLM in `generation.generate`: next-token logits are a fixed function of (row, position), so the
+    loop's bookkeeping (cache hand-over, EOS / pad, stopping criteria, lengths) can be checked on CPU."""
+
+    def __init__(self, table):
+        self.table = table                     # [B, T] token to emit at each decode step
+        self.calls = []
+
+    def __call__(self, input_ids=None, images=None, past_key_values=None, use_cache=None, last_token_logits_only=None):
+        from types import SimpleNamespace
+        if past_key_values is None:
+            past_key_values = {"step": 0}                 # like KVCache: created at prefill, then advanced IN PLACE
+        else:
+            past_key_values["step"] += 1
+        step = past_key_values["step"]
+        self.calls.append((tuple(input_ids.shape), step > 0, images is not None))
+        B = input_ids.shape[0]
+        logits = torch.full((B, 1, 50), -10.0)
+        logits[torch.arange(B), 0, self.table[:, step]] = 10.0
+        return SimpleNamespace(logits=logits, past_key_values=past_key_values)
+
+
+def test_generate_loop_eos_pad_and_cache_handover():
+    from dreamllm_b200.generation import generate
+    table = torch.tensor([[5, 6, 2, 7, 8, 9], [11, 12, 13, 14, 2, 15]])
+    m = _Scripted(table)
+    ids = torch.tensor([[1, 3, 4], [1, 3, 3]])
+    out = generate(m, ids, images="img", max_new_tokens=6, eos_token_id=2, pad_token_id=0)
+    assert out.tolist() == [[1, 3, 4, 5, 6, 2, 0, 0], [1, 3, 3, 11, 12, 13, 14, 2]]        # stops when the last row hits EOS
+    assert m.calls[0] == ((2, 3), False, True)                                               # prefill: whole prompt + images, no cache
+    assert all(c == ((2, 1), True, False) for c in m.calls[1:]) and len(m.calls) == 5        # then one token per call on the cache
+    m = _Scripted(table)
+    out = generate(m, ids, max_new_tokens=3)
+    assert out.shape == (2, 6) and len(m.calls) == 3                                         # no model call after the last token
+    m = _Scripted(table)
+    out = generate(m, ids, max_new_tokens=6, eos_token_id=[2, 13])                           # several EOS ids; pad defaults to the first
+    assert out.tolist() == [[1, 3, 4, 5, 6, 2], [1, 3, 3, 11, 12, 13]]
+
+
+def test_generate_stopping_criteria():
+    from dreamllm_b200.generation import generate
+    table = torch.tensor([[5, 6, 7, 8, 9, 10]])
+    seen = []
+
+    def stop_on_7(input_ids, scores):
+        seen.append(input_ids.shape[1])
+        return bool((input_ids[0, -1] == 7))
+    out = generate(_Scripted(table), torch.tensor([[1, 3]]), max_new_tokens=6, stopping_criteria=[stop_on_7])
+    assert out.tolist() == [[1, 3, 5, 6, 7]] and seen == [3, 4, 5]
+    per_row = lambda ids, scores: ids[:, -1] == 6                                            # BoolTensor[B] form
+    out = generate(_Scripted(torch.tensor([[5, 6, 7, 8], [6, 9, 9, 6]])), torch.tensor([[1], [1]]), max_new_tokens=4,
+                   stopping_criteria=[per_row])
+    assert out.tolist() == [[1, 5, 6], [1, 6, 0]]
