@@ -485,6 +485,9 @@ def scheduler_tables(num_inference_steps, kind="ddim", num_train=1000, beta_star
     ac = torch.cumprod(1.0 - betas, dim=0)
     ratio = num_train // num_inference_steps
     ts = (torch.arange(num_inference_steps) * ratio).flip(0) + steps_offset
+    if num_inference_steps < 1 or int(ts.max()) >= num_train:
+        raise ValueError(f"num_inference_steps={num_inference_steps} with steps_offset={steps_offset} reaches timestep {int(ts.max())} "
+                         f">= num_train_timesteps={num_train} (diffusers' leading spacing has the same limit)")
     coef = torch.zeros(num_inference_steps, 5, dtype=torch.float64)
     for i, t in enumerate(ts.tolist()):
         a_t = ac[t]
