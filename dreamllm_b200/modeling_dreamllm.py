@@ -947,7 +947,7 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
                 u_enc = None
                 if getattr(head, "drop_prob", None) is not None:                                         # (:1420-1439)
                     u_enc = self._null_prompt_states(Q)
-                vm_loss = head(images_dm[: plan.n_dreams], enc_h, u_enc, **(sd_kwargs or {}))            # (:1441)
+                vm_loss = head(images_dm, enc_h, u_enc, **(sd_kwargs or {}))   # (:1441) fewer <dream_start> than images_dm -> the head's assert, as the reference
                 loss = vm_loss * self.loss_weight_vm + (loss if loss is not None else 0.0)               # (:1486-1488)
         info["vm_loss"] = vm_loss
         sched = getattr(self.config, "loss_scale_schedule", "none")                                   # (:1472-1477, :1489)
