@@ -73,35 +73,22 @@ class DreamLLMConfig:
                  rope_theta=10000.0, rope_scaling=None, attention_bias=False, special_tokens2ids_dict=None, plugins_init_kwargs=None,
                  plugins_type=None, loss_weight_lm=1.0, loss_weight_vm=10.0, loss_scale_schedule="none", log_attentions=False,
                  log_hidden_states=False, **kwargs):
-        self.vocab_size = vocab_size
-        self.max_position_embeddings = max_position_embeddings
-        self.hidden_size = hidden_size
-        self.intermediate_size = intermediate_size
-        self.num_hidden_layers = num_hidden_layers
-        self.num_attention_heads = num_attention_heads
-        self.num_key_value_heads = num_attention_heads if num_key_value_heads is None else num_key_value_heads
-        self.hidden_act = hidden_act
-        self.initializer_range = initializer_range
-        self.rms_norm_eps = rms_norm_eps
-        self.pretraining_tp = pretraining_tp
-        self.use_cache = use_cache
-        self.rope_theta = rope_theta
-        self.rope_scaling = rope_scaling
+        llama = dict(vocab_size=vocab_size, max_position_embeddings=max_position_embeddings, hidden_size=hidden_size,
+                     intermediate_size=intermediate_size, num_hidden_layers=num_hidden_layers, num_attention_heads=num_attention_heads,
+                     num_key_value_heads=num_attention_heads if num_key_value_heads is None else num_key_value_heads,
+                     hidden_act=hidden_act, initializer_range=initializer_range, rms_norm_eps=rms_norm_eps, pretraining_tp=pretraining_tp,
+                     use_cache=use_cache, rope_theta=rope_theta, rope_scaling=rope_scaling, attention_bias=attention_bias,
+                     pad_token_id=pad_token_id, bos_token_id=bos_token_id, eos_token_id=eos_token_id,
+                     tie_word_embeddings=tie_word_embeddings)
+        dream = dict(  # the reference's mutable `{}` defaults are shared between instances; fresh dicts here
+            special_tokens2ids_dict={} if special_tokens2ids_dict is None else special_tokens2ids_dict,
+            plugins_init_kwargs={} if plugins_init_kwargs is None else plugins_init_kwargs,
+            plugins_type={} if plugins_type is None else plugins_type,
+            loss_weight_lm=loss_weight_lm, loss_weight_vm=loss_weight_vm, loss_scale_schedule=loss_scale_schedule,
+            log_attentions=log_attentions, log_hidden_states=log_hidden_states)
+        for name, value in {**llama, **dream}.items():
+            setattr(self, name, value)
         self._rope_scaling_validation()
-        self.attention_bias = attention_bias
-        self.pad_token_id = pad_token_id
-        self.bos_token_id = bos_token_id
-        self.eos_token_id = eos_token_id
-        self.tie_word_embeddings = tie_word_embeddings
-        # the reference's mutable `{}` defaults are shared between instances; fresh dicts here
-        self.special_tokens2ids_dict = {} if special_tokens2ids_dict is None else special_tokens2ids_dict
-        self.plugins_init_kwargs = {} if plugins_init_kwargs is None else plugins_init_kwargs
-        self.plugins_type = {} if plugins_type is None else plugins_type
-        self.loss_weight_lm = loss_weight_lm
-        self.loss_weight_vm = loss_weight_vm
-        self.loss_scale_schedule = loss_scale_schedule
-        self.log_attentions = log_attentions
-        self.log_hidden_states = log_hidden_states
         for k, v in kwargs.items():                     # PretrainedConfig keeps unknown kwargs as attributes
             setattr(self, k, v)
 
@@ -111,16 +98,14 @@ class DreamLLMConfig:
 
     # ---------------------------------------------------------------------------------------------- reference methods
     def update_special_tokens2ids_dict(self, tokens_dict: dict, tokenizer):
-        """:225-235 — `{"additional_special_tokens": ["<im_start>", ...], "bos_token": "<s>"}` -> ids looked up in the tokenizer."""
-        for key, token in tokens_dict.items():
-            if isinstance(token, list):
-                ids = tokenizer.convert_tokens_to_ids(token)
-                if key not in self.special_tokens2ids_dict.keys():
-                    self.special_tokens2ids_dict[key] = {}
-                for _token, _id in zip(token, ids):
-                    self.special_tokens2ids_dict[key][_token] = _id
+        """:225-235 — `{"additional_special_tokens": ["<im_start>", ...], "bos_token": "<s>"}`: a list value becomes a nested
+        `{token: id}` table under its key, a single token is stored under the token string itself."""
+        table = self.special_tokens2ids_dict
+        for key, value in tokens_dict.items():
+            if isinstance(value, list):
+                table.setdefault(key, {}).update(zip(value, tokenizer.convert_tokens_to_ids(value)))
             else:
-                self.special_tokens2ids_dict[token] = tokenizer.convert_tokens_to_ids(token)
+                table[value] = tokenizer.convert_tokens_to_ids(value)
 
     def update_plugins(self, init_kwargs: dict) -> str:
         """:237-255."""
@@ -139,17 +124,17 @@ class DreamLLMConfig:
         return name
 
     def _rope_scaling_validation(self):
-        """:257-272."""
-        if self.rope_scaling is None:
+        """:257-272 — None, or exactly {"type": "linear" | "dynamic", "factor": float > 1}; same messages as the reference."""
+        rs = self.rope_scaling
+        if rs is None:
             return
-        if not isinstance(self.rope_scaling, dict) or len(self.rope_scaling) != 2:
-            raise ValueError(f"`rope_scaling` must be a dictionary with with two fields, `type` and `factor`, got {self.rope_scaling}")
-        rope_scaling_type = self.rope_scaling.get("type", None)
-        rope_scaling_factor = self.rope_scaling.get("factor", None)
-        if rope_scaling_type is None or rope_scaling_type not in ["linear", "dynamic"]:
-            raise ValueError(f"`rope_scaling`'s type field must be one of ['linear', 'dynamic'], got {rope_scaling_type}")
-        if rope_scaling_factor is None or not isinstance(rope_scaling_factor, float) or rope_scaling_factor <= 1.0:
-            raise ValueError(f"`rope_scaling`'s factor field must be an float > 1, got {rope_scaling_factor}")
+        if not (isinstance(rs, dict) and len(rs) == 2):
+            raise ValueError(f"`rope_scaling` must be a dictionary with with two fields, `type` and `factor`, got {rs}")
+        kind, factor = rs.get("type"), rs.get("factor")
+        if kind not in ("linear", "dynamic"):
+            raise ValueError(f"`rope_scaling`'s type field must be one of ['linear', 'dynamic'], got {kind}")
+        if not (isinstance(factor, float) and factor > 1.0):
+            raise ValueError(f"`rope_scaling`'s factor field must be an float > 1, got {factor}")
 
     def reset_plugins_init_kwargs(self, pretrained_plugin_model_name_or_path: str = None):
         """:274-278."""
