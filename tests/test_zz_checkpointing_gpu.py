@@ -1,7 +1,6 @@
 """Gradient checkpointing of the decoder stack (reference modeling_dreamllm.py:994-1003; `gradient_checkpointing=True` in the shipped
 training configs): recomputing each layer's forward inside backward gives the same loss and gradients as keeping the activations, with a
-smaller activation peak.  (File sorts last on purpose: written after this round's GPU budget was spent — first hardware run is the
-round-end suite.)"""
+smaller activation peak."""
 import pytest
 import torch
 
