@@ -231,21 +231,22 @@ def _worker(rank, world, port, q, state_dtype_name):
     norms = []
     for _ in range(3):
         opt.zero_grad()
-        net(x[rank * 4:(rank + 1) * 4]).float().pow(2).mean().backward()
+        per = 8 // world if world in (2, 4) else 2
+        net(x[rank * per:(rank + 1) * per]).float().pow(2).mean().backward()
         norms.append(float(opt.step()))
     q.put((rank, {k: v.detach().clone() for k, v in net.named_parameters()}, opt.launched, opt.state_bytes_per_rank(), norms))
     dist.destroy_process_group()
 
 
-def _run_two(state_dtype_name):
+def _run_two(state_dtype_name, world=2):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, state_dtype_name)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, state_dtype_name)) for r in range(world)]
     for p in procs:
         p.start()
     try:
-        res = [q.get(timeout=240) for _ in range(2)]
+        res = [q.get(timeout=240) for _ in range(world)]
     finally:
         for p in procs:
             p.join(timeout=60)
@@ -292,3 +293,22 @@ def test_two_ranks_sharded_equals_single_process_on_averaged_grads(state_dtype_n
     assert launched0 == launched1 and launched0 >= 3 * 2 * len(opt.buckets)
     full = _make(_net(), max_grad_norm=0.0, state_dtype=state_dtype).state_bytes_per_rank()
     assert bytes0 <= full // 2 + 3 * 4 * 128 * len(opt.buckets)             # each rank holds half the state (+ padding)
+
+
+def test_three_ranks_uneven_padding_stay_in_lockstep():
+    """world 3: bucket sizes are not multiples of the world size -> padded shards; every rank must end with identical parameters that
+    moved away from the initial ones, and own a third of the optimizer state."""
+    try:
+        res = _run_two("float32", world=3)
+    except Exception:
+        res = _run_two("float32", world=3)
+    ref = _net()
+    base = {k: v.detach().clone() for k, v in ref.named_parameters()}
+    p0 = res[0][1]
+    for _, pr, launched, nbytes, norms in res[1:]:
+        for k in p0:
+            assert torch.equal(p0[k], pr[k]), k
+        assert norms == res[0][4] and launched == res[0][2]
+    assert any(not torch.equal(p0[k], base[k]) for k in p0 if k != "unused.weight")
+    full = _make(_net(), max_grad_norm=0.0, state_dtype=torch.float32).state_bytes_per_rank()
+    assert res[0][3] <= full // 3 + 3 * 4 * 128 * 8
