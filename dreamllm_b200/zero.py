@@ -73,6 +73,7 @@ class ShardedAdamW:
         self._sumsq = sumsq_fn or _cuda_sumsq
         self.step_count = 0
         self.launched = 0            # reduce-scatters + all-gathers issued (tests / bench bookkeeping)
+        self._sync = True            # False inside no_sync(): micro-batch gradients accumulate locally, nothing goes on the wire
         params = list(params)
         if params and not isinstance(params[0], dict):
             params = [{"params": params}]
@@ -170,7 +171,10 @@ class ShardedAdamW:
             p.grad = v
         b.pending.discard(p)
         if not b.pending:
-            self._reduce_scatter(b)
+            if self._sync:
+                self._reduce_scatter(b)
+            else:
+                b.pending = set(b.params)      # next micro-batch accumulates in place into the same views (p.grad stays the view)
 
     def _reduce_scatter(self, b):
         if self.world == 1:
@@ -181,6 +185,20 @@ class ShardedAdamW:
             b.flat_grad.div_(self.world)
             b.work = dist.reduce_scatter_tensor(b.gshard, b.flat_grad, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
         self.launched += 1
+
+    def no_sync(self):
+        """Gradient accumulation (HF `gradient_accumulation_steps`, DDP.no_sync semantics): inside the context, backward only accumulates
+        into the local flat gradient buckets; the first backward outside it reduce-scatters the accumulated sum."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            prev, self._sync = self._sync, False
+            try:
+                yield
+            finally:
+                self._sync = prev
+        return ctx()
 
     def zero_grad(self, set_to_none: bool = True):
         for b in self.buckets:

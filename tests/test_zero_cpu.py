@@ -312,3 +312,31 @@ def test_three_ranks_uneven_padding_stay_in_lockstep():
     assert any(not torch.equal(p0[k], base[k]) for k in p0 if k != "unused.weight")
     full = _make(_net(), max_grad_norm=0.0, state_dtype=torch.float32).state_bytes_per_rank()
     assert res[0][3] <= full // 3 + 3 * 4 * 128 * 8
+
+
+def test_no_sync_accumulates_micro_batches():
+    """Two micro-batches under no_sync() + one synced backward == one backward over the summed loss (world 1; the wire path is the same
+    reduce-scatter as every other step)."""
+    net, ref = _net(), _net()
+    opt, ropt = _make(net, max_grad_norm=0.0, state_dtype=BF), _make(ref, max_grad_norm=0.0, state_dtype=BF)
+    x = _data()
+    for _ in range(2):
+        opt.zero_grad()
+        with opt.no_sync():
+            net(x[:3]).float().pow(2).mean().backward()
+            net(x[3:5]).float().pow(2).mean().backward()
+        net(x[5:]).float().pow(2).mean().backward()
+        acc = {k: p.grad.clone() for k, p in net.named_parameters() if p.grad is not None}
+        opt.step()
+        # expectation: autograd's own accumulation of the three micro-batch gradients (bf16 adds in the same order)
+        ropt.zero_grad()
+        for p in ref.parameters():
+            p.grad = None
+        for sl in (slice(0, 3), slice(3, 5), slice(5, 8)):
+            ref(x[sl]).float().pow(2).mean().backward()
+        for k, p in ref.named_parameters():
+            if p.grad is not None:
+                assert torch.equal(acc[k], p.grad), k
+        ropt.step()
+        for (k, a), (_, b) in zip(net.named_parameters(), ref.named_parameters()):
+            assert torch.equal(a.detach(), b.detach()), k
