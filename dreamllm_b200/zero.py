@@ -53,7 +53,7 @@ def _cuda_sumsq(g, out):
 
 class _Bucket:
     __slots__ = ("params", "n", "padded", "chunk", "flat_param", "flat_grad", "pviews", "gviews", "gshard", "pshard", "master", "m", "v",
-                 "pending", "work", "group")
+                 "pending", "work", "group", "gather")
 
 
 class ShardedAdamW:
@@ -73,6 +73,7 @@ class ShardedAdamW:
         self._sumsq = sumsq_fn or _cuda_sumsq
         self.step_count = 0
         self.launched = 0            # reduce-scatters + all-gathers issued (tests / bench bookkeeping)
+        self._attached = False
         self._sync = True            # False inside no_sync(): micro-batch gradients accumulate locally, nothing goes on the wire
         params = list(params)
         if params and not isinstance(params[0], dict):
@@ -113,6 +114,11 @@ class ShardedAdamW:
         for b in self.buckets:
             for p in b.params:
                 self._bucket_of[p] = b
+        order = 0
+        for g in self.param_groups:
+            for p in g["params"]:
+                p._zero_order = order            # registration (= forward) order, used to issue the parameter all-gathers front to back
+                order += 1
         self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for b in self.buckets for p in b.params]
         dev = self.buckets[0].flat_param.device if self.buckets else torch.device("cpu")
         self._ss = torch.zeros(1, dtype=torch.float32, device=dev)
@@ -150,6 +156,7 @@ class ShardedAdamW:
             b.v = torch.zeros(b.chunk, dtype=torch.bfloat16, device=dev)
         b.pending = set(plist)
         b.work = None
+        b.gather = None
         self.buckets.append(b)
 
     def reseat(self):
@@ -208,9 +215,12 @@ class ShardedAdamW:
 
     # ------------------------------------------------------------------------------------------ step
     @torch.no_grad()
-    def step(self, lr_scale: float = 1.0):
+    def step(self, lr_scale: float = 1.0, defer_gather: bool = False):
         """Finish the gradient reduce-scatters, clip by the global norm, update the owned shards, all-gather the parameters.
-        Returns the (unclipped) global gradient norm as a 0-d device tensor (no host sync)."""
+        Returns the (unclipped) global gradient norm as a 0-d device tensor (no host sync).
+        `defer_gather=True` (needs `attach(model)`): the all-gathers are issued in forward order and only waited for by the forward
+        pre-hook of the first module that reads each bucket, so they overlap the start of the next forward instead of ending the step."""
+        self.wait_gathers()
         for b in self.buckets:
             for p in b.params:
                 if p.data.data_ptr() != b.pviews[p].data_ptr():
@@ -236,23 +246,46 @@ class ShardedAdamW:
             self._sumsq(b.gshard, self._ss)
         if self.world > 1:
             dist.all_reduce(self._ss, op=dist.ReduceOp.SUM, group=self.pg)
-        gathers = []
-        for b in live:
+        if defer_gather and not self._attached:
+            raise RuntimeError("defer_gather=True needs ShardedAdamW.attach(model) (forward pre-hooks wait for the parameter all-gathers)")
+        for b in sorted(live, key=lambda bb: bb.params[0]._zero_order):        # forward order: the first layers' parameters arrive first
             g = b.group
             self._update(b.gshard, b.pshard, b.m, b.v, b.master, lr=g["lr"] * lr_scale, beta1=g["betas"][0], beta2=g["betas"][1],
                          eps=g["eps"], weight_decay=g["weight_decay"], step=self.step_count, grad_sumsq=self._ss if clip else None,
                          max_grad_norm=self.max_grad_norm)
             if self.world > 1:
-                gathers.append(dist.all_gather_into_tensor(b.flat_param, b.pshard, group=self.pg, async_op=True))
+                b.gather = dist.all_gather_into_tensor(b.flat_param, b.pshard, group=self.pg, async_op=True)
                 self.launched += 1
-        for w in gathers:
-            w.wait()
+        if not defer_gather:
+            self.wait_gathers()
         for b in self.buckets:
             b.pending = set(b.params)
         return self._ss.sqrt().squeeze(0)
 
+    def wait_gathers(self, buckets=None):
+        """Make the current stream wait for outstanding parameter all-gathers (all buckets, or the given ones)."""
+        for b in (self.buckets if buckets is None else buckets):
+            if b.gather is not None:
+                b.gather.wait()
+                b.gather = None
+
+    def attach(self, model):
+        """Register forward pre-hooks on every module that directly owns bucketed parameters: before such a module runs, the all-gathers
+        of the buckets it reads are waited for (no-op when none is outstanding).  Enables `step(defer_gather=True)`."""
+        for mod in model.modules():
+            mine = []
+            for p in mod.parameters(recurse=False):
+                b = self._bucket_of.get(p)
+                if b is not None and b not in mine:
+                    mine.append(b)
+            if mine:
+                self._hooks.append(mod.register_forward_pre_hook(lambda m, args, _b=tuple(mine): self.wait_gathers(_b)))
+        self._attached = True
+        return self
+
     # ------------------------------------------------------------------------------------------ checkpoint / resume
     def state_dict(self):
+        self.wait_gathers()
         """This rank's shard of the optimizer state (the reference saves FSDP-sharded optimizer state per rank as well)."""
         return {"step": self.step_count, "world": self.world, "rank": self.rank, "state_dtype": str(self.state_dtype),
                 "buckets": [{"n": b.n, "chunk": b.chunk, "m": b.m.clone(), "v": b.v.clone(),

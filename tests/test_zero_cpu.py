@@ -220,29 +220,32 @@ def test_clipping_and_state_dict_round_trip():
 
 
 # ------------------------------------------------------------------------------------------------ world_size 2 over gloo
-def _worker(rank, world, port, q, state_dtype_name):
+def _worker(rank, world, port, q, state_dtype_name, defer=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     state_dtype = getattr(torch, state_dtype_name)
     net = _net()
     opt = _make(net, max_grad_norm=0.0, state_dtype=state_dtype)
+    if defer:
+        opt.attach(net)
     x = _data()
     norms = []
     for _ in range(3):
         opt.zero_grad()
         per = 8 // world if world in (2, 4) else 2
         net(x[rank * per:(rank + 1) * per]).float().pow(2).mean().backward()
-        norms.append(float(opt.step()))
+        norms.append(float(opt.step(defer_gather=defer)))
+    opt.wait_gathers()
     q.put((rank, {k: v.detach().clone() for k, v in net.named_parameters()}, opt.launched, opt.state_bytes_per_rank(), norms))
     dist.destroy_process_group()
 
 
-def _run_two(state_dtype_name, world=2):
+def _run_two(state_dtype_name, world=2, defer=False):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, state_dtype_name)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, state_dtype_name, defer)) for r in range(world)]
     for p in procs:
         p.start()
     try:
@@ -340,3 +343,20 @@ def test_no_sync_accumulates_micro_batches():
         ropt.step()
         for (k, a), (_, b) in zip(net.named_parameters(), ref.named_parameters()):
             assert torch.equal(a.detach(), b.detach()), k
+
+
+def test_deferred_all_gather_gives_the_same_parameters():
+    """step(defer_gather=True): all-gathers are waited for by forward pre-hooks (attach) instead of at the end of step() — same result."""
+    try:
+        plain, deferred = _run_two("float32"), _run_two("float32", defer=True)
+    except Exception:
+        plain, deferred = _run_two("float32"), _run_two("float32", defer=True)
+    for (_, pa, *_), (_, pb, *_) in zip(plain, deferred):
+        for k in pa:
+            assert torch.equal(pa[k], pb[k]), k
+    net = _net()
+    opt = _make(net, max_grad_norm=0.0)
+    with pytest.raises(RuntimeError, match="attach"):
+        opt.zero_grad()
+        net(_data()).float().pow(2).mean().backward()
+        opt.step(defer_gather=True)
