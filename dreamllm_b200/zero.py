@@ -41,6 +41,51 @@ def cosine_schedule_with_warmup(step: int, num_warmup_steps: int, num_training_s
     return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
 
 
+def decay_parameter_names(model) -> list:
+    """Names of the parameters weight decay applies to — `Trainer.get_decay_parameter_names` (omni/train/trainer.py:381-390): everything
+    that does not live inside a normalisation layer (`ALL_LAYERNORM_LAYERS` = nn.LayerNorm + DreamLLMRMSNorm, modeling_dreamllm.py:94) and has
+    no "bias" in its name."""
+    import torch.nn as nn
+
+    from .modeling_dreamllm import DreamLLMRMSNorm
+    norm_types = (nn.LayerNorm, DreamLLMRMSNorm)
+
+    def walk(mod, prefix):
+        names = []
+        for cname, child in mod.named_children():
+            if not isinstance(child, norm_types):
+                names += walk(child, f"{prefix}{cname}.")
+        names += [f"{prefix}{n}" for n in mod._parameters.keys()]      # parameters defined directly on this module
+        return names
+
+    return [n for n in walk(model, "") if "bias" not in n]
+
+
+def optimizer_param_groups(model, weight_decay: float) -> list:
+    """The two groups `Trainer.create_optimizer` builds (omni/train/trainer.py:436-446): trainable decay / no-decay parameters."""
+    decay = set(decay_parameter_names(model))
+    named = list(model.named_parameters())
+    return [{"params": [p for n, p in named if n in decay and p.requires_grad], "weight_decay": weight_decay},
+            {"params": [p for n, p in named if n not in decay and p.requires_grad], "weight_decay": 0.0}]
+
+
+def training_step(model, optimizer, batch: dict, lr_scale: float = 1.0, accumulate: bool = False):
+    """One data-parallel training step (`Trainer.training_step` + the optimizer part of `_inner_training_loop`,
+    omni/train/trainer.py:1007-1049, :744-835): forward, backward (gradient buckets reduce-scatter as they fill), and — unless this is an
+    accumulation micro-step — global-norm clip + sharded AdamW + parameter all-gather.  Returns (loss.detach(), grad_norm | None)."""
+    model.train()
+    if accumulate:
+        with optimizer.no_sync():
+            out = model(**batch)
+            out.loss.backward()
+        return out.loss.detach(), None
+    out = model(**batch)
+    out.loss.backward()
+    norm = optimizer.step(lr_scale=lr_scale)
+    optimizer.zero_grad()
+    return out.loss.detach(), norm
+
+
 def _cuda_update(g, p, m, v, master, **kw):
     from . import ops
     ops.adamw_step_(g, p, m, v, master, **kw)

@@ -360,3 +360,54 @@ def test_deferred_all_gather_gives_the_same_parameters():
         opt.zero_grad()
         net(_data()).float().pow(2).mean().backward()
         opt.step(defer_gather=True)
+
+
+def test_decay_groups_match_transformers_get_parameter_names():
+    """`decay_parameter_names` == transformers' `get_parameter_names(model, ALL_LAYERNORM_LAYERS)` minus "bias" (what the reference's
+    Trainer.create_optimizer does, omni/train/trainer.py:381-446), on a model mixing nn.LayerNorm, DreamLLMRMSNorm, biases and a bare Parameter."""
+    from transformers.trainer_pt_utils import get_parameter_names
+
+    from dreamllm_b200.modeling_dreamllm import DreamLLMConfig, DreamLLMForCausalMLM, DreamLLMRMSNorm
+    from dreamllm_b200.modeling_plugins import DreamEmbedding
+    from dreamllm_b200.zero import decay_parameter_names, optimizer_param_groups
+    m = DreamLLMForCausalMLM(DreamLLMConfig(vocab_size=64, hidden_size=128, intermediate_size=256, num_hidden_layers=2, num_attention_heads=2))
+    m.model.dream_embedding = DreamEmbedding(num_dream_queries=4, embed_hidden_size=128)
+    m.extra = nn.Sequential(nn.Linear(8, 8, bias=True), nn.LayerNorm(8))
+    want = [n for n in get_parameter_names(m, [nn.LayerNorm, DreamLLMRMSNorm]) if "bias" not in n]
+    got = decay_parameter_names(m)
+    assert sorted(got) == sorted(want)
+    assert "model.layers.0.input_layernorm.weight" not in got and "model.norm.weight" not in got and "extra.0.bias" not in got
+    assert "model.dream_embedding.dream_queries" in got and "model.layers.1.mlp.down_proj.weight" in got
+    m.lm_head.weight.requires_grad_(False)
+    groups = optimizer_param_groups(m, 0.1)
+    assert groups[0]["weight_decay"] == 0.1 and groups[1]["weight_decay"] == 0.0
+    n_train = sum(p.requires_grad for p in m.parameters())
+    assert len(groups[0]["params"]) + len(groups[1]["params"]) == n_train
+    assert all(p is not m.lm_head.weight for g in groups for p in g["params"])
+
+
+def test_training_step_glue_with_groups_and_accumulation():
+    from dreamllm_b200.zero import ShardedAdamW, optimizer_param_groups, training_step
+
+    class Wrapped(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = _net()
+
+        def forward(self, x):
+            from types import SimpleNamespace
+            return SimpleNamespace(loss=self.net(x).float().pow(2).mean())
+    torch.manual_seed(0)
+    m = Wrapped()
+    opt = ShardedAdamW(optimizer_param_groups(m, 0.05), lr=1e-2, max_grad_norm=1.0, bucket_cap_mb=0.001, update_fn=AO.adamw_flat_,
+                       sumsq_fn=AO.sumsq_flat)
+    assert {g["weight_decay"] for g in opt.param_groups} == {0.05, 0.0}
+    x = _data()
+    before = m.net.q.weight.detach().clone()
+    l0, n0 = training_step(m, opt, dict(x=x[:4]), accumulate=True)
+    assert n0 is None and torch.equal(m.net.q.weight.detach(), before)           # micro-step: no update yet
+    l1, n1 = training_step(m, opt, dict(x=x[4:]))
+    assert float(n1) > 0 and not torch.equal(m.net.q.weight.detach(), before)
+    assert all(p.grad is None for p in m.parameters())                            # zero_grad after the step
+    losses = [float(training_step(m, opt, dict(x=x))[0]) for _ in range(25)]
+    assert losses[-1] < 0.5 * losses[0]
