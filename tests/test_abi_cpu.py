@@ -58,3 +58,18 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "from oracle" not in txt, os.path.join(dp, f)
+
+
+def test_host_only_entry_points_answer_without_a_gpu():
+    """Version, error strings and the `*_workspace_bytes` queries are pure host code: callable on the build box (no compute is launched)."""
+    from dreamllm_b200 import _lib
+    L = _lib.lib()
+    assert L.dllm_version() >= 100
+    msgs = {code: L.dllm_error_string(code).decode() for code in (0, -1, -2, -3, -4, -5, -6)}
+    assert len(set(msgs.values())) == len(msgs) and all(msgs.values())
+    assert L.dllm_rmsnorm_bwd_workspace_bytes(16384, 4096) >= 64 * 4096 * 4 > 0          # 64-way column partials (DESIGN §4)
+    assert L.dllm_attn_bwd_workspace_bytes(8, 2048, 32, 128) >= 8 * 32 * 2048 * 4        # at least the fp32 row term D = rowsum(dO * O)
+    assert L.dllm_attn_bwd_workspace_bytes(8, 2048, 32, 128) > L.dllm_attn_bwd_workspace_bytes(1, 512, 32, 128)
+    assert L.dllm_groupnorm_workspace_bytes(16, 64 * 64, 32) > 0
+    assert L.dllm_sumsq_workspace_bytes() == 148 * 4 * 4
+    assert L.dllm_get_reserved_sms() == 0
