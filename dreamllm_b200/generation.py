@@ -87,3 +87,111 @@ def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample:
             break
         out = model(input_ids=nxt[:, None], past_key_values=cache, use_cache=True, last_token_logits_only=True)
     return seq
+
+
+# ------------------------------------------------------------------------------------------------ beam search
+def _gather_beams(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+    """t [B, K, ...], idx [B, k] -> t[b, idx[b, j], ...]"""
+    view = idx.reshape(idx.shape + (1,) * (t.dim() - 2)).expand(idx.shape + t.shape[2:])
+    return torch.gather(t, 1, view)
+
+
+@torch.no_grad()
+def beam_search(model, input_ids, images=None, num_beams: int = 5, max_new_tokens: int = 16, length_penalty: float = 1.0,
+                early_stopping=False, eos_token_id=None, pad_token_id=None, stopping_criteria=None,
+                length_normalization: str = "generated", return_scores: bool = False):
+    """Beam search over the kv-cache decode path — what `model.generate(..., num_beams=5)` does in the reference's default VQA eval
+    (omni/eval/vqa/vqa_inference.py:111-119, `--beamsearch True` is the default, omni/utils/eval_utils.py:141).
+
+    Semantics = transformers' beam search (accumulated log-probs, top `2 x num_beams` continuations per step so that `num_beams` live beams
+    survive EOS picks, finished hypotheses ranked by sum_logprobs / length**length_penalty, the `early_stopping=False` "can the best live
+    beam still beat the worst finished one" heuristic).  `length_normalization="generated"` divides by the number of generated tokens, as
+    transformers >= 4.36 and the version installed here do — tests/test_generation_cpu.py pins this mode to the installed
+    `GenerationMixin.generate(num_beams=...)` on random LLaMAs; `"total"` divides by prompt + generated length, the rule of the 4.35.x
+    scorer the reference pins (restated from memory: that version cannot be installed here, so this mode is unpinned).
+    The prompt is prefilled once per sample; the cache is then repeated per beam and re-ordered in place every step.
+    Returns [B, prompt + generated] ids of the best hypothesis per sample (padded with `pad_token_id` after EOS)."""
+    if length_normalization not in ("generated", "total"):
+        raise ValueError("length_normalization must be 'generated' or 'total'")
+    dev = input_ids.device
+    B, prompt_len = input_ids.shape
+    k = int(num_beams)
+    max_length = prompt_len + int(max_new_tokens)
+    eos = None
+    if eos_token_id is not None:
+        eos = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=dev)
+    n_eos = 0 if eos is None else int(eos.numel())
+    K = max(2, 1 + n_eos) * k                                           # candidates kept per sample and step
+    fill = pad_token_id if pad_token_id is not None else (int(eos[0]) if eos is not None else 0)
+    NEG = -1.0e9
+
+    running = torch.full((B, k, max_length), fill, dtype=torch.long, device=dev)
+    running[:, :, :prompt_len] = input_ids[:, None, :]
+    finished = running.clone()
+    running_scores = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    running_scores[:, 1:] = NEG                                         # all beams start identical: only beam 0 may branch
+    finished_scores = torch.full((B, k), NEG, dtype=torch.float32, device=dev)
+    finished_len = torch.zeros((B, k), dtype=torch.long, device=dev)    # generated tokens of each finished hypothesis
+    is_finished = torch.zeros((B, k), dtype=torch.bool, device=dev)
+    heuristic_open = torch.ones((B, 1), dtype=torch.bool, device=dev)
+    top_k_mask = torch.arange(K, device=dev)[None, :] < k
+
+    def norm_len(generated):                                             # length used by the length penalty
+        return float(generated if length_normalization == "generated" else generated + prompt_len)
+
+    out = model(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True)
+    cache = out.past_key_values
+    cache.repeat_interleave(k)
+    logits = out.logits[:, -1].float().repeat_interleave(k, dim=0)      # [B*k, V]
+    cur_len = prompt_len
+    while True:
+        V = logits.shape[-1]
+        logp = torch.log_softmax(logits, dim=-1).view(B, k, V) + running_scores[:, :, None]
+        cand_scores, flat = torch.topk(logp.view(B, k * V), K, dim=1)
+        src_beam, token = flat // V, flat % V
+        cand = _gather_beams(running, src_beam)
+        cand[:, :, cur_len] = token
+        hits = torch.zeros((B, K), dtype=torch.bool, device=dev)
+        if eos is not None:
+            hits |= torch.isin(token, eos)
+        if cur_len + 1 >= max_length:
+            hits |= True
+        for crit in (stopping_criteria or ()):                       # HF StoppingCriteria: (candidate sequences [B*K, len], scores) -> bool | [B*K]
+            done = torch.as_tensor(crit(cand[:, :, :cur_len + 1].reshape(B * K, cur_len + 1), None), device=dev, dtype=torch.bool)
+            hits |= done.reshape(B, K) if done.numel() == B * K else bool(done)
+        # live beams for the next step: the best num_beams candidates that did not just finish
+        live_scores = cand_scores + hits.float() * NEG
+        pick = torch.topk(live_scores, k, dim=1)[1]
+        running = _gather_beams(cand, pick)
+        running_scores = _gather_beams(live_scores, pick)
+        next_src = _gather_beams(src_beam, pick)
+        # finished hypotheses: only candidates ranked inside the top num_beams may finish (the rest are spares)
+        just_finished = hits & top_k_mask
+        gen_now = cur_len + 1 - prompt_len
+        fin_scores = cand_scores / (norm_len(gen_now) ** length_penalty)
+        if early_stopping is True:
+            fin_scores = fin_scores + torch.all(is_finished, dim=-1, keepdim=True).float() * NEG
+        fin_scores = fin_scores + (~heuristic_open).float() * NEG + (~just_finished).float() * NEG
+        m_seqs = torch.cat([finished, cand], 1)
+        m_scores = torch.cat([finished_scores, fin_scores], 1)
+        m_len = torch.cat([finished_len, torch.full((B, K), gen_now, dtype=torch.long, device=dev)], 1)
+        m_fin = torch.cat([is_finished, just_finished], 1)
+        best = torch.topk(m_scores, k, dim=1)[1]
+        finished, finished_scores = _gather_beams(m_seqs, best), _gather_beams(m_scores, best)
+        finished_len, is_finished = _gather_beams(m_len, best), _gather_beams(m_fin, best)
+        cur_len += 1
+        # can the best live beam still beat the worst finished hypothesis?
+        gen_live = cur_len - prompt_len
+        hyp_len = (max_length - prompt_len) if (early_stopping == "never" and length_penalty > 0.0) else gen_live
+        best_live = running_scores[:, :1] / (norm_len(hyp_len) ** length_penalty)
+        worst_fin = torch.where(is_finished, finished_scores.min(dim=1, keepdim=True)[0], torch.full_like(finished_scores, NEG))
+        heuristic_open = heuristic_open & torch.any(best_live > worst_fin, dim=-1, keepdim=True)
+        more = bool(torch.any(heuristic_open)) and not (bool(torch.all(is_finished)) and early_stopping is True) and not bool(torch.all(hits))
+        if not more:
+            break
+        cache.reorder((next_src + torch.arange(B, device=dev)[:, None] * k).reshape(-1))
+        out = model(input_ids=running[:, :, cur_len - 1].reshape(B * k, 1), past_key_values=cache, use_cache=True, last_token_logits_only=True)
+        logits = out.logits[:, -1].float()
+    out_len = prompt_len + int(finished_len[:, 0].max())
+    seqs = finished[:, 0, :out_len]
+    return (seqs, finished_scores[:, 0]) if return_scores else seqs

@@ -321,6 +321,23 @@ class KVCache:
     def get_seq_length(self):
         return self.len
 
+    def repeat_interleave(self, k: int):
+        """Beam search: every sample's cache rows repeated k times along the batch dimension (in place)."""
+        for li in range(len(self.k)):
+            self.k[li] = self.k[li].repeat_interleave(k, dim=0)
+            self.v[li] = self.v[li].repeat_interleave(k, dim=0)
+        return self
+
+    def reorder(self, beam_idx):
+        """Beam search: row b takes the history of row beam_idx[b] (reference `_reorder_cache`, :1549-1554).  Only the valid prefix
+        [:len] is moved."""
+        L = self.len
+        for li in range(len(self.k)):
+            idx = beam_idx.to(self.k[li].device)
+            self.k[li][:, :L] = self.k[li][:, :L].index_select(0, idx)
+            self.v[li][:, :L] = self.v[li][:, :L].index_select(0, idx)
+        return self
+
 
 class DreamLLMDecoderLayer(nn.Module):
     def __init__(self, config):
@@ -875,11 +892,7 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
     def _reorder_cache(past_key_values, beam_idx):
         """reference :1549-1554; a `KVCache` is reordered in place along its batch dimension."""
         if isinstance(past_key_values, KVCache):
-            for li in range(len(past_key_values.k)):
-                idx = beam_idx.to(past_key_values.k[li].device)
-                past_key_values.k[li] = past_key_values.k[li].index_select(0, idx)
-                past_key_values.v[li] = past_key_values.v[li].index_select(0, idx)
-            return past_key_values
+            return past_key_values.reorder(beam_idx)
         reordered_past = ()
         for layer_past in past_key_values:
             reordered_past += (tuple(past_state.index_select(0, beam_idx.to(past_state.device)) for past_state in layer_past),)
@@ -982,10 +995,18 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
                  repetition_penalty=1.0, eos_token_id=None, pad_token_id=None, generator=None, attention_mask=None,
                  stopping_criteria=None, **kwargs):
         """Decoding with the kv-cache (what HF `generate` does through the reference: omni/eval/vqa/vqa_inference.py:112-130): greedy or
-        temperature / top-k / top-p sampling with HF's processor semantics (dreamllm_b200/generation.py).  Beam search is not built."""
-        if kwargs.get("num_beams", 1) != 1:
-            raise NotImplementedError("beam search is not built (num_beams must be 1)")
-        from .generation import generate
+        temperature / top-k / top-p sampling with HF's processor semantics, or beam search with `num_beams > 1` (dreamllm_b200/generation.py)."""
+        from .generation import beam_search, generate
+        num_beams = int(kwargs.get("num_beams", 1))
+        if num_beams > 1:                                      # the reference's default VQA eval: num_beams=5 (vqa_inference.py:111-119)
+            if do_sample:
+                raise NotImplementedError("beam sampling (num_beams > 1 with do_sample=True) is not built")
+            if attention_mask is not None and not bool(attention_mask.all()):
+                raise NotImplementedError("padded prompt batches are not supported by the kv-cache path")
+            return beam_search(self, input_ids, images=images, num_beams=num_beams, max_new_tokens=max_new_tokens,
+                               length_penalty=kwargs.get("length_penalty", 1.0), early_stopping=kwargs.get("early_stopping", False),
+                               eos_token_id=eos_token_id, pad_token_id=pad_token_id, stopping_criteria=stopping_criteria,
+                               length_normalization=kwargs.get("length_normalization", "generated"))
         return generate(self, input_ids, images=images, max_new_tokens=max_new_tokens, do_sample=do_sample, temperature=temperature,
                         top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty, eos_token_id=eos_token_id,
                         pad_token_id=pad_token_id, generator=generator, attention_mask=attention_mask,

@@ -103,3 +103,86 @@ def test_generate_stopping_criteria():
     out = generate(_Scripted(torch.tensor([[5, 6, 7, 8], [6, 9, 9, 6]])), torch.tensor([[1], [1]]), max_new_tokens=4,
                    stopping_criteria=[per_row])
     assert out.tolist() == [[1, 5, 6], [1, 6, 0]]
+
+
+# ------------------------------------------------------------------------------------------------ beam search pinned to transformers
+class _HFCache:
+    """KVCache protocol (in-place advance, `repeat_interleave`, `reorder`) over a transformers DynamicCache."""
+
+    def __init__(self, cache):
+        self.cache = cache
+
+    def repeat_interleave(self, k):
+        self.cache.batch_repeat_interleave(k)
+
+    def reorder(self, idx):
+        self.cache.reorder_cache(idx)
+
+
+class _HFAdapter:
+    """A transformers causal LM behind the call signature `generation.generate` / `beam_search` use."""
+
+    def __init__(self, hf):
+        self.hf = hf
+
+    def __call__(self, input_ids=None, images=None, past_key_values=None, use_cache=None, last_token_logits_only=None):
+        from types import SimpleNamespace
+        pkv = past_key_values.cache if past_key_values is not None else None
+        out = self.hf(input_ids=input_ids, past_key_values=pkv, use_cache=True)
+        cache = past_key_values if past_key_values is not None else _HFCache(out.past_key_values)
+        return SimpleNamespace(logits=out.logits[:, -1:].float(), past_key_values=cache)
+
+
+def _tiny_llama(seed, vocab=40):
+    from transformers import LlamaConfig, LlamaForCausalLM
+    torch.manual_seed(seed)
+    cfg = LlamaConfig(vocab_size=vocab, hidden_size=32, intermediate_size=64, num_hidden_layers=2, num_attention_heads=2,
+                      max_position_embeddings=64, eos_token_id=2, bos_token_id=1, pad_token_id=0)
+    m = LlamaForCausalLM(cfg).eval()
+    with torch.no_grad():
+        m.lm_head.weight.mul_(8.0)            # peaked next-token distributions: hypotheses of different lengths and EOS picks occur
+    return m
+
+
+@pytest.mark.parametrize("seed", range(6))
+@pytest.mark.parametrize("num_beams,length_penalty,early", [(3, 1.0, False), (5, 1.0, False), (4, 0.6, False), (3, 1.0, True)])
+def test_beam_search_equals_transformers_generate(seed, num_beams, length_penalty, early):
+    from dreamllm_b200.generation import beam_search
+    hf = _tiny_llama(seed)
+    g = torch.Generator().manual_seed(100 + seed)
+    ids = torch.cat([torch.ones(2, 1, dtype=torch.long), torch.randint(3, 40, (2, 4), generator=g)], 1)
+    with torch.no_grad():
+        want = hf.generate(ids, num_beams=num_beams, do_sample=False, max_new_tokens=10, length_penalty=length_penalty, early_stopping=early,
+                           eos_token_id=2, pad_token_id=39, return_dict_in_generate=True, output_scores=True)
+    # (pad id != 0: the installed transformers fills with `pad_token_id or eos_token_id`, i.e. treats pad id 0 as unset)
+    got, scores = beam_search(_HFAdapter(hf), ids, num_beams=num_beams, max_new_tokens=10, length_penalty=length_penalty,
+                              early_stopping=early, eos_token_id=2, pad_token_id=39, return_scores=True)
+    assert got.tolist() == want.sequences.tolist()
+    torch.testing.assert_close(scores, want.sequences_scores, rtol=1e-4, atol=1e-4)
+
+
+def test_beam_search_modes_and_kvcache_beam_ops():
+    from dreamllm_b200.generation import beam_search
+    from dreamllm_b200.modeling_dreamllm import DreamLLMForCausalMLM, KVCache
+    hf = _tiny_llama(1)
+    ids = torch.tensor([[1, 7, 9]])
+    a = beam_search(_HFAdapter(hf), ids, num_beams=1, max_new_tokens=6, eos_token_id=2, pad_token_id=0)
+    with torch.no_grad():
+        greedy = hf.generate(ids, do_sample=False, max_new_tokens=6, eos_token_id=2, pad_token_id=0)
+    assert a.tolist() == greedy.tolist()                                   # one beam = greedy
+    t = beam_search(_HFAdapter(hf), ids, num_beams=3, max_new_tokens=6, eos_token_id=2, pad_token_id=0, length_normalization="total")
+    assert t.shape[0] == 1 and t[0, :3].tolist() == [1, 7, 9]
+    with pytest.raises(ValueError):
+        beam_search(_HFAdapter(hf), ids, length_normalization="words")
+    # KVCache beam ops (CPU tensors): repeat per beam, then re-order only the valid prefix
+    c = KVCache(2, 2, 8, 1, 4, "cpu", dtype=torch.float32)
+    c.len = 3
+    for li in range(2):
+        c.k[li][:, :3] = torch.arange(2.)[:, None, None, None] + 1        # row b holds b + 1
+        c.v[li][:, :3] = -(torch.arange(2.)[:, None, None, None] + 1)
+    c.repeat_interleave(3)
+    assert c.k[0].shape[0] == 6 and c.k[0][:, 0, 0, 0].tolist() == [1, 1, 1, 2, 2, 2]
+    c.reorder(torch.tensor([3, 3, 0, 5, 4, 1]))
+    assert c.k[1][:, 2, 0, 0].tolist() == [2, 2, 1, 2, 2, 1] and c.v[1][:, 0, 0, 0].tolist() == [-2, -2, -1, -2, -2, -1]
+    assert float(c.k[0][:, 3:].abs().sum()) == 0                           # rows past the valid length stay zero
+    assert DreamLLMForCausalMLM._reorder_cache(c, torch.arange(6)) is c

@@ -177,7 +177,7 @@ def test_generation_helpers():
     assert out["input_ids"].shape == (2, 1) and torch.equal(out["input_ids"], ids[:, 4:]) and out["position_ids"].shape == (2, 1)
     legacy = tuple((torch.zeros(2, 2, 4, 64), torch.zeros(2, 2, 4, 64)) for _ in range(2))
     assert m.prepare_inputs_for_generation(ids, past_key_values=legacy)["input_ids"].shape == (2, 1)
-    cache.k[0][0] += 1.0
+    cache.k[0][0, :cache.len] += 1.0                       # only the valid prefix [:len] is ever written / moved
     beam = torch.tensor([1, 0])
     cache = m._reorder_cache(cache, beam)
     assert float(cache.k[0][1].sum()) > 0 and float(cache.k[0][0].sum()) == 0
