@@ -472,13 +472,20 @@ class _CfgDropFn(torch.autograd.Function):
         return d_enc, d_u, None
 
 
+def numpy_to_pil(images):
+    """[B, H, W, 3] floats in [0, 1] -> list of PIL images (diffusers `VaeImageProcessor.numpy_to_pil`: x255, round, uint8)."""
+    from PIL import Image
+    arr = (images * 255).round().astype("uint8")
+    return [Image.fromarray(a) for a in arr]
+
+
 class StableDiffusionHead(MultimodalHead):
     """Mirror of reference `StableDiffusionHead` (modeling_plugins.py:335-850): same constructor arguments, `projector` /
     `unet` attribute names (state-dict keys `projector.projector.weight`, `unet.*`), `pipeline(...)` signature.
 
     Built: the training `forward` (:493-577: VAE encode -> add_noise -> UNet fwd + dgrad-only backward -> MSE) and the sampler
     (`pipeline`, :672-850) on the native UNet with a CUDA-graph loop, `output_type="latent"`.
-    `output_type` "latent" | "pt" | "np" (VAE decode on the native decoder); PIL conversion is host glue and not provided.
+    `output_type` "latent" | "pt" | "np" | "pil" (VAE decode on the native decoder).
     `diffusion_name_or_path` may be a dict of UNet config overrides for random init (no checkpoints exist in the sandbox);
     a checkpoint directory is loaded through safetensors into the native module (identical key names).
     """
@@ -627,8 +634,8 @@ class StableDiffusionHead(MultimodalHead):
         assert prompt_embeds is not None, "`prompt_embeds` must be provided by LLM."
         if guidance_rescale > 0.0 or callback is not None or (num_images_per_prompt or 1) != 1:
             raise NotImplementedError("guidance_rescale / callback / num_images_per_prompt>1 are not built")
-        if output_type not in ("latent", "pt", "np"):
-            raise NotImplementedError("output_type must be 'latent', 'pt' or 'np' (PIL conversion is host-side glue)")
+        if output_type not in ("latent", "pt", "np", "pil"):
+            raise ValueError(f"output_type must be one of 'latent', 'pt', 'np', 'pil', got {output_type!r}")
         cond = self.projector(prompt_embeds)[-1]
         if guidance_scale > 1.0:
             assert negative_prompt_embeds is not None, "When using classifier free guidance, `negative_prompt_embeds` must be provided by LLM."
@@ -640,4 +647,7 @@ class StableDiffusionHead(MultimodalHead):
             return lat
         image = self.vae_decoder.decode(lat)                                  # vae.decode(latents / scaling_factor), :842
         image = (image / 2 + 0.5).clamp(0, 1)                                 # VaeImageProcessor.postprocess denormalize
-        return image if output_type == "pt" else image.permute(0, 2, 3, 1).cpu().numpy()
+        if output_type == "pt":
+            return image
+        arr = image.permute(0, 2, 3, 1).cpu().numpy()
+        return arr if output_type == "np" else numpy_to_pil(arr)
