@@ -632,8 +632,15 @@ class StableDiffusionHead(MultimodalHead):
         if height % 8 or width % 8:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
         assert prompt_embeds is not None, "`prompt_embeds` must be provided by LLM."
-        if guidance_rescale > 0.0 or callback is not None or (num_images_per_prompt or 1) != 1:
-            raise NotImplementedError("guidance_rescale / callback / num_images_per_prompt>1 are not built")
+        if guidance_rescale > 0.0:
+            raise NotImplementedError("guidance_rescale > 0 (`_rescale_noise_cfg`, :658-669) is not built; every shipped call uses 0.0")
+        n_img = int(num_images_per_prompt or 1)
+        if n_img > 1:                                           # (:760-772) each prompt's embeddings repeated per requested image
+            prompt_embeds = prompt_embeds.repeat_interleave(n_img, dim=0)
+            if negative_prompt_embeds is not None:
+                negative_prompt_embeds = negative_prompt_embeds.repeat_interleave(n_img, dim=0)
+            if latents is not None and latents.shape[0] != prompt_embeds.shape[0]:
+                raise ValueError(f"latents batch {latents.shape[0]} != prompts x num_images_per_prompt = {prompt_embeds.shape[0]}")
         if output_type not in ("latent", "pt", "np", "pil"):
             raise ValueError(f"output_type must be one of 'latent', 'pt', 'np', 'pil', got {output_type!r}")
         cond = self.projector(prompt_embeds)[-1]
@@ -642,7 +649,7 @@ class StableDiffusionHead(MultimodalHead):
             cond = torch.cat([self.projector(negative_prompt_embeds)[-1], cond])
         loop = DenoiseLoop(self.unet, cond, num_inference_steps, guidance_scale, scheduler, latents=latents, height=height, width=width,
                            use_cuda_graph=use_cuda_graph, generator=generator)
-        lat = loop.run()
+        lat = loop.run(callback=callback, callback_steps=callback_steps)
         if output_type == "latent":
             return lat
         image = self.vae_decoder.decode(lat)                                  # vae.decode(latents / scaling_factor), :842

@@ -523,6 +523,7 @@ class DenoiseLoop:
         h, w = height // 8, width // 8
         ts, coef = scheduler_tables(num_inference_steps, scheduler)
         self.timesteps, self.coef = ts.to(dev), coef.to(dev)
+        self.timesteps_host = ts.tolist()
         self.step = torch.zeros(1, device=dev, dtype=torch.int32)
         if latents is None:
             latents = torch.randn((self.B, 4, h, w), generator=generator, device=dev, dtype=torch.float32)
@@ -542,10 +543,16 @@ class DenoiseLoop:
         ops.sampler_step_(self.eps, self.latents, self.coef, self.step, self.guidance, self.use_cfg, self.mode, self.noise)
 
     @torch.no_grad()
-    def run(self):
+    def run(self, callback=None, callback_steps: int = 1):
+        """`callback(i, t, latents)` every `callback_steps` steps, between graph replays (reference :836-839)."""
+        def report(i):
+            if callback is not None and i % callback_steps == 0:
+                callback(i, self.timesteps_host[i], self.latents)
+
         if not self.use_cuda_graph:
-            for _ in range(self.N):
+            for i in range(self.N):
                 self._one_step()
+                report(i)
             return self.latents
         if self.graph is None:
             # warm up on a side stream (allocator + lazy attribute setup), then restore state and capture one step
@@ -562,6 +569,7 @@ class DenoiseLoop:
                 self._one_step()
             self.latents.copy_(lat0)
             self.step.copy_(st0)
-        for _ in range(self.N):
+        for i in range(self.N):
             self.graph.replay()
+            report(i)
         return self.latents
