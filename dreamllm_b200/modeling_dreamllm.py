@@ -461,6 +461,13 @@ class _LMHeadLossFn(torch.autograd.Function):
         return dh, dw, None
 
 
+def average_init_token_embeddings(model, num_added_tokens: int):
+    """omni/utils/tokenizer_utils.py:70-80: newly added token rows of embed_tokens / lm_head start at the mean of the existing rows."""
+    assert num_added_tokens > 0, "`num_added_tokens` should be positive"
+    for emb in (model.get_input_embeddings().weight.data, model.get_output_embeddings().weight.data):
+        emb[-num_added_tokens:] = emb[:-num_added_tokens].mean(dim=0, keepdim=True)
+
+
 @dataclass
 class BaseModelOutputWithPast:
     last_hidden_state: torch.Tensor = None
@@ -765,6 +772,12 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
         """reference :1045-1158: embed_tokens -> dream-query splice -> CLIP features -> image splice -> `_forward`.
         `input_ids_cpu` (the collator's host copy) lets the index maps be built without a device->host sync;
         `splice_plan` lets the caller pass prebuilt maps."""
+        # reference :1059-1064: with `freeze_embed_tokens` + newly added special tokens, only the last `num_added_tokens` rows may
+        # move — the original rows are restored from the backup every forward (projects/dreamllm/train.py:149-155 sets both attributes)
+        backup = getattr(self, "embed_tokens_backup", None)
+        if backup is not None:
+            with torch.no_grad():
+                self.embed_tokens.weight[: -self.num_added_tokens] = backup[: -self.num_added_tokens].data
         need_splice = (images is not None) or (images_dm is not None)
         if past_key_values is not None and images is not None and input_ids is not None and \
                 not bool((input_ids == getattr(self, "image_start_id", -1)).any()):

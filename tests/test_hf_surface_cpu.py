@@ -184,3 +184,16 @@ def test_generation_helpers():
     re = m._reorder_cache(tuple((torch.arange(2.).view(2, 1, 1, 1), torch.arange(2.).view(2, 1, 1, 1)) for _ in range(2)), beam)
     assert re[0][0].flatten().tolist() == [1.0, 0.0]
     assert m.fsdp_ignored_modules() == []
+
+
+def test_average_init_of_added_token_rows():
+    from dreamllm_b200.modeling_dreamllm import average_init_token_embeddings
+    m = _tiny_model(with_plugin=False)
+    e0, h0 = m.get_input_embeddings().weight.detach().clone(), m.lm_head.weight.detach().clone()
+    average_init_token_embeddings(m, 8)
+    e, h = m.get_input_embeddings().weight, m.lm_head.weight
+    assert torch.equal(e[:-8], e0[:-8]) and torch.equal(h[:-8], h0[:-8])
+    torch.testing.assert_close(e[-8:], e0[:-8].mean(0, keepdim=True).expand(8, -1))
+    torch.testing.assert_close(h[-3], h0[:-8].mean(0))
+    with pytest.raises(AssertionError):
+        average_init_token_embeddings(m, 0)
