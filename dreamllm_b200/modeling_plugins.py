@@ -632,8 +632,6 @@ class StableDiffusionHead(MultimodalHead):
         if height % 8 or width % 8:
             raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
         assert prompt_embeds is not None, "`prompt_embeds` must be provided by LLM."
-        if guidance_rescale > 0.0:
-            raise NotImplementedError("guidance_rescale > 0 (`_rescale_noise_cfg`, :658-669) is not built; every shipped call uses 0.0")
         n_img = int(num_images_per_prompt or 1)
         if n_img > 1:                                           # (:760-772) each prompt's embeddings repeated per requested image
             prompt_embeds = prompt_embeds.repeat_interleave(n_img, dim=0)
@@ -648,7 +646,7 @@ class StableDiffusionHead(MultimodalHead):
             assert negative_prompt_embeds is not None, "When using classifier free guidance, `negative_prompt_embeds` must be provided by LLM."
             cond = torch.cat([self.projector(negative_prompt_embeds)[-1], cond])
         loop = DenoiseLoop(self.unet, cond, num_inference_steps, guidance_scale, scheduler, latents=latents, height=height, width=width,
-                           use_cuda_graph=use_cuda_graph, generator=generator)
+                           use_cuda_graph=use_cuda_graph, generator=generator, guidance_rescale=guidance_rescale)
         lat = loop.run(callback=callback, callback_steps=callback_steps)
         if output_type == "latent":
             return lat

@@ -505,17 +505,28 @@ def scheduler_tables(num_inference_steps, kind="ddim", num_train=1000, beta_star
     return ts.to(torch.int32), coef.to(torch.float32)
 
 
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale: float):
+    """`StableDiffusionHead._rescale_noise_cfg` (modeling_plugins.py:658-669; "Common Diffusion Noise Schedules and Sample Steps are
+    Flawed" §3.4): match the per-sample std of the guided prediction to the text-conditioned one, then blend by `guidance_rescale`.
+    [B, 4, h, w] fp32 — a few hundred KB per step, plain torch ops inside the captured step."""
+    dims = list(range(1, noise_pred_text.ndim))
+    std_text = noise_pred_text.std(dim=dims, keepdim=True)
+    std_cfg = noise_cfg.std(dim=dims, keepdim=True)
+    return guidance_rescale * (noise_cfg * (std_text / std_cfg)) + (1 - guidance_rescale) * noise_cfg
+
+
 class DenoiseLoop:
     """N-step sampler: one CUDA graph of {time embedding -> UNet -> fused CFG + scheduler update}, replayed N times."""
 
     def __init__(self, unet: UNet2DConditionModel, cond, num_inference_steps=50, guidance_scale=7.5, scheduler="ddim",
-                 latents=None, noise=None, height=512, width=512, use_cuda_graph=True, generator=None):
+                 latents=None, noise=None, height=512, width=512, use_cuda_graph=True, generator=None, guidance_rescale: float = 0.0):
         """cond: [B, Q, ctx] projected prompt embeddings, or [2B, Q, ctx] = cat([negative, positive]) when guidance_scale > 1
         (reference order, modeling_plugins.py:774-784)."""
         self.unet = unet
         dev = cond.device
         self.use_cfg = guidance_scale > 1.0
         self.guidance = float(guidance_scale)
+        self.guidance_rescale = float(guidance_rescale)
         self.nb = cond.shape[0]
         self.B = self.nb // 2 if self.use_cfg else self.nb
         self.N = num_inference_steps
@@ -540,6 +551,11 @@ class DenoiseLoop:
     def _one_step(self):
         temb_sin = ops.timestep_embedding(self.timesteps, self.step, self.nb, self.unet.cfg["block_out_channels"][0])
         self.unet.forward_nhwc(self.latents, temb_sin, self.cross_kv, self.nb, eps_out=self.eps)
+        if self.use_cfg and self.guidance_rescale > 0.0:          # (:826-831) guided prediction rescaled before the scheduler update
+            eu, ec = self.eps[: self.B], self.eps[self.B:]
+            self.eps[: self.B].copy_(rescale_noise_cfg(eu + self.guidance * (ec - eu), ec, self.guidance_rescale))
+            ops.sampler_step_(self.eps, self.latents, self.coef, self.step, 1.0, False, self.mode, self.noise)
+            return
         ops.sampler_step_(self.eps, self.latents, self.coef, self.step, self.guidance, self.use_cfg, self.mode, self.noise)
 
     @torch.no_grad()
