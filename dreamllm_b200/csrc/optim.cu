@@ -36,6 +36,12 @@ __device__ __forceinline__ BVec8 bpack8(const float* f) {
   for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return p;
 }
+// 128-bit accesses spelled as uint4: a struct copy of BVec8 compiles to four 32-bit LDG/STG (checked in SASS)
+__device__ __forceinline__ BVec8 ld8(const BVec8* p) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  return *reinterpret_cast<const BVec8*>(&u);
+}
+__device__ __forceinline__ void st8(BVec8* p, const BVec8& v) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v); }
 __device__ __forceinline__ float rbf(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 struct AdamWArgs {
@@ -81,11 +87,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const BVec8* __restrict__ gr
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     float g[8], p[8], m[8], v[8];
-    bunpack8(grad[i], g);
+    bunpack8(ld8(grad + i), g);
     if constexpr (kBf16State) {
-      bunpack8(param[i], p);
-      bunpack8(reinterpret_cast<const BVec8*>(mom)[i], m);
-      bunpack8(reinterpret_cast<const BVec8*>(var)[i], v);
+      bunpack8(ld8(param + i), p);
+      bunpack8(ld8(reinterpret_cast<const BVec8*>(mom) + i), m);
+      bunpack8(ld8(reinterpret_cast<const BVec8*>(var) + i), v);
     } else {
       const float4* w4 = reinterpret_cast<const float4*>(master) + 2 * i;
       const float4* m4 = reinterpret_cast<const float4*>(mom) + 2 * i;
@@ -104,8 +110,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const BVec8* __restrict__ gr
       adamw_elem<kBf16State>(gj, p[j], m[j], v[j], a);
     }
     if constexpr (kBf16State) {
-      reinterpret_cast<BVec8*>(mom)[i] = bpack8(m);
-      reinterpret_cast<BVec8*>(var)[i] = bpack8(v);
+      st8(reinterpret_cast<BVec8*>(mom) + i, bpack8(m));
+      st8(reinterpret_cast<BVec8*>(var) + i, bpack8(v));
     } else {
       float4* w4 = reinterpret_cast<float4*>(master) + 2 * i;
       float4* m4 = reinterpret_cast<float4*>(mom) + 2 * i;
@@ -117,7 +123,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const BVec8* __restrict__ gr
       v4[0] = *reinterpret_cast<float4*>(v);
       v4[1] = *reinterpret_cast<float4*>(v + 4);
     }
-    param[i] = bpack8(p);
+    st8(param + i, bpack8(p));
   }
 }
 
@@ -129,7 +135,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const BVec8* __restr
   const long stride = static_cast<long>(gridDim.x) * blockDim.x;
   for (long i = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x; i < nvec; i += stride) {
     float f[8];
-    bunpack8(x[i], f);
+    bunpack8(ld8(x + i), f);
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc = fmaf(f[j], f[j], acc);
   }

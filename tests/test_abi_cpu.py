@@ -73,3 +73,26 @@ def test_host_only_entry_points_answer_without_a_gpu():
     assert L.dllm_groupnorm_workspace_bytes(16, 64 * 64, 32) > 0
     assert L.dllm_sumsq_workspace_bytes() == 148 * 4 * 4
     assert L.dllm_get_reserved_sms() == 0
+
+
+def test_optimizer_kernels_use_128_bit_accesses():
+    """The HBM-bound optimizer-shard kernels stream through 128-bit vector loads / stores (LDG.E.128 / STG.E.128), no 32-bit bulk traffic."""
+    import subprocess
+    from dreamllm_b200 import _lib
+    _lib.build()
+    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "adamw_kernel", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if "adamw_kernel" not in sass:                       # older cuobjdump: -fun needs the mangled name; fall back to the whole dump
+        sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    funcs = re.split(r"Function : ", sass)
+    seen = 0
+    for f in funcs:
+        name = f.split("\n", 1)[0]
+        if "adamw_kernel" in name or "sumsq_partial_kernel" in name:
+            seen += 1
+            wide = len(re.findall(r"LDG\.E\.128", f))
+            narrow = len(re.findall(r"LDG\.E(?:\.CONSTANT)?\s", f))          # 32-bit loads: only the scalar sum-of-squares read is allowed
+            assert wide >= (1 if "sumsq" in name else 4), (name, wide)
+            assert narrow <= 1, (name, narrow)
+            if "adamw" in name:
+                assert len(re.findall(r"STG\.E\.128", f)) >= 3 and not re.findall(r"STG\.E\s", f), name
+    assert seen >= 3
