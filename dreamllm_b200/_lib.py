@@ -31,13 +31,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _needs_build():
         return LIB_PATH
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    # A/B builds (with DLLM_LIB_PATH pointing at a second .so): e.g. DLLM_NVCC_EXTRA="-DDLLM_VEC128 -DDLLM_GN_GROUP2" 
+    extra = os.environ.get("DLLM_NVCC_EXTRA", "").split()
     objs = []
     procs = []
     os.makedirs(os.path.join(_HERE, "build"), exist_ok=True)
     for src in SOURCES:
         obj = os.path.join(_HERE, "build", src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(_CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(_CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -1,20 +1,40 @@
 // HBM-bound kernels of the DreamLLM decoder path (sm_100a): RMSNorm fwd/bwd (+fused residual add),
 // RoPE (in place on the fused qkv buffer), SwiGLU fwd/bwd, shifted masked cross-entropy (fwd + in-place
 // dlogits), embedding gather / sorted segment scatter, bf16 add.
-// All use 128-bit vector accesses, fp32 math, warp-shuffle reductions; rounding points follow the
+// All move 8-element (16-byte) vectors per thread (128-bit LDG/STG with -DDLLM_VEC128, see the Vec8 note below), fp32 math, warp-shuffle reductions; rounding points follow the
 // reference's bf16 eager path (cited per kernel) so bf16-vs-bf16 parity holds to the last place where cheap.
 #include "common.cuh"
 #include "gemm_sm100.h"
 
 namespace dllm {
 
+// DLLM_VEC128 (build flag, OFF by default until measured on hardware — DESIGN.md section 8): with the bfloat162[4] layout nvcc compiles
+// every struct copy into four 32-bit LDG/STG (cuobjdump -sass); a single uint4 member makes the same copies LDG.E.128 / STG.E.128.
+// Bit-identical results either way; the wide form additionally requires 16-byte aligned row starts (true for every caller: row widths and
+// row strides are multiples of 8 elements).
+#ifdef DLLM_VEC128
+struct alignas(16) Vec8 {
+  uint4 u;
+  __device__ __forceinline__ __nv_bfloat162 get(int i) const {
+    const uint32_t w = (i == 0) ? u.x : (i == 1) ? u.y : (i == 2) ? u.z : u.w;
+    return *reinterpret_cast<const __nv_bfloat162*>(&w);
+  }
+  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&h);
+    if (i == 0) u.x = w; else if (i == 1) u.y = w; else if (i == 2) u.z = w; else u.w = w;
+  }
+};
+#else
 struct alignas(16) Vec8 {
   __nv_bfloat162 v[4];
+  __device__ __forceinline__ __nv_bfloat162 get(int i) const { return v[i]; }
+  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) { v[i] = h; }
 };
+#endif
 __device__ __forceinline__ void unpack8(const Vec8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p.v[i]);
+    float2 t = __bfloat1622float2(p.get(i));
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -22,7 +42,7 @@ __device__ __forceinline__ void unpack8(const Vec8& p, float* f) {
 __device__ __forceinline__ Vec8 pack8(const float* f) {
   Vec8 p;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) p.set(i, __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]));
   return p;
 }
 __device__ __forceinline__ float bf16r(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -380,7 +400,7 @@ __global__ void __launch_bounds__(kCeThreads) ce_fwd_bwd_kernel(bf16* __restrict
     if (write_grad) {
       Vec8 z;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) z.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+      for (int i = 0; i < 4; ++i) z.set(i, __floats2bfloat162_rn(0.f, 0.f));
       for (int v = threadIdx.x; v < nvec; v += kCeThreads) reinterpret_cast<Vec8*>(lr)[v] = z;
     }
     return;
@@ -723,7 +743,7 @@ __global__ void zero_rows_kernel(bf16* __restrict__ dst, const int* __restrict__
   if (gid >= static_cast<long>(R) * nvec) return;
   Vec8 z;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) z.v[i] = __floats2bfloat162_rn(0.f, 0.f);
+  for (int i = 0; i < 4; ++i) z.set(i, __floats2bfloat162_rn(0.f, 0.f));
   reinterpret_cast<Vec8*>(dst + static_cast<size_t>(idx[gid / nvec]) * H)[gid % nvec] = z;
 }
 int copy_rows(void* dst, const int* dst_idx, const void* src, const int* src_idx, int R, int H, int mode, cudaStream_t s) {

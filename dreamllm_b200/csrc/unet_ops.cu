@@ -8,13 +8,33 @@
 
 namespace dllm {
 
+// DLLM_VEC128 (build flag, OFF by default until measured on hardware — DESIGN.md section 8): with the bfloat162[4] layout nvcc compiles
+// every struct copy into four 32-bit LDG/STG (cuobjdump -sass); a single uint4 member makes the same copies LDG.E.128 / STG.E.128.
+// Bit-identical results either way; the wide form additionally requires 16-byte aligned row starts (true for every caller: row widths and
+// row strides are multiples of 8 elements).
+#ifdef DLLM_VEC128
+struct alignas(16) V8 {
+  uint4 u;
+  __device__ __forceinline__ __nv_bfloat162 get(int i) const {
+    const uint32_t w = (i == 0) ? u.x : (i == 1) ? u.y : (i == 2) ? u.z : u.w;
+    return *reinterpret_cast<const __nv_bfloat162*>(&w);
+  }
+  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) {
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(&h);
+    if (i == 0) u.x = w; else if (i == 1) u.y = w; else if (i == 2) u.z = w; else u.w = w;
+  }
+};
+#else
 struct alignas(16) V8 {
   __nv_bfloat162 v[4];
+  __device__ __forceinline__ __nv_bfloat162 get(int i) const { return v[i]; }
+  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) { v[i] = h; }
 };
+#endif
 __device__ __forceinline__ void up8(const V8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const float2 t = __bfloat1622float2(p.v[i]);
+    const float2 t = __bfloat1622float2(p.get(i));
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -22,7 +42,7 @@ __device__ __forceinline__ void up8(const V8& p, float* f) {
 __device__ __forceinline__ V8 pk8(const float* f) {
   V8 p;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  for (int i = 0; i < 4; ++i) p.set(i, __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]));
   return p;
 }
 __device__ __forceinline__ float r16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
@@ -105,11 +125,33 @@ __global__ void gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restri
   up8(reinterpret_cast<const V8*>(x)[gid], f);
   up8(reinterpret_cast<const V8*>(w)[v], wf);
   up8(reinterpret_cast<const V8*>(b)[v], bf);
+#ifdef DLLM_GN_GROUP2
+  // DLLM_GN_GROUP2 (build flag, OFF until measured — DESIGN.md section 8): with >= 8 channels per group the 8 channels of a vector touch at
+  // most two groups, so one integer division and two (mean, rstd) pairs replace eight divisions and sixteen scalar loads per thread.
+  const bool two = cpg >= 8;
+  const int g0 = (v * 8) / cpg;
+  const int split = two ? (g0 + 1) * cpg - v * 8 : 0;                       // channels [0, split) of this vector belong to group g0
+  const size_t s0 = (static_cast<size_t>(n) * G + g0) * 2, s1 = (static_cast<size_t>(n) * G + min(g0 + 1, G - 1)) * 2;
+  const float mean0 = two ? __ldg(stats + s0) : 0.f, rstd0 = two ? __ldg(stats + s0 + 1) : 0.f;
+  const float mean1 = two ? __ldg(stats + s1) : 0.f, rstd1 = two ? __ldg(stats + s1 + 1) : 0.f;
+#endif
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
+#ifdef DLLM_GN_GROUP2
+    float mean, rstd;
+    if (two) {
+      mean = j < split ? mean0 : mean1;
+      rstd = j < split ? rstd0 : rstd1;
+    } else {
+      const int g = (v * 8 + j) / cpg;
+      mean = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2);
+      rstd = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2 + 1);
+    }
+#else
     const int g = (v * 8 + j) / cpg;
     const float mean = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2);
     const float rstd = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2 + 1);
+#endif
     float o = r16((f[j] - mean) * rstd * wf[j] + bf[j]);
     if (silu) o = o / (1.f + expf(-o));
     f[j] = o;
@@ -474,12 +516,35 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
   up8(reinterpret_cast<const V8*>(w)[v], wf);
   up8(reinterpret_cast<const V8*>(b)[v], bf);
   if (dres) up8(reinterpret_cast<const V8*>(dres)[gid], rs);
+#ifdef DLLM_GN_GROUP2
+  const bool two = cpg >= 8;                                                // see gn_apply_kernel
+  const int g0 = (v * 8) / cpg;
+  const int split = two ? (g0 + 1) * cpg - v * 8 : 0;
+  const size_t s0 = (static_cast<size_t>(n) * G + g0) * 2, s1 = (static_cast<size_t>(n) * G + min(g0 + 1, G - 1)) * 2;
+  float st0[4] = {0.f, 0.f, 0.f, 0.f}, st1[4] = {0.f, 0.f, 0.f, 0.f};         // {mean, rstd, m1, m2} of the two groups
+  if (two) {
+    st0[0] = __ldg(stats + s0); st0[1] = __ldg(stats + s0 + 1); st0[2] = __ldg(sums + s0); st0[3] = __ldg(sums + s0 + 1);
+    st1[0] = __ldg(stats + s1); st1[1] = __ldg(stats + s1 + 1); st1[2] = __ldg(sums + s1); st1[3] = __ldg(sums + s1 + 1);
+  }
+#endif
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
+#ifdef DLLM_GN_GROUP2
+    float mean, rstd, m1, m2;
+    if (two) {
+      const bool first = j < split;
+      mean = first ? st0[0] : st1[0]; rstd = first ? st0[1] : st1[1]; m1 = first ? st0[2] : st1[2]; m2 = first ? st0[3] : st1[3];
+    } else {
+      const int g = (v * 8 + j) / cpg;
+      const size_t si = (static_cast<size_t>(n) * G + g) * 2;
+      mean = __ldg(stats + si); rstd = __ldg(stats + si + 1); m1 = __ldg(sums + si); m2 = __ldg(sums + si + 1);
+    }
+#else
     const int g = (v * 8 + j) / cpg;
     const size_t si = (static_cast<size_t>(n) * G + g) * 2;
     const float mean = __ldg(stats + si), rstd = __ldg(stats + si + 1);
     const float m1 = __ldg(sums + si), m2 = __ldg(sums + si + 1);
+#endif
     const float xh = (f[j] - mean) * rstd;
     float gg = d[j];
     if (silu) {

@@ -96,3 +96,28 @@ def test_optimizer_kernels_use_128_bit_accesses():
             if "adamw" in name:
                 assert len(re.findall(r"STG\.E\.128", f)) >= 3 and not re.findall(r"STG\.E\s", f), name
     assert seen >= 3
+
+
+def test_vec128_build_flag_widens_the_hbm_kernels(tmp_path):
+    """Finding from the SASS: nvcc splits every copy of the `bfloat162[4]` vector struct into four 32-bit LDG / STG, so the
+    HBM-bound decoder / UNet kernels issue 4x the memory instructions they need.  `-DDLLM_VEC128` (one uint4 member) turns them into
+    LDG.E.128 / STG.E.128 with bit-identical results; it stays OFF in the shipped build until it has been timed on hardware."""
+    import subprocess
+    from dreamllm_b200 import _lib
+    csrc = os.path.join(os.path.dirname(_lib.__file__), "csrc")
+    obj = str(tmp_path / "elementwise.o")
+    r = subprocess.run(["/usr/local/cuda/bin/nvcc", *_lib.NVCC_FLAGS, "-DDLLM_VEC128", "-c", os.path.join(csrc, "elementwise.cu"), "-o", obj],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+
+    def widths(path, kernel):
+        sass = subprocess.run(["cuobjdump", "-sass", path], capture_output=True, text=True).stdout
+        body = next(f for f in re.split(r"Function : ", sass) if f.split("\n", 1)[0].find(kernel) >= 0)
+        return len(re.findall(r"(?:LDG|STG)\.E\.128", body)), len(re.findall(r"(?:LDG|STG)\.E(?:\.CONSTANT)?\s", body))
+    shipped = os.path.join(os.path.dirname(_lib.__file__), "build", "elementwise.o")
+    for kernel in ("rmsnorm_fwd_kernel", "rope_kernelILi128", "swiglu_fwd_kernel", "rmsnorm_bwd_dx_kernel"):
+        wide, narrow = widths(obj, kernel)
+        assert wide >= 3 and narrow <= 2, (kernel, wide, narrow)
+        if os.path.isfile(shipped):
+            wide0, narrow0 = widths(shipped, kernel)
+            assert wide0 == 0 and narrow0 >= 8, (kernel, wide0, narrow0)          # today's build: 32-bit accesses only
