@@ -35,9 +35,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     extra = os.environ.get("DLLM_NVCC_EXTRA", "").split()
     objs = []
     procs = []
-    os.makedirs(os.path.join(_HERE, "build"), exist_ok=True)
+    objdir = os.path.join(_HERE, "build") if LIB_PATH == os.path.join(_HERE, "libdreamllm_sm100.so") else LIB_PATH + ".objs"
+    os.makedirs(objdir, exist_ok=True)          # A/B builds keep their objects next to their own .so
     for src in SOURCES:
-        obj = os.path.join(_HERE, "build", src.replace(".cu", ".o"))
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
         cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(_CSRC, src), "-o", obj]
         if verbose:
