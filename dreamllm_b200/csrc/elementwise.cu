@@ -212,6 +212,7 @@ __global__ void colsum_partials_kernel(const float* __restrict__ partial, bf16* 
 
 int rmsnorm_fwd(const void* x, const void* add, const void* w, void* x_out, void* y, float* rstd, int T, int H,
                 float eps, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(x, add, w, x_out, y);
   if (H % 8 || H > kNormThreads * kNormMaxV * 8 || T <= 0) return DLLM_ERR_SHAPE;
   rmsnorm_fwd_kernel<<<T, kNormThreads, 0, s>>>((const bf16*)x, (const bf16*)add, (const bf16*)w, (bf16*)x_out, (bf16*)y,
                                                 rstd, H, eps);
@@ -222,6 +223,7 @@ size_t rmsnorm_bwd_workspace(int T, int H) { return static_cast<size_t>(kDwSplit
 
 int rmsnorm_bwd(const void* dy, const void* x, const void* w, const float* rstd, const void* dres, void* dx, void* dw,
                 int dw_accumulate, void* workspace, size_t workspace_bytes, int T, int H, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dy, x, w, dres, dx);
   if (H % 8 || H > kNormThreads * kNormMaxV * 8 || T <= 0) return DLLM_ERR_SHAPE;
   if (dw && workspace_bytes < rmsnorm_bwd_workspace(T, H)) return DLLM_ERR_SHAPE;
   rmsnorm_bwd_dx_kernel<<<T, kNormThreads, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w, rstd, (const bf16*)dres,
@@ -277,6 +279,7 @@ __global__ void rope_kernel(bf16* __restrict__ buf, const bf16* __restrict__ cos
 
 int rope_inplace(void* buf, const void* cos_t, const void* sin_t, const int* pos, long ld, int T, int heads_total,
                  int head_dim, int mode, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(buf, cos_t, sin_t);
   if (T <= 0 || heads_total <= 0 || (ld % 8)) return DLLM_ERR_SHAPE;
   const int vph = head_dim / 16;
   const long total = static_cast<long>(T) * heads_total * vph;
@@ -336,12 +339,14 @@ __global__ void swiglu_bwd_kernel(const bf16* __restrict__ dact, const bf16* __r
 }
 
 int swiglu_fwd(const void* gu, void* act, long ld_gu, int T, int I, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(gu, act);
   if (I % 8 || ld_gu % 8 || T <= 0) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(T) * (I / 8);
   swiglu_fwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)gu, (bf16*)act, ld_gu, T, I);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int swiglu_bwd(const void* dact, const void* gu, void* dgu, long ld_gu, int T, int I, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dact, gu, dgu);
   if (I % 8 || ld_gu % 8 || T <= 0) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(T) * (I / 8);
   swiglu_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)dact, (const bf16*)gu, (bf16*)dgu,
@@ -361,6 +366,7 @@ __global__ void add_kernel(const bf16* __restrict__ a, const bf16* __restrict__ 
   reinterpret_cast<Vec8*>(o)[i] = pack8(x);
 }
 int add_bf16(const void* a, const void* b, void* o, long n, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(a, b, o);
   if (n % 8 || n <= 0) return DLLM_ERR_SHAPE;
   const long nvec = n / 8;
   add_kernel<<<static_cast<unsigned>((nvec + 255) / 256), 256, 0, s>>>((const bf16*)a, (const bf16*)b, (bf16*)o, nvec);
@@ -463,6 +469,7 @@ __global__ void ce_reduce_kernel(const float* __restrict__ row_loss, int T, cons
 // workspace: float[T + 2] (row losses, then {1/n_valid, n_valid})
 int cross_entropy(void* logits, const long long* labels, float* loss, float dloss, void* workspace, long ld, int T,
                   int V, int write_grad, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(logits);
   if (V % 8 || ld % 8 || T <= 0) return DLLM_ERR_SHAPE;
   float* row_loss = static_cast<float*>(workspace);
   float* inv_count = row_loss + T;
@@ -520,6 +527,7 @@ int embedding_fwd(const long long* ids, const void* W, void* out, int T, int H, 
 }
 int embedding_bwd(const long long* sorted_ids, const long long* order, const void* dy, void* dW, int T, int H,
                   int accumulate, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dy, dW);
   if (H % 8 || T <= 0) return DLLM_ERR_SHAPE;
   embedding_bwd_kernel<<<T, 128, 0, s>>>(sorted_ids, order, (const bf16*)dy, (bf16*)dW, T, H, accumulate);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
@@ -622,6 +630,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_warp_kernel(const bf16* __r
 }
 
 int layernorm_fwd(const void* x, const void* w, const void* b, void* y, int T, int H, float eps, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(x, w, b, y);
   if (H % 8 || H > kNormThreads * kNormMaxV * 8 || T <= 0) return DLLM_ERR_SHAPE;
   const int nvec = H / 8;
   if (nvec <= 32 * 6) {
@@ -686,6 +695,7 @@ int clip_patchify(const void* img, void* out, int N, int R, int patch, int Kpad,
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int clip_assemble(const void* patches, const void* cls, const void* pos, void* out, int N, int P, int C, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(patches, cls, pos, out);
   if (N <= 0 || P <= 0 || C % 8) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(N) * (P + 1) * (C / 8);
   clip_assemble_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)patches, (const bf16*)cls,
@@ -747,6 +757,7 @@ __global__ void zero_rows_kernel(bf16* __restrict__ dst, const int* __restrict__
   reinterpret_cast<Vec8*>(dst + static_cast<size_t>(idx[gid / nvec]) * H)[gid % nvec] = z;
 }
 int copy_rows(void* dst, const int* dst_idx, const void* src, const int* src_idx, int R, int H, int mode, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dst, src);
   if (H % 8 || R < 0) return DLLM_ERR_SHAPE;
   if (R == 0) return 0;
   const long total = static_cast<long>(R) * (H / 8);
@@ -754,11 +765,13 @@ int copy_rows(void* dst, const int* dst_idx, const void* src, const int* src_idx
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int segment_sum_rows(void* dst, const void* src, const int* seg, const int* rows, int Q, int H, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dst, src);
   if (H % 8 || Q <= 0) return DLLM_ERR_SHAPE;
   segment_sum_rows_kernel<<<Q, 128, 0, s>>>((bf16*)dst, (const bf16*)src, seg, rows, H);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int zero_rows(void* dst, const int* idx, int R, int H, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dst);
   if (H % 8 || R < 0) return DLLM_ERR_SHAPE;
   if (R == 0) return 0;
   const long total = static_cast<long>(R) * (H / 8);

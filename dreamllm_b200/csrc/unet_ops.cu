@@ -173,6 +173,7 @@ size_t groupnorm_workspace(int N, int HW, int G) {
 }
 int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW, int C,
                    int G, float eps, int silu, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(x, w, b, y);
   if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
   if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
   const int rows = gn_rows(HW);
@@ -203,6 +204,7 @@ __global__ void geglu_kernel(const bf16* __restrict__ in, bf16* __restrict__ out
   *reinterpret_cast<V8*>(out + t * I + v * 8) = pk8(a);
 }
 int geglu(const void* in, void* out, int T, int I, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(in, out);
   if (I % 8 || T <= 0) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(T) * (I / 8);
   geglu_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)in, (bf16*)out, T, I);
@@ -562,6 +564,7 @@ __global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
 // stats: [N, G, 2] {mean, rstd} from the forward (groupnorm_stats); workspace as in the forward
 int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void* b, const float* stats, const void* dres, void* dx,
                        void* workspace, size_t ws_bytes, int N, int HW, int C, int G, int silu, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dy, x, w, b, dres, dx);
   if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
   if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
   const int rows = gn_rows(HW);
@@ -579,6 +582,7 @@ int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void*
 }
 // forward statistics only ([N, G, 2]) — kept by the training path for the backward
 int groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(x);
   if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
   if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
   const int rows = gn_rows(HW);
@@ -590,6 +594,7 @@ int groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_byte
 }
 int groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
                     cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(x, w, b, y);
   const long total_vec = static_cast<long>(N) * HW * (C / 8);
   gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, stats,
                                                                                (bf16*)y, HW, C, G, silu, total_vec);
@@ -663,6 +668,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_warp_kernel(const bf16* __r
   }
 }
 int layernorm_bwd(const void* dy, const void* x, const void* w, const void* dres, void* dx, int T, int H, float eps, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dy, x, w, dres, dx);
   const int nvec = H / 8;
   if (H % 8 || nvec > 32 * 6 || T <= 0) return DLLM_ERR_SHAPE;
   const unsigned grid = static_cast<unsigned>((static_cast<long>(T) * 32 + 255) / 256);
@@ -694,6 +700,7 @@ __global__ void geglu_bwd_kernel(const bf16* __restrict__ dout, const bf16* __re
   *reinterpret_cast<V8*>(din + t * 2 * I + I + v * 8) = pk8(og);
 }
 int geglu_bwd(const void* dout, const void* in, void* din, int T, int I, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dout, in, din);
   if (I % 8 || T <= 0) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(T) * (I / 8);
   geglu_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)dout, (const bf16*)in, (bf16*)din, T, I);
@@ -759,12 +766,14 @@ __global__ void copy_cols2_kernel(const bf16* __restrict__ src, bf16* __restrict
   *reinterpret_cast<uint4*>(dst + r * Cd + dcol0 + v * 8) = *reinterpret_cast<const uint4*>(src + r * Cs + scol0 + v * 8);
 }
 int upsample2x_bwd_nhwc(const void* dy, void* dx, int N, int H, int W, int C, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dy, dx);
   if (C % 8) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(N) * H * W * (C / 8);
   upsample2x_bwd_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)dy, (bf16*)dx, N, H, W, C);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int col2im_s2_nhwc(const void* dcols, void* dx, int N, int H, int W, int C, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(dcols, dx);
   if (C % 8 || H % 2 || W % 2) return DLLM_ERR_SHAPE;
   const long total = static_cast<long>(N) * H * W * (C / 8);
   col2im_s2_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)dcols, (bf16*)dx, N, H, W, C);
@@ -929,6 +938,7 @@ __global__ void __launch_bounds__(256) softmax_rows_kernel(bf16* __restrict__ x,
   }
 }
 int softmax_rows(void* x, long rows, int cols, float scale, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(x);
   if (cols % 8 || rows <= 0) return DLLM_ERR_SHAPE;
   softmax_rows_kernel<<<static_cast<unsigned>(rows), 256, 0, s>>>((bf16*)x, cols, scale);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
