@@ -50,6 +50,20 @@ def pick_next_token(logits: torch.Tensor, input_ids: torch.Tensor | None = None,
     return torch.multinomial(probs, 1, generator=generator).squeeze(1)
 
 
+def ragged(decode_one, input_ids, attention_mask, pad_id: int):
+    """Run `decode_one(ids [1, L])` on every row's valid tokens and pad the outputs to a rectangle.  Left-padded inputs (HF's convention
+    for decoder-only generation) come back left-padded, right-padded inputs right-padded."""
+    mask = attention_mask.bool()
+    left = bool((~mask[:, 0]).any())
+    outs = [decode_one(row[m][None]) [0] for row, m in zip(input_ids, mask)]
+    width = max(o.numel() for o in outs)
+    rows = []
+    for o in outs:
+        pad = torch.full((width - o.numel(),), pad_id, dtype=o.dtype, device=o.device)
+        rows.append(torch.cat([pad, o]) if left else torch.cat([o, pad]))
+    return torch.stack(rows)
+
+
 @torch.no_grad()
 def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample: bool = False, temperature: float = 1.0, top_k: int = 0,
              top_p: float = 1.0, repetition_penalty: float = 1.0, eos_token_id=None, pad_token_id=None, generator=None,
@@ -59,7 +73,15 @@ def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample:
     (HF `StoppingCriteria` semantics; the reference's VQA eval passes a keyword criterion, omni/eval/vqa/vqa_inference.py:105-106).
     Returns [B, S + n_generated] ids (prompt included, like HF for decoder-only models)."""
     if attention_mask is not None and not bool(attention_mask.all()):
-        raise NotImplementedError("padded prompt batches are not supported by the kv-cache path; generate prompts of different lengths one at a time")
+        # ragged batch: the kv-cache kernels take one valid length per call, so each prompt is decoded on its own (batch 1) and the results
+        # are padded back to a rectangle on the side the inputs were padded on
+        if images is not None:
+            raise NotImplementedError("padded prompt batches with images: pass the prompts one at a time (images are matched to <im_start> "
+                                      "tokens in batch order)")
+        return ragged(lambda ids: generate(model, ids, None, max_new_tokens, do_sample, temperature, top_k, top_p, repetition_penalty,
+                                           eos_token_id, pad_token_id, generator, None, stopping_criteria),
+                      input_ids, attention_mask, pad_token_id if pad_token_id is not None else
+                      (eos_token_id if isinstance(eos_token_id, int) else (eos_token_id[0] if eos_token_id else 0)))
     eos = None
     if eos_token_id is not None:
         eos = torch.as_tensor([eos_token_id] if isinstance(eos_token_id, int) else list(eos_token_id), device=input_ids.device)

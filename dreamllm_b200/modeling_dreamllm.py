@@ -1015,7 +1015,13 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
             if do_sample:
                 raise NotImplementedError("beam sampling (num_beams > 1 with do_sample=True) is not built")
             if attention_mask is not None and not bool(attention_mask.all()):
-                raise NotImplementedError("padded prompt batches are not supported by the kv-cache path")
+                if images is not None:
+                    raise NotImplementedError("padded prompt batches with images: pass the prompts one at a time")
+                from .generation import ragged
+                kw = dict(kwargs)
+                return ragged(lambda ids: self.generate(ids, max_new_tokens=max_new_tokens, eos_token_id=eos_token_id, pad_token_id=pad_token_id,
+                                                        stopping_criteria=stopping_criteria, **kw), input_ids, attention_mask,
+                              pad_token_id if pad_token_id is not None else (eos_token_id if isinstance(eos_token_id, int) else 0))
             return beam_search(self, input_ids, images=images, num_beams=num_beams, max_new_tokens=max_new_tokens,
                                length_penalty=kwargs.get("length_penalty", 1.0), early_stopping=kwargs.get("early_stopping", False),
                                eos_token_id=eos_token_id, pad_token_id=pad_token_id, stopping_criteria=stopping_criteria,

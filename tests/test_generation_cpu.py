@@ -186,3 +186,30 @@ def test_beam_search_modes_and_kvcache_beam_ops():
     assert c.k[1][:, 2, 0, 0].tolist() == [2, 2, 1, 2, 2, 1] and c.v[1][:, 0, 0, 0].tolist() == [-2, -2, -1, -2, -2, -1]
     assert float(c.k[0][:, 3:].abs().sum()) == 0                           # rows past the valid length stay zero
     assert DreamLLMForCausalMLM._reorder_cache(c, torch.arange(6)) is c
+
+
+def test_ragged_batches_are_decoded_row_by_row():
+    """Padded prompt batches: each row's valid tokens are decoded on their own (batch 1) and re-padded on the input's padding side."""
+    from dreamllm_b200.generation import generate
+
+    class ByLength:                       # emits (prompt length + step) % 50: the answer depends on the un-padded prompt only
+        def __call__(self, input_ids=None, images=None, past_key_values=None, use_cache=None, last_token_logits_only=None):
+            from types import SimpleNamespace
+            assert input_ids.shape[0] == 1
+            if past_key_values is None:
+                past_key_values = {"n": input_ids.shape[1]}
+            else:
+                past_key_values["n"] += 1
+            logits = torch.full((1, 1, 50), -10.0)
+            logits[0, 0, past_key_values["n"] % 50] = 10.0
+            return SimpleNamespace(logits=logits, past_key_values=past_key_values)
+    ids = torch.tensor([[0, 0, 7, 8], [5, 6, 7, 8]])
+    mask = torch.tensor([[0, 0, 1, 1], [1, 1, 1, 1]])
+    out = generate(ByLength(), ids, attention_mask=mask, max_new_tokens=3, pad_token_id=0)
+    assert out.tolist() == [[0, 0, 7, 8, 2, 3, 4], [5, 6, 7, 8, 4, 5, 6]]            # left-padded in, left-padded out
+    ids_r = torch.tensor([[7, 8, 0, 0], [5, 6, 7, 8]])
+    out = generate(ByLength(), ids_r, attention_mask=mask.flip(1)[[0, 1]] * 0 + torch.tensor([[1, 1, 0, 0], [1, 1, 1, 1]]), max_new_tokens=3,
+                   pad_token_id=0)
+    assert out.tolist() == [[7, 8, 2, 3, 4, 0, 0], [5, 6, 7, 8, 4, 5, 6]]            # right-padded in, right-padded out
+    with pytest.raises(NotImplementedError):
+        generate(ByLength(), ids, images="x", attention_mask=mask, max_new_tokens=1)

@@ -92,5 +92,9 @@ def test_sampling_generate_and_eos_padding():
     assert int(out[0, 20]) == eos and bool((out[0, 21:] == 0).all())
     if eos not in greedy[1, 20:].tolist():
         assert torch.equal(out[1], greedy[1])                # the other row is unaffected
-    with pytest.raises(NotImplementedError):
-        m.generate(ids, attention_mask=torch.tensor([[1] * 20, [1] * 19 + [0]], device="cuda"))
+    # ragged (right-padded) batch: every row is decoded on its own valid tokens and the results are padded back to a rectangle
+    mask = torch.tensor([[1] * 20, [1] * 19 + [0]], device="cuda")
+    rag = m.generate(ids, attention_mask=mask, max_new_tokens=3, pad_token_id=0)
+    assert rag.shape == (2, 23)
+    assert torch.equal(rag[0], m.generate(ids[:1], max_new_tokens=3)[0])
+    assert torch.equal(rag[1, :22], m.generate(ids[1:, :19], max_new_tokens=3)[0]) and int(rag[1, 22]) == 0
