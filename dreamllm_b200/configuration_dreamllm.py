@@ -94,7 +94,9 @@ class DreamLLMConfig:
 
     @classmethod
     def vicuna_7b(cls, **kw):
-        return cls(vocab_size=32008, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32, **kw)
+        base = dict(vocab_size=32008, hidden_size=4096, intermediate_size=11008, num_hidden_layers=32, num_attention_heads=32)
+        base.update(kw)                      # e.g. num_hidden_layers=2 for a reduced-depth dev run
+        return cls(**base)
 
     # ---------------------------------------------------------------------------------------------- reference methods
     def update_special_tokens2ids_dict(self, tokens_dict: dict, tokenizer):

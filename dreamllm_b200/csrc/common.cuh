@@ -271,20 +271,14 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N, bool a_mn, 
          (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 
-// -DDLLM_VEC128 turns the 8-element vector copies of the HBM-bound kernels into 128-bit accesses, which fault on addresses that are
-// not 16-byte aligned: under that flag the host wrappers reject such pointers up front (DLLM_ERR_ALIGN).  Without it: expands to nothing.
-#ifdef DLLM_VEC128
+// The 8-element vector copies of the HBM-bound kernels are 128-bit accesses, which fault on addresses that are not 16-byte aligned:
+// the host wrappers reject such pointers up front (DLLM_ERR_ALIGN).
 #define DLLM_REQUIRE_ALIGN16(...)                                                        \
   do {                                                                                   \
     const void* dllm_ps_[] = {__VA_ARGS__};                                              \
     for (const void* dllm_p_ : dllm_ps_)                                                 \
       if (reinterpret_cast<uintptr_t>(dllm_p_) & 15u) return -2; /* DLLM_ERR_ALIGN */    \
   } while (0)
-#else
-#define DLLM_REQUIRE_ALIGN16(...) \
-  do {                            \
-  } while (0)
-#endif
 
 // ----------------------------------------------------------------------------- small math helpers
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -1,18 +1,17 @@
 // HBM-bound kernels of the DreamLLM decoder path (sm_100a): RMSNorm fwd/bwd (+fused residual add),
 // RoPE (in place on the fused qkv buffer), SwiGLU fwd/bwd, shifted masked cross-entropy (fwd + in-place
 // dlogits), embedding gather / sorted segment scatter, bf16 add.
-// All move 8-element (16-byte) vectors per thread (128-bit LDG/STG with -DDLLM_VEC128, see the Vec8 note below), fp32 math, warp-shuffle reductions; rounding points follow the
+// All move 8-element (16-byte) vectors per thread (128-bit LDG/STG, see the Vec8 note below), fp32 math, warp-shuffle reductions; rounding points follow the
 // reference's bf16 eager path (cited per kernel) so bf16-vs-bf16 parity holds to the last place where cheap.
 #include "common.cuh"
 #include "gemm_sm100.h"
 
 namespace dllm {
 
-// DLLM_VEC128 (build flag, OFF by default until measured on hardware — DESIGN.md section 8): with the bfloat162[4] layout nvcc compiles
-// every struct copy into four 32-bit LDG/STG (cuobjdump -sass); a single uint4 member makes the same copies LDG.E.128 / STG.E.128.
-// Bit-identical results either way; the wide form additionally requires 16-byte aligned row starts (true for every caller: row widths and
-// row strides are multiples of 8 elements).
-#ifdef DLLM_VEC128
+// 8 bf16 = one 16-byte vector.  The single uint4 member makes every copy of the struct one LDG.E.128 / STG.E.128; the earlier
+// `__nv_bfloat162 v[4]` layout was split by nvcc into four 32-bit accesses (4x the LSU / L1 wavefronts: rmsnorm 0.62 -> 0.75, rope
+// 0.63 -> 0.68, layernorm 0.47 -> 0.67 of the HBM copy peak on the same box, profiles/r02_ab_hbm_flags.txt).  Row starts must be 16-byte
+// aligned (true for every caller: widths and strides are multiples of 8 elements); the host wrappers check the base pointers.
 struct alignas(16) Vec8 {
   uint4 u;
   __device__ __forceinline__ __nv_bfloat162 get(int i) const {
@@ -24,13 +23,6 @@ struct alignas(16) Vec8 {
     if (i == 0) u.x = w; else if (i == 1) u.y = w; else if (i == 2) u.z = w; else u.w = w;
   }
 };
-#else
-struct alignas(16) Vec8 {
-  __nv_bfloat162 v[4];
-  __device__ __forceinline__ __nv_bfloat162 get(int i) const { return v[i]; }
-  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) { v[i] = h; }
-};
-#endif
 __device__ __forceinline__ void unpack8(const Vec8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {

@@ -8,11 +8,10 @@
 
 namespace dllm {
 
-// DLLM_VEC128 (build flag, OFF by default until measured on hardware — DESIGN.md section 8): with the bfloat162[4] layout nvcc compiles
-// every struct copy into four 32-bit LDG/STG (cuobjdump -sass); a single uint4 member makes the same copies LDG.E.128 / STG.E.128.
-// Bit-identical results either way; the wide form additionally requires 16-byte aligned row starts (true for every caller: row widths and
-// row strides are multiples of 8 elements).
-#ifdef DLLM_VEC128
+// 8 bf16 = one 16-byte vector.  The single uint4 member makes every copy of the struct one LDG.E.128 / STG.E.128; the earlier
+// `__nv_bfloat162 v[4]` layout was split by nvcc into four 32-bit accesses (4x the LSU / L1 wavefronts: rmsnorm 0.62 -> 0.75, rope
+// 0.63 -> 0.68, layernorm 0.47 -> 0.67 of the HBM copy peak on the same box, profiles/r02_ab_hbm_flags.txt).  Row starts must be 16-byte
+// aligned (true for every caller: widths and strides are multiples of 8 elements); the host wrappers check the base pointers.
 struct alignas(16) V8 {
   uint4 u;
   __device__ __forceinline__ __nv_bfloat162 get(int i) const {
@@ -24,13 +23,6 @@ struct alignas(16) V8 {
     if (i == 0) u.x = w; else if (i == 1) u.y = w; else if (i == 2) u.z = w; else u.w = w;
   }
 };
-#else
-struct alignas(16) V8 {
-  __nv_bfloat162 v[4];
-  __device__ __forceinline__ __nv_bfloat162 get(int i) const { return v[i]; }
-  __device__ __forceinline__ void set(int i, __nv_bfloat162 h) { v[i] = h; }
-};
-#endif
 __device__ __forceinline__ void up8(const V8& p, float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -48,52 +40,133 @@ __device__ __forceinline__ V8 pk8(const float* f) {
 __device__ __forceinline__ float r16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
 
 // ------------------------------------------------------------------------------------------------ GroupNorm (+SiLU)
-// x [N, HW, C]; G groups of C/G channels.  Pass 1: per (n, pixel-chunk) partial sum / sum-of-squares per group.
-constexpr int kGnThreads = 256;
-constexpr int kGnMaxV = 2;  // C <= 256 * 2 * 8 = 4096
+// x [N, HW, C]; G groups of C/G channels.  All four kernels (forward statistics / apply, backward sums / apply) share one thread mapping:
+// a CTA owns `rows` consecutive pixel rows of one image and runs RL * (C/8) threads — thread (rl, v) keeps the 8 channels of vector v
+// in registers (weight, bias, the <= 2 group records they belong to) and walks rows rl, rl + RL, ... with four independent 16-byte
+// loads in flight, so there is no per-element integer division and every lane of the CTA carries data (r01's mapping left 216 of 256
+// threads idle at C = 320 and issued one load per thread per trip: 0.13-0.25 of the HBM peak, profiles/r02_ab_hbm_flags.txt).
+// Reductions are two-stage and order-fixed (per-thread registers -> smem [RL][C] -> one thread per group -> global partials ->
+// finalize), i.e. deterministic: graph replays stay bit-identical to eager launches.
+constexpr int kGnMaxThreads = 512;
+template <bool kBwd>
+struct GnUnroll { static constexpr int v = kBwd ? 2 : 4; };   // rows in flight per thread (the backward kernels carry twice the state)
 
-__global__ void __launch_bounds__(kGnThreads) gn_partial_kernel(const bf16* __restrict__ x, float* __restrict__ partial, int HW,
-                                                                int C, int G, int rows_per_cta) {
-  extern __shared__ float sm[];  // [2][C]
+struct GnMap {
+  int nvec, RL, threads;
+};
+static inline GnMap gn_map(int C) {
+  GnMap m;
+  m.nvec = C >> 3;
+  m.RL = kGnMaxThreads / m.nvec;
+  if (m.RL < 1) m.RL = 1;
+  if (m.RL > 32) m.RL = 32;
+  m.threads = m.RL * m.nvec;
+  return m;
+}
+
+// the (at most two) groups the 8 channels [8v, 8v+8) fall into: channels j < split belong to g0, the rest to g0 + 1 (cpg >= 8);
+// for cpg < 8 (VAE: 128 channels / 32 groups) `gidx` lists the group of every channel instead
+struct GnVecGroups {
+  int g0, split;
+  bool two;
+  int gidx[8];
+};
+__device__ __forceinline__ GnVecGroups gn_vec_groups(int v, int cpg, int G) {
+  GnVecGroups r;
+  r.two = cpg >= 8;
+  r.g0 = (v * 8) / cpg;
+  r.split = r.two ? min(8, (r.g0 + 1) * cpg - v * 8) : 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) r.gidx[j] = r.two ? min(r.g0 + (j >= r.split ? 1 : 0), G - 1) : (v * 8 + j) / cpg;
+  return r;
+}
+
+// forward statistics partials (kBwd = false): per (n, chunk, g) {sum x, sum x^2}
+// backward partials          (kBwd = true ): per (n, chunk, g) {sum g, sum g * xhat} with g = dy * silu'(y) * w
+template <bool kBwd>
+__global__ void __launch_bounds__(kGnMaxThreads) gn_partial_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                                   const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                                   const float* __restrict__ stats, float* __restrict__ partial, int HW,
+                                                                   int C, int G, int rows_per_cta, int RL, int silu) {
+  extern __shared__ float sm[];  // [RL][2][C]
   const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  const int nvec = C >> 3;
+  const int nvec = C >> 3, cpg = C / G;
+  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
   const int r0 = chunk * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
-  float s[kGnMaxV][8], q[kGnMaxV][8];
+  float s[8], q[8];
 #pragma unroll
-  for (int i = 0; i < kGnMaxV; ++i)
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  float wf[8], bf_[8], mean[8], rstd[8];
+  if constexpr (kBwd) {
+    up8(reinterpret_cast<const V8*>(w)[v], wf);
+    up8(reinterpret_cast<const V8*>(b)[v], bf_);
+    const GnVecGroups gg = gn_vec_groups(v, cpg, G);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) s[i][j] = q[i][j] = 0.f;
-  const bf16* xb = x + (static_cast<size_t>(n) * HW) * C;
-  for (int r = r0; r < r1; ++r) {
+    for (int j = 0; j < 8; ++j) {
+      const float2 st = *reinterpret_cast<const float2*>(stats + (static_cast<size_t>(n) * G + gg.gidx[j]) * 2);
+      mean[j] = st.x;
+      rstd[j] = st.y;
+    }
+  }
+  const size_t base = static_cast<size_t>(n) * HW * C;
+  const V8* xb = reinterpret_cast<const V8*>(x + base) + v;
+  const V8* db = kBwd ? reinterpret_cast<const V8*>(dy + base) + v : nullptr;
+  constexpr int kGnUnroll = GnUnroll<kBwd>::v;
+  for (int r = r0 + rl; r < r1; r += RL * kGnUnroll) {
+    V8 xv[kGnUnroll], dv[kGnUnroll];
 #pragma unroll
-    for (int i = 0; i < kGnMaxV; ++i) {
-      const int v = threadIdx.x + i * kGnThreads;
-      if (v < nvec) {
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const int rr = r + u * RL;
+      if (rr < r1) {
+        xv[u] = xb[static_cast<size_t>(rr) * nvec];
+        if constexpr (kBwd) dv[u] = db[static_cast<size_t>(rr) * nvec];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const int rr = r + u * RL;
+      if (rr < r1) {
         float f[8];
-        up8(reinterpret_cast<const V8*>(xb + static_cast<size_t>(r) * C)[v], f);
+        up8(xv[u], f);
+        if constexpr (!kBwd) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[i][j] += f[j]; q[i][j] += f[j] * f[j]; }
+          for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
+        } else {
+          float d[8];
+          up8(dv[u], d);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - mean[j]) * rstd[j];
+            float gq = d[j];
+            if (silu) {
+              const float y = r16(xh * wf[j] + bf_[j]);
+              const float sg = 1.f / (1.f + expf(-y));
+              gq *= sg * (1.f + y * (1.f - sg));
+            }
+            gq *= wf[j];
+            s[j] += gq;
+            q[j] += gq * xh;
+          }
+        }
       }
     }
   }
+  float* sm_s = sm + (static_cast<size_t>(rl) * 2) * C + v * 8;
 #pragma unroll
-  for (int i = 0; i < kGnMaxV; ++i) {
-    const int v = threadIdx.x + i * kGnThreads;
-    if (v < nvec)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { sm[v * 8 + j] = s[i][j]; sm[C + v * 8 + j] = q[i][j]; }
-  }
+  for (int j = 0; j < 8; ++j) { sm_s[j] = s[j]; sm_s[C + j] = q[j]; }
   __syncthreads();
-  const int cpg = C / G;
-  for (int g = threadIdx.x; g < G; g += kGnThreads) {
-    float a = 0.f, b = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sm[c]; b += sm[C + c]; }
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float a = 0.f, c2 = 0.f;
+    for (int l = 0; l < RL; ++l) {
+      const float* p0 = sm + (static_cast<size_t>(l) * 2) * C;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += p0[c]; c2 += p0[C + c]; }
+    }
     float* p = partial + ((static_cast<size_t>(n) * nchunks + chunk) * G + g) * 2;
     p[0] = a;
-    p[1] = b;
+    p[1] = c2;
   }
 }
-// stats[n, g] = {mean, rstd}
+// forward: stats[n, g] = {mean, rstd};  backward (eps < 0): sums[n, g] = {sum g / count, sum g xhat / count}
 __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __restrict__ stats, int nchunks, int G, float count,
                                    float eps, int total) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // n * G + g
@@ -105,109 +178,200 @@ __global__ void gn_finalize_kernel(const float* __restrict__ partial, float* __r
     a += p[0];
     b += p[1];
   }
+  if (eps < 0.f) {
+    stats[2 * i] = a / count;
+    stats[2 * i + 1] = b / count;
+    return;
+  }
   const float mean = a / count;
   const float var = fmaxf(b / count - mean * mean, 0.f);
   stats[2 * i] = mean;
   stats[2 * i + 1] = rsqrtf(var + eps);
 }
-// y = silu?( bf16( (x - mean) * rstd * w + b ) )
-__global__ void gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w, const bf16* __restrict__ b,
-                                const float* __restrict__ stats, bf16* __restrict__ y, int HW, int C, int G, int silu,
-                                long total_vec) {
-  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= total_vec) return;
-  const int nvec = C >> 3;
-  const int v = static_cast<int>(gid % nvec);
-  const long pix = gid / nvec;
-  const int n = static_cast<int>(pix / HW);
-  const int cpg = C / G;
-  float f[8], wf[8], bf[8];
-  up8(reinterpret_cast<const V8*>(x)[gid], f);
+// forward  (kBwd = false): y  = silu?( bf16( (x - mean) * rstd * w + b ) )
+// backward (kBwd = true ): dx = rstd * (g - mean_g(g) - xhat * mean_g(g * xhat)) (+ dres),   g = dy * silu'(y) * w
+template <bool kBwd>
+__global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy,
+                                                                 const bf16* __restrict__ w, const bf16* __restrict__ b,
+                                                                 const float* __restrict__ stats, const float* __restrict__ sums,
+                                                                 const bf16* __restrict__ dres, bf16* __restrict__ out, int HW, int C, int G,
+                                                                 int rows_per_cta, int RL, int silu) {
+  const int n = blockIdx.y, chunk = blockIdx.x;
+  const int nvec = C >> 3, cpg = C / G;
+  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
+  const int r0 = chunk * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
+  float wf[8], bf_[8], mean[8], rstd[8], m1[8], m2[8];
   up8(reinterpret_cast<const V8*>(w)[v], wf);
-  up8(reinterpret_cast<const V8*>(b)[v], bf);
-#ifdef DLLM_GN_GROUP2
-  // DLLM_GN_GROUP2 (build flag, OFF until measured — DESIGN.md section 8): with >= 8 channels per group the 8 channels of a vector touch at
-  // most two groups, so one integer division and two (mean, rstd) pairs replace eight divisions and sixteen scalar loads per thread.
-  const bool two = cpg >= 8;
-  const int g0 = (v * 8) / cpg;
-  const int split = two ? (g0 + 1) * cpg - v * 8 : 0;                       // channels [0, split) of this vector belong to group g0
-  const size_t s0 = (static_cast<size_t>(n) * G + g0) * 2, s1 = (static_cast<size_t>(n) * G + min(g0 + 1, G - 1)) * 2;
-  const float mean0 = two ? __ldg(stats + s0) : 0.f, rstd0 = two ? __ldg(stats + s0 + 1) : 0.f;
-  const float mean1 = two ? __ldg(stats + s1) : 0.f, rstd1 = two ? __ldg(stats + s1 + 1) : 0.f;
-#endif
+  up8(reinterpret_cast<const V8*>(b)[v], bf_);
+  const GnVecGroups gg = gn_vec_groups(v, cpg, G);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-#ifdef DLLM_GN_GROUP2
-    float mean, rstd;
-    if (two) {
-      mean = j < split ? mean0 : mean1;
-      rstd = j < split ? rstd0 : rstd1;
-    } else {
-      const int g = (v * 8 + j) / cpg;
-      mean = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2);
-      rstd = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2 + 1);
+    const size_t si = (static_cast<size_t>(n) * G + gg.gidx[j]) * 2;
+    const float2 st = *reinterpret_cast<const float2*>(stats + si);
+    mean[j] = st.x;
+    rstd[j] = st.y;
+    if constexpr (kBwd) {
+      const float2 sm2 = *reinterpret_cast<const float2*>(sums + si);
+      m1[j] = sm2.x;
+      m2[j] = sm2.y;
     }
-#else
-    const int g = (v * 8 + j) / cpg;
-    const float mean = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2);
-    const float rstd = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2 + 1);
-#endif
-    float o = r16((f[j] - mean) * rstd * wf[j] + bf[j]);
-    if (silu) o = o / (1.f + expf(-o));
-    f[j] = o;
   }
-  reinterpret_cast<V8*>(y)[gid] = pk8(f);
+  const size_t base = static_cast<size_t>(n) * HW * C;
+  const V8* xb = reinterpret_cast<const V8*>(x + base) + v;
+  const V8* db = kBwd ? reinterpret_cast<const V8*>(dy + base) + v : nullptr;
+  const V8* rb = (kBwd && dres) ? reinterpret_cast<const V8*>(dres + base) + v : nullptr;
+  V8* ob = reinterpret_cast<V8*>(out + base) + v;
+  constexpr int kGnUnroll = GnUnroll<kBwd>::v;
+  for (int r = r0 + rl; r < r1; r += RL * kGnUnroll) {
+    V8 xv[kGnUnroll], dv[kGnUnroll], rv[kGnUnroll];
+#pragma unroll
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const int rr = r + u * RL;
+      if (rr < r1) {
+        xv[u] = xb[static_cast<size_t>(rr) * nvec];
+        if constexpr (kBwd) {
+          dv[u] = db[static_cast<size_t>(rr) * nvec];
+          if (rb) rv[u] = rb[static_cast<size_t>(rr) * nvec];
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kGnUnroll; ++u) {
+      const int rr = r + u * RL;
+      if (rr < r1) {
+        float f[8], o[8];
+        up8(xv[u], f);
+        if constexpr (!kBwd) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float t = r16((f[j] - mean[j]) * rstd[j] * wf[j] + bf_[j]);
+            if (silu) t = t / (1.f + expf(-t));
+            o[j] = t;
+          }
+        } else {
+          float d[8], rs[8];
+          up8(dv[u], d);
+          if (rb) up8(rv[u], rs);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = (f[j] - mean[j]) * rstd[j];
+            float gq = d[j];
+            if (silu) {
+              const float y = r16(xh * wf[j] + bf_[j]);
+              const float sg = 1.f / (1.f + expf(-y));
+              gq *= sg * (1.f + y * (1.f - sg));
+            }
+            gq *= wf[j];
+            float t = rstd[j] * (gq - m1[j] - xh * m2[j]);
+            if (rb) t += rs[j];
+            o[j] = t;
+          }
+        }
+        ob[static_cast<size_t>(rr) * nvec] = pk8(o);
+      }
+    }
+  }
 }
 
-// pixel rows per partial-sum CTA: 64 for the UNet planes, more for the VAE's 512x512 planes so that the finalize pass never
-// walks more than 128 partials (it took 35 us per GroupNorm with 4096 of them — profiles/r01_stage1_launch_list_summary.md)
-static inline int gn_rows(int HW) {
+// pixel rows per partial-sum CTA: 64 for the big UNet planes, more for the VAE's 512x512 planes so that the finalize pass never walks
+// more than 128 partials, fewer for small planes so that the grid still covers the 148 SMs
+static inline int gn_rows(int HW, int N) {
   int rows = 64;
   while ((HW + rows - 1) / rows > 128) rows *= 2;
+  while (rows > 8 && static_cast<long>(N) * ((HW + rows - 1) / rows) < 2 * 148 && (HW + rows / 2 - 1) / (rows / 2) <= 128) rows /= 2;
   return rows;
 }
 size_t groupnorm_workspace(int N, int HW, int G) {
-  const int rows = gn_rows(HW);
+  const int rows = gn_rows(HW, N);
   const int nchunks = (HW + rows - 1) / rows;
   return (static_cast<size_t>(N) * nchunks * G * 2 + static_cast<size_t>(N) * G * 2) * sizeof(float);
+}
+static int gn_check(int N, int HW, int C, int G, size_t ws_bytes) {
+  if (C % 8 || C % G || (C >> 3) > kGnMaxThreads || N <= 0 || HW <= 0) return DLLM_ERR_SHAPE;
+  if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
+  return 0;
+}
+static int gn_launch_stats(const bf16* x, float* stats, float* partial, int N, int HW, int C, int G, float eps, cudaStream_t s) {
+  const GnMap m = gn_map(C);
+  const int rows = gn_rows(HW, N);
+  const int nchunks = (HW + rows - 1) / rows;
+  gn_partial_kernel<false><<<dim3(nchunks, N), m.threads, static_cast<size_t>(m.RL) * 2 * C * sizeof(float), s>>>(
+      x, nullptr, nullptr, nullptr, nullptr, partial, HW, C, G, rows, m.RL, 0);
+  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, stats, nchunks, G, static_cast<float>(HW) * (C / G), eps, N * G);
+  return 0;
+}
+static void gn_launch_apply(const bf16* x, const bf16* w, const bf16* b, const float* stats, bf16* y, int N, int HW, int C, int G, int silu,
+                            cudaStream_t s) {
+  const GnMap m = gn_map(C);
+  int rows = 32;
+  while (rows > m.RL && static_cast<long>(N) * ((HW + rows - 1) / rows) < 4 * 148) rows /= 2;
+  gn_apply_kernel<false><<<dim3((HW + rows - 1) / rows, N), m.threads, 0, s>>>(x, nullptr, w, b, stats, nullptr, nullptr, y, HW, C, G, rows,
+                                                                                m.RL, silu);
 }
 int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW, int C,
                    int G, float eps, int silu, cudaStream_t s) {
   DLLM_REQUIRE_ALIGN16(x, w, b, y);
-  if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
-  if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
-  const int rows = gn_rows(HW);
-  const int nchunks = (HW + rows - 1) / rows;
+  if (int rc = gn_check(N, HW, C, G, ws_bytes)) return rc;
   float* partial = static_cast<float*>(workspace);
-  float* stats = partial + static_cast<size_t>(N) * nchunks * G * 2;
-  gn_partial_kernel<<<dim3(nchunks, N), kGnThreads, 2 * C * sizeof(float), s>>>((const bf16*)x, partial, HW, C, G, rows);
-  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, stats, nchunks, G, static_cast<float>(HW) * (C / G), eps, N * G);
-  const long total_vec = static_cast<long>(N) * HW * (C / 8);
-  gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, stats,
-                                                                               (bf16*)y, HW, C, G, silu, total_vec);
+  const int rows = gn_rows(HW, N);
+  float* stats = partial + static_cast<size_t>(N) * ((HW + rows - 1) / rows) * G * 2;
+  gn_launch_stats((const bf16*)x, stats, partial, N, HW, C, G, eps, s);
+  gn_launch_apply((const bf16*)x, (const bf16*)w, (const bf16*)b, stats, (bf16*)y, N, HW, C, G, silu, s);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
 // ------------------------------------------------------------------------------------------------ GEGLU
 // diffusers GEGLU: h, gate = proj(x).chunk(2); out = h * gelu(gate)      in [T, 2I] -> out [T, I]
-__global__ void geglu_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int T, int I) {
+// grid = (ceil(I/8 / 256), T / kGegluRows): a thread keeps its column vector and walks kGegluRows token rows with all loads of two rows
+// issued before the erf math (no 64-bit index division, 4 x 16 B in flight per thread)
+constexpr int kGegluRows = 4;
+__global__ void __launch_bounds__(256) geglu_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int T, int I) {
   const int nvec = I >> 3;
-  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= static_cast<long>(T) * nvec) return;
-  const int v = static_cast<int>(gid % nvec);
-  const long t = gid / nvec;
-  float a[8], g[8];
-  up8(*reinterpret_cast<const V8*>(in + t * 2 * I + v * 8), a);
-  up8(*reinterpret_cast<const V8*>(in + t * 2 * I + I + v * 8), g);
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvec) return;
+  const int t0 = blockIdx.y * kGegluRows;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) a[j] *= r16(0.5f * g[j] * (1.f + erff(g[j] * 0.70710678118654752f)));
-  *reinterpret_cast<V8*>(out + t * I + v * 8) = pk8(a);
+  for (int tt = 0; tt < kGegluRows; tt += 2) {
+    V8 av[2], gv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long t = t0 + tt + u;
+      if (t < T) {
+        av[u] = *reinterpret_cast<const V8*>(in + t * 2 * I + v * 8);
+        gv[u] = *reinterpret_cast<const V8*>(in + t * 2 * I + I + v * 8);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long t = t0 + tt + u;
+      if (t < T) {
+        float a[8], g[8];
+        up8(av[u], a);
+        up8(gv[u], g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] *= r16(0.5f * g[j] * (1.f + erff(g[j] * 0.70710678118654752f)));
+        *reinterpret_cast<V8*>(out + t * I + v * 8) = pk8(a);
+      }
+    }
+  }
 }
 int geglu(const void* in, void* out, int T, int I, cudaStream_t s) {
   DLLM_REQUIRE_ALIGN16(in, out);
   if (I % 8 || T <= 0) return DLLM_ERR_SHAPE;
-  const long total = static_cast<long>(T) * (I / 8);
-  geglu_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)in, (bf16*)out, T, I);
+  const int nvec = I / 8;
+  const int bt = ((nvec < 256 ? nvec : 256) + 31) / 32 * 32;      // no idle lanes when I/8 < 256 (I = 1280: 160 threads)
+  const long rows = (static_cast<long>(T) + kGegluRows - 1) / kGegluRows;
+  if (rows > 65535L * 32768L) return DLLM_ERR_SHAPE;
+  // blockIdx.y is limited to 65535: fold the excess into more columns per launch is not needed for T <= 262 140
+  if (rows > 65535) {
+    for (long r0 = 0; r0 < T; r0 += 65535L * kGegluRows) {
+      const int Tc = static_cast<int>(T - r0 < 65535L * kGegluRows ? T - r0 : 65535L * kGegluRows);
+      geglu_kernel<<<dim3((nvec + bt - 1) / bt, (Tc + kGegluRows - 1) / kGegluRows), bt, 0, s>>>((const bf16*)in + r0 * 2 * I,
+                                                                                                 (bf16*)out + r0 * I, Tc, I);
+    }
+  } else {
+    geglu_kernel<<<dim3((nvec + bt - 1) / bt, static_cast<unsigned>(rows)), bt, 0, s>>>((const bf16*)in, (bf16*)out, T, I);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
@@ -433,171 +597,39 @@ int sampler_step(const float* eps, float* latents, const float* noise, const flo
 // dream-query conditioning, so every op needs d/d(input) but no weight gradients (SURVEY §7 "Backward through frozen towers").
 
 // ---- GroupNorm(+SiLU) backward.  g = dy * silu'(y_gn) * w;  dx = rstd * (g - mean_g(g) - xhat * mean_g(g * xhat))
-__global__ void __launch_bounds__(kGnThreads) gn_bwd_partial_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x,
-                                                                    const bf16* __restrict__ w, const bf16* __restrict__ b,
-                                                                    const float* __restrict__ stats, float* __restrict__ partial,
-                                                                    int HW, int C, int G, int rows_per_cta, int silu) {
-  extern __shared__ float sm[];  // [2][C]
-  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  const int nvec = C >> 3, cpg = C / G;
-  const int r0 = chunk * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
-  float s1[kGnMaxV][8], s2[kGnMaxV][8];
-#pragma unroll
-  for (int i = 0; i < kGnMaxV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s1[i][j] = s2[i][j] = 0.f;
-  const size_t base = static_cast<size_t>(n) * HW * C;
-  for (int r = r0; r < r1; ++r) {
-#pragma unroll
-    for (int i = 0; i < kGnMaxV; ++i) {
-      const int v = threadIdx.x + i * kGnThreads;
-      if (v < nvec) {
-        float d[8], f[8], wf[8], bf[8];
-        up8(reinterpret_cast<const V8*>(dy + base + static_cast<size_t>(r) * C)[v], d);
-        up8(reinterpret_cast<const V8*>(x + base + static_cast<size_t>(r) * C)[v], f);
-        up8(reinterpret_cast<const V8*>(w)[v], wf);
-        up8(reinterpret_cast<const V8*>(b)[v], bf);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int g = (v * 8 + j) / cpg;
-          const float mean = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2), rstd = __ldg(stats + (static_cast<size_t>(n) * G + g) * 2 + 1);
-          const float xh = (f[j] - mean) * rstd;
-          float gg = d[j];
-          if (silu) {
-            const float y = r16(xh * wf[j] + bf[j]);
-            const float sg = 1.f / (1.f + expf(-y));
-            gg *= sg * (1.f + y * (1.f - sg));
-          }
-          gg *= wf[j];
-          s1[i][j] += gg;
-          s2[i][j] += gg * xh;
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < kGnMaxV; ++i) {
-    const int v = threadIdx.x + i * kGnThreads;
-    if (v < nvec)
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { sm[v * 8 + j] = s1[i][j]; sm[C + v * 8 + j] = s2[i][j]; }
-  }
-  __syncthreads();
-  for (int g = threadIdx.x; g < G; g += kGnThreads) {
-    float a = 0.f, c2 = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += sm[c]; c2 += sm[C + c]; }
-    float* p = partial + ((static_cast<size_t>(n) * nchunks + chunk) * G + g) * 2;
-    p[0] = a;
-    p[1] = c2;
-  }
-}
-__global__ void gn_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, int nchunks, int G, float count, int total) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int n = i / G, g = i - n * G;
-  float a = 0.f, b = 0.f;
-  for (int c = 0; c < nchunks; ++c) {
-    const float* p = partial + ((static_cast<size_t>(n) * nchunks + c) * G + g) * 2;
-    a += p[0];
-    b += p[1];
-  }
-  sums[2 * i] = a / count;
-  sums[2 * i + 1] = b / count;
-}
-__global__ void gn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                    const bf16* __restrict__ b, const float* __restrict__ stats, const float* __restrict__ sums,
-                                    const bf16* __restrict__ dres, bf16* __restrict__ dx, int HW, int C, int G, int silu, long total_vec) {
-  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (gid >= total_vec) return;
-  const int nvec = C >> 3, cpg = C / G;
-  const int v = static_cast<int>(gid % nvec);
-  const int n = static_cast<int>((gid / nvec) / HW);
-  float d[8], f[8], wf[8], bf[8], rs[8];
-  up8(reinterpret_cast<const V8*>(dy)[gid], d);
-  up8(reinterpret_cast<const V8*>(x)[gid], f);
-  up8(reinterpret_cast<const V8*>(w)[v], wf);
-  up8(reinterpret_cast<const V8*>(b)[v], bf);
-  if (dres) up8(reinterpret_cast<const V8*>(dres)[gid], rs);
-#ifdef DLLM_GN_GROUP2
-  const bool two = cpg >= 8;                                                // see gn_apply_kernel
-  const int g0 = (v * 8) / cpg;
-  const int split = two ? (g0 + 1) * cpg - v * 8 : 0;
-  const size_t s0 = (static_cast<size_t>(n) * G + g0) * 2, s1 = (static_cast<size_t>(n) * G + min(g0 + 1, G - 1)) * 2;
-  float st0[4] = {0.f, 0.f, 0.f, 0.f}, st1[4] = {0.f, 0.f, 0.f, 0.f};         // {mean, rstd, m1, m2} of the two groups
-  if (two) {
-    st0[0] = __ldg(stats + s0); st0[1] = __ldg(stats + s0 + 1); st0[2] = __ldg(sums + s0); st0[3] = __ldg(sums + s0 + 1);
-    st1[0] = __ldg(stats + s1); st1[1] = __ldg(stats + s1 + 1); st1[2] = __ldg(sums + s1); st1[3] = __ldg(sums + s1 + 1);
-  }
-#endif
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-#ifdef DLLM_GN_GROUP2
-    float mean, rstd, m1, m2;
-    if (two) {
-      const bool first = j < split;
-      mean = first ? st0[0] : st1[0]; rstd = first ? st0[1] : st1[1]; m1 = first ? st0[2] : st1[2]; m2 = first ? st0[3] : st1[3];
-    } else {
-      const int g = (v * 8 + j) / cpg;
-      const size_t si = (static_cast<size_t>(n) * G + g) * 2;
-      mean = __ldg(stats + si); rstd = __ldg(stats + si + 1); m1 = __ldg(sums + si); m2 = __ldg(sums + si + 1);
-    }
-#else
-    const int g = (v * 8 + j) / cpg;
-    const size_t si = (static_cast<size_t>(n) * G + g) * 2;
-    const float mean = __ldg(stats + si), rstd = __ldg(stats + si + 1);
-    const float m1 = __ldg(sums + si), m2 = __ldg(sums + si + 1);
-#endif
-    const float xh = (f[j] - mean) * rstd;
-    float gg = d[j];
-    if (silu) {
-      const float y = r16(xh * wf[j] + bf[j]);
-      const float sg = 1.f / (1.f + expf(-y));
-      gg *= sg * (1.f + y * (1.f - sg));
-    }
-    gg *= wf[j];
-    float o = rstd * (gg - m1 - xh * m2);
-    if (dres) o += rs[j];
-    d[j] = o;
-  }
-  reinterpret_cast<V8*>(dx)[gid] = pk8(d);
-}
+// (kernels: gn_partial_kernel<true> / gn_finalize_kernel(eps < 0) / gn_apply_kernel<true> above)
 // stats: [N, G, 2] {mean, rstd} from the forward (groupnorm_stats); workspace as in the forward
 int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void* b, const float* stats, const void* dres, void* dx,
                        void* workspace, size_t ws_bytes, int N, int HW, int C, int G, int silu, cudaStream_t s) {
   DLLM_REQUIRE_ALIGN16(dy, x, w, b, dres, dx);
-  if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
-  if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
-  const int rows = gn_rows(HW);
+  if (int rc = gn_check(N, HW, C, G, ws_bytes)) return rc;
+  const GnMap m = gn_map(C);
+  const int rows = gn_rows(HW, N);
   const int nchunks = (HW + rows - 1) / rows;
   float* partial = static_cast<float*>(workspace);
   float* sums = partial + static_cast<size_t>(N) * nchunks * G * 2;
-  gn_bwd_partial_kernel<<<dim3(nchunks, N), kGnThreads, 2 * C * sizeof(float), s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w,
-                                                                                   (const bf16*)b, stats, partial, HW, C, G, rows, silu);
-  gn_bwd_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, sums, nchunks, G, static_cast<float>(HW) * (C / G), N * G);
-  const long total_vec = static_cast<long>(N) * HW * (C / 8);
-  gn_bwd_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, s>>>((const bf16*)dy, (const bf16*)x, (const bf16*)w,
-                                                                                   (const bf16*)b, stats, sums, (const bf16*)dres,
-                                                                                   (bf16*)dx, HW, C, G, silu, total_vec);
+  gn_partial_kernel<true><<<dim3(nchunks, N), m.threads, static_cast<size_t>(m.RL) * 2 * C * sizeof(float), s>>>(
+      (const bf16*)x, (const bf16*)dy, (const bf16*)w, (const bf16*)b, stats, partial, HW, C, G, rows, m.RL, silu);
+  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, sums, nchunks, G, static_cast<float>(HW) * (C / G), -1.f, N * G);
+  int arows = 32;
+  while (arows > m.RL && static_cast<long>(N) * ((HW + arows - 1) / arows) < 4 * 148) arows /= 2;
+  gn_apply_kernel<true><<<dim3((HW + arows - 1) / arows, N), m.threads, 0, s>>>((const bf16*)x, (const bf16*)dy, (const bf16*)w,
+                                                                                (const bf16*)b, stats, sums, (const bf16*)dres, (bf16*)dx,
+                                                                                HW, C, G, arows, m.RL, silu);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 // forward statistics only ([N, G, 2]) — kept by the training path for the backward
 int groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, cudaStream_t s) {
   DLLM_REQUIRE_ALIGN16(x);
-  if (C % 8 || C % G || C > kGnThreads * kGnMaxV * 8 || N <= 0) return DLLM_ERR_SHAPE;
-  if (ws_bytes < groupnorm_workspace(N, HW, G)) return DLLM_ERR_SHAPE;
-  const int rows = gn_rows(HW);
-  const int nchunks = (HW + rows - 1) / rows;
-  float* partial = static_cast<float*>(workspace);
-  gn_partial_kernel<<<dim3(nchunks, N), kGnThreads, 2 * C * sizeof(float), s>>>((const bf16*)x, partial, HW, C, G, rows);
-  gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, stats, nchunks, G, static_cast<float>(HW) * (C / G), eps, N * G);
+  if (int rc = gn_check(N, HW, C, G, ws_bytes)) return rc;
+  gn_launch_stats((const bf16*)x, stats, static_cast<float*>(workspace), N, HW, C, G, eps, s);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 int groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
                     cudaStream_t s) {
   DLLM_REQUIRE_ALIGN16(x, w, b, y);
-  const long total_vec = static_cast<long>(N) * HW * (C / 8);
-  gn_apply_kernel<<<static_cast<unsigned>((total_vec + 255) / 256), 256, 0, s>>>((const bf16*)x, (const bf16*)w, (const bf16*)b, stats,
-                                                                               (bf16*)y, HW, C, G, silu, total_vec);
+  if (C % 8 || C % G || (C >> 3) > kGnMaxThreads || N <= 0) return DLLM_ERR_SHAPE;
+  gn_launch_apply((const bf16*)x, (const bf16*)w, (const bf16*)b, stats, (bf16*)y, N, HW, C, G, silu, s);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 

@@ -23,6 +23,7 @@ import torch.nn as nn
 import torch.utils.checkpoint
 
 from . import ops
+from .ddp import grad_out_view
 
 BF16 = torch.bfloat16
 
@@ -233,6 +234,10 @@ class _LayerMeta:
     seqlens: torch.Tensor | None
     wqkv: torch.Tensor          # fused [3H, H] view
     wgu: torch.Tensor           # fused [2I, H] view
+    p_qkv: tuple = ()           # the Parameters behind the fused views / o_proj / down_proj: their `_dllm_grad_view` (set by a gradient
+    p_gu: tuple = ()            # reducer or sharded optimizer) lets the wgrad GEMMs write straight into the flat gradient bucket
+    p_o: tuple = ()
+    p_d: tuple = ()
 
 
 class _DecoderLayerFn(torch.autograd.Function):
@@ -278,19 +283,19 @@ class _DecoderLayerFn(torch.autograd.Function):
             dy2 = dy2.contiguous()
         # ---- MLP
         dact = ops.linear_dgrad(dy2, wd)
-        dwd = ops.linear_wgrad(dy2, act) if need[9] else None
+        dwd = ops.linear_wgrad(dy2, act, out=grad_out_view(meta.p_d)) if need[9] else None
         dgu = ops.swiglu_bwd(dact, gu, I)
         del dact
         dh2 = ops.linear_dgrad(dgu, meta.wgu)
         dwg = dwu = None
         if need[7] or need[8]:
-            dwgu = ops.linear_wgrad(dgu, h2)
+            dwgu = ops.linear_wgrad(dgu, h2, out=grad_out_view(meta.p_gu))
             dwg, dwu = dwgu[:I], dwgu[I:]
         del dgu
         dxmid, dw_post = ops.rmsnorm_bwd(dh2, xmid, w_post, rstd2, dres=dy2, need_dw=need[6])
         # ---- attention
         dao = ops.linear_dgrad(dxmid, wo)
-        dwo = ops.linear_wgrad(dxmid, ao2) if need[5] else None
+        dwo = ops.linear_wgrad(dxmid, ao2, out=grad_out_view(meta.p_o)) if need[5] else None
         dqkv = torch.empty_like(qkv)
         q4 = qkv.view(B, S, 3, nh, d)
         dq4 = dqkv.view(B, S, 3, nh, d)
@@ -300,7 +305,7 @@ class _DecoderLayerFn(torch.autograd.Function):
         dh1 = ops.linear_dgrad(dqkv, meta.wqkv)
         dwq = dwk = dwv = None
         if need[2] or need[3] or need[4]:
-            dwqkv = ops.linear_wgrad(dqkv, h1)
+            dwqkv = ops.linear_wgrad(dqkv, h1, out=grad_out_view(meta.p_qkv))
             dwq, dwk, dwv = dwqkv[:H], dwqkv[H:2 * H], dwqkv[2 * H:]
         dx, dw_in = ops.rmsnorm_bwd(dh1, x2, w_in, rstd1, dres=dxmid, need_dw=need[1])
         return (dx.view(B, S, H) if need[0] else None, dw_in, dwq, dwk, dwv, dwo, dw_post, dwg, dwu, dwd, None)
@@ -380,7 +385,9 @@ class DreamLLMDecoderLayer(nn.Module):
         meta = _LayerMeta(att.num_heads, att.head_dim, self.mlp.intermediate_size, self.input_layernorm.variance_epsilon,
                           B, S, pos, cos, sin, seqlens,
                           _fuse_rows([att.q_proj.weight, att.k_proj.weight, att.v_proj.weight]),
-                          _fuse_rows([self.mlp.gate_proj.weight, self.mlp.up_proj.weight]))
+                          _fuse_rows([self.mlp.gate_proj.weight, self.mlp.up_proj.weight]),
+                          (att.q_proj.weight, att.k_proj.weight, att.v_proj.weight), (self.mlp.gate_proj.weight, self.mlp.up_proj.weight),
+                          (att.o_proj.weight,), (self.mlp.down_proj.weight,))
         y = _DecoderLayerFn.apply(hidden_states, self.input_layernorm.weight, att.q_proj.weight, att.k_proj.weight,
                                   att.v_proj.weight, att.o_proj.weight, self.post_attention_layernorm.weight,
                                   self.mlp.gate_proj.weight, self.mlp.up_proj.weight, self.mlp.down_proj.weight, meta)
@@ -425,16 +432,18 @@ class DreamLLMDecoderLayer(nn.Module):
 # ------------------------------------------------------------------------------------------------ model
 class _EmbeddingFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, ids, weight):
-        ctx.save_for_backward(ids)
+    def forward(ctx, ids, weight, padding_idx=None):
+        ctx.save_for_backward(ids, weight)
         ctx.vocab = weight.shape[0]
+        ctx.padding_idx = padding_idx
         return ops.embedding_fwd(ids, weight)
 
     @staticmethod
     def backward(ctx, dy):
-        (ids,) = ctx.saved_tensors
+        ids, weight = ctx.saved_tensors
         H = dy.shape[-1]
-        return None, ops.embedding_bwd(ids, dy.reshape(-1, H).contiguous(), ctx.vocab)
+        return None, ops.embedding_bwd(ids, dy.reshape(-1, H).contiguous(), ctx.vocab, out=grad_out_view((weight,)),
+                                       padding_idx=ctx.padding_idx), None
 
 
 class _LMHeadLossFn(torch.autograd.Function):
@@ -452,7 +461,7 @@ class _LMHeadLossFn(torch.autograd.Function):
     def backward(ctx, dloss):
         h2, weight, dlogits = ctx.saved_tensors
         dh = ops.linear_dgrad(dlogits, weight) if ctx.needs_input_grad[0] else None
-        dw = ops.linear_wgrad(dlogits, h2) if ctx.needs_input_grad[1] else None
+        dw = ops.linear_wgrad(dlogits, h2, out=grad_out_view((weight,))) if ctx.needs_input_grad[1] else None
         g = dloss.to(BF16)
         if dh is not None:
             dh.mul_(g)
@@ -699,7 +708,7 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
         if input_ids is None and inputs_embeds is None:
             raise ValueError("You have to specify either input_ids or inputs_embeds")
         if inputs_embeds is None:
-            inputs_embeds = _EmbeddingFn.apply(input_ids, self.embed_tokens.weight)
+            inputs_embeds = _EmbeddingFn.apply(input_ids, self.embed_tokens.weight, self.embed_tokens.padding_idx)
         if attention_mask_has_padding is False:
             attention_mask = None
             seqlens = None
@@ -792,7 +801,7 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
         if input_ids is None:
             raise ValueError("image / dream splicing needs input_ids")
         if inputs_embeds is None:
-            inputs_embeds = _EmbeddingFn.apply(input_ids, self.embed_tokens.weight)
+            inputs_embeds = _EmbeddingFn.apply(input_ids, self.embed_tokens.weight, self.embed_tokens.padding_idx)
         image_features = self.clip_vision_embedding(images) if images is not None else None
         dq = self.dream_embedding.dream_queries if images_dm is not None else None
         if splice_plan is None:

@@ -230,13 +230,21 @@ def embedding_fwd(ids, weight):
     return out
 
 
-def embedding_bwd(ids, dy2d, vocab):
-    _chk_cuda(ids, dy2d)
+def embedding_bwd(ids, dy2d, vocab, out=None, padding_idx=None):
+    """dW[v] = sum of dy rows whose id is v (deterministic: ids sorted, one segment per row).  `out` = preallocated [vocab, H] (e.g. the
+    gradient-bucket slice); `padding_idx` row gets no gradient, as nn.Embedding (reference modeling_dreamllm.py:814)."""
+    _chk_cuda(ids, dy2d, out)
     T, H = dy2d.shape
     sorted_ids, order = torch.sort(ids.reshape(-1), stable=True)
-    dW = torch.zeros((vocab, H), device=dy2d.device, dtype=dy2d.dtype)
+    if out is None:
+        dW = torch.zeros((vocab, H), device=dy2d.device, dtype=dy2d.dtype)
+    else:
+        assert out.shape == (vocab, H) and out.is_contiguous() and out.dtype == dy2d.dtype
+        dW = out.zero_()
     check(lib().dllm_embedding_bwd(_p(sorted_ids), _p(order), _p(dy2d), _p(dW), T, H, 0, _stream()), "dllm_embedding_bwd")
     LAUNCHES.add(1)
+    if padding_idx is not None and 0 <= int(padding_idx) < vocab:
+        dW[int(padding_idx)].zero_()
     return dW
 
 

@@ -516,10 +516,16 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale: float):
 
 
 class DenoiseLoop:
-    """N-step sampler: one CUDA graph of {time embedding -> UNet -> fused CFG + scheduler update}, replayed N times."""
+    """N-step sampler.  The step {time embedding -> UNet -> fused CFG + scheduler update -> step counter += 1} reads its timestep and
+    scheduler coefficients from device tables indexed by a device-side step counter, so it is position-independent:
+      * `whole_loop_graph=True` (default): ALL N steps are captured into ONE CUDA graph and `run()` is a single `graph.replay()` — the host
+        is out of the loop entirely (the "CUDA-graph-captured persistent loop" of the north star; reference: the Python `for t in
+        timesteps` loop of modeling_plugins.py:809-833);
+      * with a `callback` (which must observe the latents between steps, :836-839) one single-step graph is replayed N times."""
 
     def __init__(self, unet: UNet2DConditionModel, cond, num_inference_steps=50, guidance_scale=7.5, scheduler="ddim",
-                 latents=None, noise=None, height=512, width=512, use_cuda_graph=True, generator=None, guidance_rescale: float = 0.0):
+                 latents=None, noise=None, height=512, width=512, use_cuda_graph=True, generator=None, guidance_rescale: float = 0.0,
+                 whole_loop_graph: bool = True):
         """cond: [B, Q, ctx] projected prompt embeddings, or [2B, Q, ctx] = cat([negative, positive]) when guidance_scale > 1
         (reference order, modeling_plugins.py:774-784)."""
         self.unet = unet
@@ -545,8 +551,33 @@ class DenoiseLoop:
                           else noise.to(dev)).float().contiguous()
         self.cross_kv = unet.precompute_cross_kv(cond)
         self.eps = torch.empty((self.nb, 4, h, w), device=dev, dtype=torch.float32)
-        self.graph = None
+        self.graph = None              # single-step graph (callback path)
+        self.loop_graph = None         # all N steps in one graph
         self.use_cuda_graph = use_cuda_graph
+        self.whole_loop_graph = whole_loop_graph
+        self._latents0 = self.latents.clone()
+
+    def reset(self, latents=None):
+        """Rewind to step 0 with the initial (or the given) latents — the captured graphs stay valid (static buffers)."""
+        self.step.zero_()
+        self.latents.copy_(self._latents0 if latents is None else latents.to(self.latents.dtype))
+
+    def _capture(self, n_steps):
+        lat0, st0 = self.latents.clone(), self.step.clone()
+        s = torch.cuda.Stream()                      # warm up on a side stream (allocator + lazy attribute setup), then restore state
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._one_step()
+        torch.cuda.current_stream().wait_stream(s)
+        self.latents.copy_(lat0)
+        self.step.copy_(st0)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(n_steps):
+                self._one_step()
+        self.latents.copy_(lat0)
+        self.step.copy_(st0)
+        return graph
 
     def _one_step(self):
         temb_sin = ops.timestep_embedding(self.timesteps, self.step, self.nb, self.unet.cfg["block_out_channels"][0])
@@ -570,21 +601,13 @@ class DenoiseLoop:
                 self._one_step()
                 report(i)
             return self.latents
+        if self.whole_loop_graph and callback is None:
+            if self.loop_graph is None:
+                self.loop_graph = self._capture(self.N)
+            self.loop_graph.replay()
+            return self.latents
         if self.graph is None:
-            # warm up on a side stream (allocator + lazy attribute setup), then restore state and capture one step
-            lat0, st0 = self.latents.clone(), self.step.clone()
-            s = torch.cuda.Stream()
-            s.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(s):
-                self._one_step()
-            torch.cuda.current_stream().wait_stream(s)
-            self.latents.copy_(lat0)
-            self.step.copy_(st0)
-            self.graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.graph):
-                self._one_step()
-            self.latents.copy_(lat0)
-            self.step.copy_(st0)
+            self.graph = self._capture(1)
         for i in range(self.N):
             self.graph.replay()
             report(i)

@@ -69,21 +69,30 @@ def optimizer_param_groups(model, weight_decay: float) -> list:
             {"params": [p for n, p in named if n not in decay and p.requires_grad], "weight_decay": 0.0}]
 
 
-def training_step(model, optimizer, batch: dict, lr_scale: float = 1.0, accumulate: bool = False):
+def training_step(model, optimizer, batch: dict, lr_scale: float = 1.0, accumulate: bool = False, grad_accum_steps: int = 1):
     """One data-parallel training step (`Trainer.training_step` + the optimizer part of `_inner_training_loop`,
     omni/train/trainer.py:1007-1049, :744-835): forward, backward (gradient buckets reduce-scatter as they fill), and — unless this is an
-    accumulation micro-step — global-norm clip + sharded AdamW + parameter all-gather.  Returns (loss.detach(), grad_norm | None)."""
+    accumulation micro-step — global-norm clip + sharded AdamW + parameter all-gather.
+    With gradient accumulation every micro-step back-propagates `loss / grad_accum_steps` (accelerate's `backward` scales the loss by
+    1 / gradient_accumulation_steps, and `training_step` returns `loss.detach() / gradient_accumulation_steps`, trainer.py:1043-1047), so
+    the accumulated gradient — and with it `grad_norm` and the `max_grad_norm` clip — is the mean over micro-batches, as in the reference.
+    Returns (scaled loss.detach(), grad_norm | None)."""
     model.train()
+    ga = max(int(grad_accum_steps), 1)
+
+    def fwd_bwd():
+        out = model(**batch)
+        loss = out.loss / ga if ga > 1 else out.loss
+        loss.backward()
+        return loss.detach()
+
     if accumulate:
         with optimizer.no_sync():
-            out = model(**batch)
-            out.loss.backward()
-        return out.loss.detach(), None
-    out = model(**batch)
-    out.loss.backward()
+            return fwd_bwd(), None
+    loss = fwd_bwd()
     norm = optimizer.step(lr_scale=lr_scale)
     optimizer.zero_grad()
-    return out.loss.detach(), norm
+    return loss, norm
 
 
 def _cuda_update(g, p, m, v, master, **kw):
@@ -98,7 +107,7 @@ def _cuda_sumsq(g, out):
 
 class _Bucket:
     __slots__ = ("params", "n", "padded", "chunk", "flat_param", "flat_grad", "pviews", "gviews", "gshard", "pshard", "master", "m", "v",
-                 "pending", "work", "group", "gather")
+                 "pending", "seen", "ready", "launched", "work", "group", "gather")
 
 
 class ShardedAdamW:
@@ -120,6 +129,7 @@ class ShardedAdamW:
         self.launched = 0            # reduce-scatters + all-gathers issued (tests / bench bookkeeping)
         self._attached = False
         self._sync = True            # False inside no_sync(): micro-batch gradients accumulate locally, nothing goes on the wire
+        self._next = 0               # next bucket to reduce-scatter: collectives are issued in bucket order on every rank (ddp.py)
         params = list(params)
         if params and not isinstance(params[0], dict):
             params = [{"params": params}]
@@ -187,6 +197,7 @@ class ShardedAdamW:
                 p.data = pv                                   # the parameter now lives in the bucket (identity / state-dict key unchanged)
                 b.pviews[p] = pv
                 b.gviews[p] = b.flat_grad[off:off + p.numel()].view(p.shape)
+                p._dllm_grad_view = b.gviews[p]               # fused wgrad GEMMs write straight into the bucket (ddp.grad_out_view)
                 off += p.numel()
         lo = self.rank * b.chunk
         b.pshard = b.flat_param[lo:lo + b.chunk]
@@ -200,6 +211,8 @@ class ShardedAdamW:
             b.m = torch.zeros(b.chunk, dtype=torch.bfloat16, device=dev)
             b.v = torch.zeros(b.chunk, dtype=torch.bfloat16, device=dev)
         b.pending = set(plist)
+        b.seen = set()               # parameters that received a gradient since zero_grad() (any micro-batch)
+        b.ready = b.launched = False
         b.work = None
         b.gather = None
         self.buckets.append(b)
@@ -221,14 +234,21 @@ class ShardedAdamW:
         if p.grad.data_ptr() != v.data_ptr():
             v.copy_(p.grad)
             p.grad = v
+        b.seen.add(p)
         b.pending.discard(p)
-        if not b.pending:
-            if self._sync:
-                self._reduce_scatter(b)
-            else:
-                b.pending = set(b.params)      # next micro-batch accumulates in place into the same views (p.grad stays the view)
+        if not b.pending and self._sync and not b.launched:
+            b.ready = True
+            self._launch_ready()
+
+    def _launch_ready(self):
+        """In-order rule (torch DDP's): bucket i goes on the wire only after buckets 0..i-1 — every rank issues the same sequence of
+        reduce-scatters even when its batch left some parameters without a gradient (those buckets are flushed by `step()`)."""
+        while self._next < len(self.buckets) and self.buckets[self._next].ready:
+            self._reduce_scatter(self.buckets[self._next])
+            self._next += 1
 
     def _reduce_scatter(self, b):
+        b.launched = True
         if self.world == 1:
             return
         if self.backend == "nccl":
@@ -250,6 +270,9 @@ class ShardedAdamW:
                 yield
             finally:
                 self._sync = prev
+                for b in self.buckets:                 # the next backward awaits every parameter again (p.grad stays the bucket view,
+                    if not b.launched:                 # so later micro-batches accumulate in place)
+                        b.pending = set(b.params)
         return ctx()
 
     def zero_grad(self, set_to_none: bool = True):
@@ -257,6 +280,9 @@ class ShardedAdamW:
             for p in b.params:
                 p.grad = None
             b.pending = set(b.params)
+            b.seen = set()
+            b.ready = b.launched = False
+        self._next = 0
 
     # ------------------------------------------------------------------------------------------ step
     @torch.no_grad()
@@ -271,14 +297,14 @@ class ShardedAdamW:
                 if p.data.data_ptr() != b.pviews[p].data_ptr():
                     raise RuntimeError("a parameter was moved out of its optimizer bucket (module.to() / load_state_dict(assign=True) / a "
                                        "weight re-fusion after ShardedAdamW was built); call ShardedAdamW.reseat() after such changes")
-        for b in self.buckets:                                # grads that never arrived this step count as zero
-            if b.pending:
-                if len(b.pending) < len(b.params) or self.world > 1:
-                    for p in b.pending:
+        for b in self.buckets[self._next:]:                   # flush in bucket order; a parameter that received no gradient in ANY
+            if b.seen or self.world > 1:                      # micro-batch since zero_grad() counts as zero (never discard accumulated ones)
+                for p in b.params:
+                    if p not in b.seen:
                         b.gviews[p].zero_()
                         p.grad = b.gviews[p]
-                    b.pending = set()
-                    self._reduce_scatter(b)
+            self._reduce_scatter(b)
+        self._next = len(self.buckets)
         for b in self.buckets:
             if b.work is not None:
                 b.work.wait()
@@ -286,7 +312,7 @@ class ShardedAdamW:
         self.step_count += 1
         clip = self.max_grad_norm > 0
         self._ss.zero_()
-        live = [b for b in self.buckets if not b.pending]     # world == 1 and no grad at all in a bucket: skip it (torch skips p.grad None)
+        live = [b for b in self.buckets if b.seen or self.world > 1]   # single process, no grad at all in a bucket: skip it (torch skips p.grad None)
         for b in live:
             self._sumsq(b.gshard, self._ss)
         if self.world > 1:
@@ -305,6 +331,8 @@ class ShardedAdamW:
             self.wait_gathers()
         for b in self.buckets:
             b.pending = set(b.params)
+            b.ready = b.launched = False
+        self._next = 0
         return self._ss.sqrt().squeeze(0)
 
     def wait_gathers(self, buckets=None):

@@ -411,3 +411,139 @@ def test_training_step_glue_with_groups_and_accumulation():
     assert all(p.grad is None for p in m.parameters())                            # zero_grad after the step
     losses = [float(training_step(m, opt, dict(x=x))[0]) for _ in range(25)]
     assert losses[-1] < 0.5 * losses[0]
+
+
+# ------------------------------------------------------------------------------------------------ ranks with different unused parameters
+class BranchNet(nn.Module):
+    """`proj` is only used when the batch carries "images" (stage-2 interleaved data: a text-only rank produces no gradient for the CLIP /
+    SD projectors and the dream queries, modeling_plugins.py:242)."""
+
+    def __init__(self):
+        super().__init__()
+        self.body = nn.Linear(24, 24, bias=False)
+        self.head = nn.Linear(24, 7, bias=False)
+        self.proj = nn.Linear(24, 24, bias=False)
+
+    def forward(self, x, use_proj):
+        h = torch.tanh(self.body(x))
+        if use_proj:
+            h = h + self.proj(x)
+        return self.head(h)
+
+
+def _branch_net():
+    torch.manual_seed(3)
+    return BranchNet().to(BF)
+
+
+def _uneven_worker(rank, world, port, q, kind):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    net = _branch_net()
+    x = _data()
+    if kind == "zero":
+        opt = _make(net, max_grad_norm=0.0, state_dtype=torch.float32)
+        for _ in range(2):
+            opt.zero_grad()
+            net(x[rank * 4:(rank + 1) * 4], use_proj=(rank == 0)).float().pow(2).mean().backward()
+            opt.step()
+        q.put((rank, {k: v.detach().clone() for k, v in net.named_parameters()}))
+    else:
+        from dreamllm_b200.ddp import BucketedGradReducer
+        red = BucketedGradReducer(net.parameters(), bucket_cap_mb=0.001)
+        assert len(red.buckets) >= 3
+        for _ in range(2):
+            red.zero_grad()
+            net(x[rank * 4:(rank + 1) * 4], use_proj=(rank == 0)).float().pow(2).mean().backward()
+            red.finalize()
+        q.put((rank, {k: v.grad.detach().clone() for k, v in net.named_parameters()}))
+    dist.destroy_process_group()
+
+
+def _run_uneven(kind):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_uneven_worker, args=(r, 2, port, q, kind)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        res = [q.get(timeout=240) for _ in range(2)]
+    finally:
+        for p in procs:
+            p.join(timeout=60)
+            if p.is_alive():
+                p.kill()
+    assert all(p.exitcode == 0 for p in procs)
+    return sorted(res, key=lambda r: r[0])
+
+
+@pytest.mark.parametrize("kind", ["ddp", "zero"])
+def test_ranks_with_different_unused_parameters_issue_matching_collectives(kind):
+    """Only rank 0's batch touches `proj`.  Collectives must still pair up (bucket-order launch rule): before the fix rank 1 flushed the
+    proj bucket at the end while rank 0 launched it mid-backward -> gloo 'Received data size doesn't match', NCCL hang."""
+    try:
+        res = _run_uneven(kind)
+    except Exception:
+        res = _run_uneven(kind)
+    (_, a), (_, b) = res
+    for k in a:
+        assert torch.equal(a[k], b[k]), f"ranks diverged on {k}"
+    if kind == "ddp":                         # proj's averaged gradient = rank 0's half; rank 1 contributed zeros
+        net = _branch_net()
+        x = _data()
+        net(x[:4], use_proj=True).float().pow(2).mean().backward()
+        torch.testing.assert_close(a["proj.weight"].float(), net.proj.weight.grad.float() / 2, rtol=2 ** -7, atol=1e-6)
+        assert float(a["proj.weight"].float().abs().sum()) > 0
+    else:
+        assert not torch.equal(a["proj.weight"], _branch_net().proj.weight.detach())      # the weight moved on both ranks
+
+
+def test_accumulated_gradient_survives_a_micro_batch_that_skips_the_parameter():
+    """ADVICE r1 (zero.py:277): micro-step 1 (no_sync) uses `proj`, micro-step 2 (synced) is 'text-only'.  The accumulated proj gradient
+    must reach the optimizer, and the bucket must be reduced exactly once."""
+    net = _branch_net()
+    opt = _make(net, max_grad_norm=0.0, state_dtype=torch.float32)
+    x = _data()
+    before = net.proj.weight.detach().clone()
+    opt.zero_grad()
+    with opt.no_sync():
+        net(x[:4], use_proj=True).float().pow(2).mean().backward()
+    g1 = net.proj.weight.grad.detach().clone()
+    assert float(g1.float().abs().sum()) > 0
+    net(x[4:], use_proj=False).float().pow(2).mean().backward()
+    assert torch.equal(net.proj.weight.grad, g1)                       # untouched by the second micro-batch ...
+    launched_before = sum(b.launched for b in opt.buckets)
+    opt.step()
+    assert launched_before < len(opt.buckets)                           # ... its bucket was flushed by step(), once
+    assert not torch.equal(net.proj.weight.detach(), before)            # ... and it stepped the weight
+
+
+def test_training_step_scales_the_loss_by_grad_accum_steps():
+    """accelerate.backward / Trainer.training_step (omni/train/trainer.py:1043-1047): each micro-batch back-propagates loss / GA, so the
+    accumulated gradient (hence grad_norm and the clip threshold) is the mean over micro-batches."""
+    from types import SimpleNamespace
+
+    from dreamllm_b200.zero import ShardedAdamW, training_step
+
+    class Wrapped(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.net = _net()
+
+        def forward(self, x):
+            return SimpleNamespace(loss=self.net(x).float().pow(2).mean())
+    x = _data()
+    norms, losses = {}, {}
+    for ga in (1, 2):
+        m = Wrapped()
+        opt = ShardedAdamW(m.parameters(), lr=0.0, max_grad_norm=1e9, bucket_cap_mb=0.001, update_fn=AO.adamw_flat_, sumsq_fn=AO.sumsq_flat)
+        if ga == 1:
+            losses[ga], norms[ga] = training_step(m, opt, dict(x=x[:4]))
+        else:
+            l0, _ = training_step(m, opt, dict(x=x[:4]), accumulate=True, grad_accum_steps=2)
+            l1, norms[ga] = training_step(m, opt, dict(x=x[:4]), grad_accum_steps=2)
+            losses[ga] = l0 + l1
+    torch.testing.assert_close(losses[2], losses[1], rtol=1e-6, atol=0)         # two half-weighted copies of the same micro-batch
+    torch.testing.assert_close(norms[2], norms[1], rtol=2e-2, atol=0)           # not 2x: bf16 accumulation of two halves
