@@ -26,7 +26,10 @@ CASES = [
     ("tiny", 256, 512, 2, 2, 48, 11, 0),
     ("ragged", 256, 384, 2, 2, 200, 12, 37),
     ("mid", 512, 1408, 4, 1, 384, 13, 0),
+    # BASELINE.json configs[0] itself: Vicuna-7B layer, hidden 4096, 32 heads, seq 512, bs 1 (y / dx stored strided to keep the file small)
+    ("c1", 4096, 11008, 32, 1, 512, 14, 0),
 ]
+STRIDED = {"c1": (4, 8)}        # name -> (row step, column step) of the stored y / dx
 
 
 def make_inputs(hidden, bsz, seq, seed):
@@ -66,6 +69,11 @@ def run_reference(ns, name, hidden, inter, heads, bsz, seq, seed, pad):
         "y": y.detach().numpy().astype(np.float32),
         "dx": x.grad.numpy().astype(np.float32),
     }
+    if name in STRIDED:
+        rs, cs = STRIDED[name]
+        out["stride"] = np.array([rs, cs], dtype=np.int64)
+        out["y_abs_sum"], out["dx_abs_sum"] = np.float64(checksum(y.detach())), np.float64(checksum(x.grad))
+        out["y"], out["dx"] = out["y"][:, ::rs, ::cs].copy(), out["dx"][:, ::rs, ::cs].copy()
     for k, prm in layer.named_parameters():
         g = prm.grad
         out["d_" + k] = (g[:8, :64] if g.dim() == 2 else g).numpy().astype(np.float32)
@@ -78,7 +86,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     ns = ref_exec.load_reference_namespace()
+    only = set(sys.argv[1:])
     for case in CASES:
+        if only and case[0] not in only:
+            continue
         out = run_reference(ns, *case)
         path = os.path.join(OUT, f"decoder_layer_{case[0]}.npz")
         np.savez_compressed(path, **out)

@@ -86,3 +86,61 @@ def test_token_index_paths_bit_exact():
     l1 = m(input_ids=ids).logits
     l2 = m(input_ids=ids).logits
     assert torch.equal(l1.argmax(-1), l2.argmax(-1)) and torch.equal(l1, l2)
+
+
+def test_argmax_and_greedy_ids_vs_bf16_oracle():
+    """Token-id paths against the ORACLE (the r1 tests compared the CUDA model with itself).  The bf16 oracle is
+    bit-identical to the reference's bf16 path (tests/test_oracle_pin.py), so wherever the top-1 margin of the fp32 logits exceeds twice
+    the bf16 error budget the argmax — and with it every greedily decoded id — must agree exactly:
+      * budget e = 2 x max|logits(ref bf16) - logits(ref fp32)|  (the like-for-like criterion of DESIGN.md §2, measured here);
+      * our logits must stay inside it, the margin rule must cover most positions (otherwise the test is vacuous), and on those positions
+        argmax(ours) == argmax(ref bf16) == argmax(ref fp32);
+      * greedy decoding through the kv-cache path reproduces the oracle's greedy ids (full re-forward on the CPU each step) for as long as
+        every decoded position is a clear-margin one."""
+    from dreamllm_b200.modeling_dreamllm import DreamLLMConfig, DreamLLMForCausalMLM
+    hidden, inter, heads, layers, vocab, B, S = 256, 512, 2, 2, 512, 2, 96
+    cfg = DreamLLMConfig(vocab_size=vocab, hidden_size=hidden, intermediate_size=inter, num_hidden_layers=layers, num_attention_heads=heads)
+    torch.manual_seed(7)
+    model = DreamLLMForCausalMLM(cfg)
+    with torch.no_grad():                                  # N(0, 0.02) init gives near-uniform logits; widen the head so margins are real
+        model.lm_head.weight.mul_(8.0)
+    model = model.to(device="cuda", dtype=BF).eval()
+    ids = torch.randint(0, vocab, (B, S), generator=torch.Generator().manual_seed(8))
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+
+    def oracle_logits(x_ids, dtype):
+        emb = sd["model.embed_tokens.weight"].to(dtype)
+        lay = [{k: sd[f"model.layers.{i}.{k}"].to(dtype) for k in O.LAYER_KEYS} for i in range(layers)]
+        with torch.no_grad():
+            return O.causal_lm(x_ids, None, emb, lay, sd["model.norm.weight"].to(dtype), sd["lm_head.weight"].to(dtype), heads)[1]
+
+    l32, lbf = oracle_logits(ids, torch.float32), oracle_logits(ids, BF)
+    with torch.no_grad():
+        ours = model(input_ids=ids.cuda()).logits.float().cpu()
+    budget = 2.0 * float((lbf - l32).abs().max())
+    assert float((ours - l32).abs().max()) <= budget, (float((ours - l32).abs().max()), budget)
+    top2 = l32.topk(2, dim=-1).values
+    clear = (top2[..., 0] - top2[..., 1]) > 2 * budget
+    assert float(clear.float().mean()) > 0.5, f"only {float(clear.float().mean()):.2f} of the positions have a clear top-1 margin"
+    assert torch.equal(ours.argmax(-1)[clear], l32.argmax(-1)[clear])
+    assert torch.equal(ours.argmax(-1)[clear], lbf.argmax(-1)[clear])
+
+    # greedy decode (kv-cache path) vs the oracle's greedy ids
+    prompt = ids[:, :24]
+    n_new = 12
+    got = model.generate(prompt.cuda(), max_new_tokens=n_new, do_sample=False).cpu()
+    assert torch.equal(got[:, :24], prompt)
+    cur = prompt.clone()
+    compared = 0
+    alive = torch.ones(B, dtype=torch.bool)
+    for step in range(n_new):
+        lg32, lgbf = oracle_logits(cur, torch.float32)[:, -1], oracle_logits(cur, BF)[:, -1]
+        t2 = lg32.topk(2, dim=-1).values
+        alive &= (t2[:, 0] - t2[:, 1]) > 2 * budget                      # once a near-tie is decoded the continuations may differ
+        nxt = lgbf.argmax(-1)
+        for b in range(B):
+            if alive[b]:
+                assert int(got[b, 24 + step]) == int(nxt[b]), (b, step, int(got[b, 24 + step]), int(nxt[b]))
+                compared += 1
+        cur = torch.cat([cur, got[:, 24 + step: 25 + step]], dim=1)         # follow OUR sequence so later steps stay comparable
+    assert compared >= B * 3, compared
