@@ -88,6 +88,7 @@ SIGNATURES = {
     "dllm_zero_rows": (_i, [_vp, _vp, _i, _i, _vp]),
     "dllm_attn_fwd_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _l, _l, _l, _i, _f, _vp]),
     "dllm_attn_fwd_cache": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _l, _l, _l, _i, _f, _vp]),
+    "dllm_attn_fwd_cache_mask": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _l, _l, _l, _i, _f, _vp]),
     "dllm_conv3x3_nhwc": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dllm_groupnorm_workspace_bytes": (_sz, [_i, _i, _i]),
     "dllm_groupnorm_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _i, _vp]),

@@ -109,7 +109,10 @@ template <int D, bool kCausal>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, float* __restrict__ lse,
-                const int* __restrict__ seqlens, int S, int Skv, int nh, float scale_log2) {
+                const int* __restrict__ seqlens, int S, int Skv, int nh, float scale_log2,
+                const uint8_t* __restrict__ kv_mask, int mask_ld) {
+  // kv_mask (nullable): [B, mask_ld] bytes, 0 = padded key position that no query may attend to — the 2-D `attention_mask` of a padded
+  // batch living inside a kv-cache (reference :553-583 drops those tokens with `_upad_input`; HF left-pads decoder-only prompts)
   // causal with Skv > S = kv-cache decode / continuation (reference :344-355, :444-449): query i sits at absolute position
   // (Skv - S) + i, i.e. the mask is bottom-right aligned:  kv <= q + coff
   const int coff = kCausal ? (Skv - S) : 0;
@@ -209,13 +212,25 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       tmem_ld32(tmem_S + lane_off + (j & 1) * 64 + 32, sv + 32);
       tmem_ld_wait();
       const int kv0 = j * 64;
-      const bool need_mask = (kCausal && kv0 + 63 > q0 + warp * 32 + coff) || (kv0 + 64 > kv_len);
+      const bool need_mask = (kCausal && kv0 + 63 > q0 + warp * 32 + coff) || (kv0 + 64 > kv_len) || (kv_mask != nullptr);
       float mx = -INFINITY;
       if (need_mask) {
+        uint32_t mw[16];                                      // this tile's 64 key-mask bytes (all-ones when there is no mask)
+        if (kv_mask != nullptr) {
+          const uint4* mp = reinterpret_cast<const uint4*>(kv_mask + static_cast<size_t>(b) * mask_ld + kv0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint4 t = __ldg(mp + i);
+            mw[4 * i] = t.x; mw[4 * i + 1] = t.y; mw[4 * i + 2] = t.z; mw[4 * i + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) mw[i] = 0x01010101u;
+        }
 #pragma unroll
         for (int c = 0; c < 64; ++c) {
           const int kvi = kv0 + c;
-          const bool ok = (kvi < kv_len) && (!kCausal || kvi <= q_row + coff);
+          const bool ok = (kvi < kv_len) && (!kCausal || kvi <= q_row + coff) && (((mw[c >> 2] >> (8 * (c & 3))) & 0xffu) != 0u);
           float s = ok ? __uint_as_float(sv[c]) : -INFINITY;
           sv[c] = __float_as_uint(s);
           mx = fmaxf(mx, s);
@@ -722,7 +737,8 @@ static int set_smem(K kern, int bytes) {
 
 template <int D, bool C>
 static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
-                      const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st) {
+                      const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st,
+                      const uint8_t* kv_mask = nullptr, int mask_ld = 0) {
   auto kern = attn_fwd_kernel<D, C>;
   static bool once = false;
   if (!once) {
@@ -731,7 +747,7 @@ static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtens
     once = true;
   }
   dim3 grid((S + 127) / 128, nh, B);
-  kern<<<grid, kAttnThreads, FwdSmem<D>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, Skv, nh, scale_log2);
+  kern<<<grid, kAttnThreads, FwdSmem<D>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, Skv, nh, scale_log2, kv_mask, mask_ld);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
@@ -750,7 +766,17 @@ int attn_fwd_ex(const void* q, const void* k, const void* v, void* out, float* l
 // place with Skv valid rows.  causal with Skv > S uses the bottom-right aligned mask (decode / continuation).
 int attn_fwd_cache(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int Skv,
                    int kv_rows, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, cudaStream_t st) {
+  return attn_fwd_cache_mask(q, k, v, out, lse, seqlens, nullptr, 0, B, S, Skv, kv_rows, nh, d, ld_q, ld_kv, ld_o, causal, scale, st);
+}
+
+// + kv_mask [B, mask_ld] bytes (0 = padded key): a padded prompt batch inside the kv-cache.  mask_ld must cover whole 64-key tiles
+// (mask_ld % 16 == 0, mask_ld >= round_up(Skv, 64)) because the kernel fetches the mask 64 bytes at a time.
+int attn_fwd_cache_mask(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, const void* kv_mask,
+                        int mask_ld, int B, int S, int Skv, int kv_rows, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal,
+                        float scale, cudaStream_t st) {
   if (B <= 0 || S <= 0 || Skv <= 0 || nh <= 0 || kv_rows < Skv) return DLLM_ERR_SHAPE;
+  if (kv_mask && ((mask_ld & 15) || mask_ld < (Skv + 63) / 64 * 64 || (reinterpret_cast<uintptr_t>(kv_mask) & 15))) return DLLM_ERR_ALIGN;
+  const uint8_t* km = static_cast<const uint8_t*>(kv_mask);
   if (d != 128 && d != 64) return DLLM_ERR_UNSUPPORTED;
   if (S != Skv && seqlens) return DLLM_ERR_UNSUPPORTED;
   if (causal && Skv < S) return DLLM_ERR_SHAPE;
@@ -761,10 +787,10 @@ int attn_fwd_cache(const void* q, const void* k, const void* v, void* out, float
   if ((rc = make_tmap_bsc(&tv, v, B, kv_rows, nh * d, ld_kv, 64))) return rc;
   if ((rc = make_tmap_bsc(&to, out, B, S, nh * d, ld_o, 32))) return rc;
   const float sl2 = scale * kLog2e;
-  if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st)
-                              : launch_fwd<128, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st);
-  return causal ? launch_fwd<64, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st)
-                : launch_fwd<64, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st);
+  if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld)
+                              : launch_fwd<128, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld);
+  return causal ? launch_fwd<64, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld)
+                : launch_fwd<64, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld);
 }
 
 static inline int s_pad(int S) { return (S + 63) / 64 * 64; }

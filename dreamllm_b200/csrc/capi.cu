@@ -156,6 +156,12 @@ int dllm_attn_fwd_cache(const void* q, const void* k, const void* v, void* out, 
   ensure_context(q);
   return attn_fwd_cache(q, k, v, out, lse, nullptr, B, Sq, Skv, kv_rows, nh, d, ld_q, ld_kv, ld_o, causal, scale, S(stream));
 }
+int dllm_attn_fwd_cache_mask(const void* q, const void* k, const void* v, void* out, float* lse, const void* kv_mask, int mask_ld, int B,
+                             int Sq, int Skv, int kv_rows, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale,
+                             void* stream) {
+  return attn_fwd_cache_mask(q, k, v, out, lse, nullptr, kv_mask, mask_ld, B, Sq, Skv, kv_rows, nh, d, ld_q, ld_kv, ld_o, causal, scale,
+                             S(stream));
+}
 int dllm_conv3x3_nhwc(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, const void* bias,
                       const void* rowbias, const void* residual, void* stream) {
   ensure_context(x);

@@ -51,17 +51,33 @@ def pick_next_token(logits: torch.Tensor, input_ids: torch.Tensor | None = None,
 
 
 def ragged(decode_one, input_ids, attention_mask, pad_id: int):
-    """Run `decode_one(ids [1, L])` on every row's valid tokens and pad the outputs to a rectangle.  Left-padded inputs (HF's convention
-    for decoder-only generation) come back left-padded, right-padded inputs right-padded."""
+    """Row-by-row fallback for RIGHT-padded prompt batches (pads between the prompt and the new tokens; HF itself warns against that layout
+    for decoder-only generation): run `decode_one(ids [1, L])` on every row's valid tokens and lay the result out as HF `generate` does —
+    `[original padded prompt row | generated tokens | pad]`, i.e. `out[:, :S] == input_ids` and `out[:, S:]` holds only new tokens (the
+    slice `vqa_inference.py` decodes), whatever side the prompt was padded on and however many tokens each row produced."""
     mask = attention_mask.bool()
-    left = bool((~mask[:, 0]).any())
-    outs = [decode_one(row[m][None]) [0] for row, m in zip(input_ids, mask)]
-    width = max(o.numel() for o in outs)
-    rows = []
-    for o in outs:
-        pad = torch.full((width - o.numel(),), pad_id, dtype=o.dtype, device=o.device)
-        rows.append(torch.cat([pad, o]) if left else torch.cat([o, pad]))
-    return torch.stack(rows)
+    S = input_ids.shape[1]
+    gens = []
+    for row, m in zip(input_ids, mask):
+        n_valid = int(m.sum())
+        gens.append(decode_one(row[m][None])[0][n_valid:])
+    width = max(g.numel() for g in gens)
+    out = torch.full((input_ids.shape[0], S + width), pad_id, dtype=input_ids.dtype, device=input_ids.device)
+    out[:, :S] = input_ids
+    for b, g in enumerate(gens):
+        out[b, S:S + g.numel()] = g
+    return out
+
+
+def _left_padded(attention_mask) -> bool:
+    """True when every row's LAST prompt position is a real token (left padding, or no padding): the batched kv-cache path applies."""
+    return bool(attention_mask[:, -1].all())
+
+
+def _positions(attention_mask):
+    """reference `prepare_inputs_for_generation`, :1521-1526: position = number of real tokens before it; pad positions get 1."""
+    pos = attention_mask.long().cumsum(-1) - 1
+    return pos.masked_fill(attention_mask == 0, 1)
 
 
 @torch.no_grad()
@@ -72,12 +88,14 @@ def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample:
     stops when every row has produced an EOS or a `stopping_criteria` callable `(input_ids, scores) -> bool | BoolTensor[B]` fires for it
     (HF `StoppingCriteria` semantics; the reference's VQA eval passes a keyword criterion, omni/eval/vqa/vqa_inference.py:105-106).
     Returns [B, S + n_generated] ids (prompt included, like HF for decoder-only models)."""
+    am = None
     if attention_mask is not None and not bool(attention_mask.all()):
-        # ragged batch: the kv-cache kernels take one valid length per call, so each prompt is decoded on its own (batch 1) and the results
-        # are padded back to a rectangle on the side the inputs were padded on
+        am = attention_mask.to(input_ids.device)
+    if am is not None and not _left_padded(am):
+        # right-padded batch: pads would sit between the prompt and the new tokens — each prompt is decoded on its own (batch 1)
         if images is not None:
-            raise NotImplementedError("padded prompt batches with images: pass the prompts one at a time (images are matched to <im_start> "
-                                      "tokens in batch order)")
+            raise NotImplementedError("right-padded prompt batches with images: left-pad them (HF's convention for decoder-only models) or "
+                                      "pass the prompts one at a time (images are matched to <im_start> tokens in batch order)")
         return ragged(lambda ids: generate(model, ids, None, max_new_tokens, do_sample, temperature, top_k, top_p, repetition_penalty,
                                            eos_token_id, pad_token_id, generator, None, stopping_criteria),
                       input_ids, attention_mask, pad_token_id if pad_token_id is not None else
@@ -92,7 +110,10 @@ def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample:
     warp = dict(temperature=temperature, top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty)
     seq = input_ids
     unfinished = torch.ones(input_ids.shape[0], dtype=torch.bool, device=input_ids.device)
-    out = model(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True)
+    # left-padded batch: ONE batched prefill + batched decode steps; the pad keys stay masked inside the kv-cache and RoPE positions come
+    # from the mask, exactly as HF generate drives the reference (vqa_inference.py:112-130, modeling_dreamllm.py:1511-1547)
+    mask_kw = {} if am is None else dict(attention_mask=am, position_ids=_positions(am))
+    out = model(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True, **mask_kw)
     cache = out.past_key_values
     for i in range(max_new_tokens):
         nxt = pick_next_token(out.logits[:, -1], seq, do_sample=do_sample, generator=generator, **warp)
@@ -107,7 +128,10 @@ def generate(model, input_ids, images=None, max_new_tokens: int = 16, do_sample:
             unfinished = unfinished & ~(done.expand_as(unfinished))
         if i + 1 == max_new_tokens or ((eos is not None or stopping_criteria) and not bool(unfinished.any())):
             break
-        out = model(input_ids=nxt[:, None], past_key_values=cache, use_cache=True, last_token_logits_only=True)
+        if am is not None:
+            am = torch.cat([am, torch.ones_like(am[:, :1])], 1)
+            mask_kw = dict(attention_mask=am, position_ids=am.long().sum(-1, keepdim=True) - 1)
+        out = model(input_ids=nxt[:, None], past_key_values=cache, use_cache=True, last_token_logits_only=True, **mask_kw)
     return seq
 
 
@@ -121,7 +145,7 @@ def _gather_beams(t: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
 @torch.no_grad()
 def beam_search(model, input_ids, images=None, num_beams: int = 5, max_new_tokens: int = 16, length_penalty: float = 1.0,
                 early_stopping=False, eos_token_id=None, pad_token_id=None, stopping_criteria=None,
-                length_normalization: str = "generated", return_scores: bool = False):
+                length_normalization: str = "generated", return_scores: bool = False, attention_mask=None):
     """Beam search over the kv-cache decode path — what `model.generate(..., num_beams=5)` does in the reference's default VQA eval
     (omni/eval/vqa/vqa_inference.py:111-119, `--beamsearch True` is the default, omni/utils/eval_utils.py:141).
 
@@ -161,9 +185,17 @@ def beam_search(model, input_ids, images=None, num_beams: int = 5, max_new_token
     def norm_len(generated):                                             # length used by the length penalty
         return float(generated if length_normalization == "generated" else generated + prompt_len)
 
-    out = model(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True)
+    am = None                                                            # left-padded prompt batch: pad keys masked inside the cache
+    if attention_mask is not None and not bool(attention_mask.all()):
+        am = attention_mask.to(dev)
+        if not _left_padded(am):
+            raise ValueError("beam search over a padded batch needs LEFT padding (HF's convention for decoder-only models)")
+    mask_kw = {} if am is None else dict(attention_mask=am, position_ids=_positions(am))
+    out = model(input_ids=input_ids, images=images, use_cache=True, last_token_logits_only=True, **mask_kw)
     cache = out.past_key_values
     cache.repeat_interleave(k)
+    if am is not None:
+        am = am.repeat_interleave(k, dim=0)
     logits = out.logits[:, -1].float().repeat_interleave(k, dim=0)      # [B*k, V]
     cur_len = prompt_len
     while True:
@@ -212,7 +244,11 @@ def beam_search(model, input_ids, images=None, num_beams: int = 5, max_new_token
         if not more:
             break
         cache.reorder((next_src + torch.arange(B, device=dev)[:, None] * k).reshape(-1))
-        out = model(input_ids=running[:, :, cur_len - 1].reshape(B * k, 1), past_key_values=cache, use_cache=True, last_token_logits_only=True)
+        if am is not None:                                               # (rows of one sample share a mask: re-ordering beams keeps it)
+            am = torch.cat([am, torch.ones_like(am[:, :1])], 1)
+            mask_kw = dict(attention_mask=am, position_ids=am.long().sum(-1, keepdim=True) - 1)
+        out = model(input_ids=running[:, :, cur_len - 1].reshape(B * k, 1), past_key_values=cache, use_cache=True, last_token_logits_only=True,
+                    **mask_kw)
         logits = out.logits[:, -1].float()
     out_len = prompt_len + int(finished_len[:, 0].max())
     seqs = finished[:, 0, :out_len]

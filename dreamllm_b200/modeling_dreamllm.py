@@ -322,15 +322,30 @@ class KVCache:
         self.v = [torch.zeros((batch, max_len, num_heads, head_dim), device=device, dtype=dtype) for _ in range(num_layers)]
         self.len = 0
         self.max_len = max_len
+        # key-padding mask of a PADDED prompt batch: uint8 [B, round_up(max_len, 64)], 0 = pad position inside the cache (HF left-pads
+        # decoder-only prompts and keeps extending the 2-D attention_mask, reference :1511-1547).  None = no padding anywhere.
+        self.mask = None
 
     def get_seq_length(self):
         return self.len
+
+    def set_mask(self, attention_mask):
+        """attention_mask [B, L] (L = tokens in the cache after the current forward), any integer / bool dtype."""
+        B, L = attention_mask.shape
+        if self.mask is None:
+            ld = (self.max_len + 63) // 64 * 64
+            self.mask = torch.ones((self.k[0].shape[0], ld), device=self.k[0].device, dtype=torch.uint8)
+        if B != self.mask.shape[0] or L > self.mask.shape[1]:
+            raise ValueError(f"attention_mask {tuple(attention_mask.shape)} does not fit the kv-cache mask {tuple(self.mask.shape)}")
+        self.mask[:, :L] = attention_mask.to(device=self.mask.device, dtype=torch.uint8)
 
     def repeat_interleave(self, k: int):
         """Beam search: every sample's cache rows repeated k times along the batch dimension (in place)."""
         for li in range(len(self.k)):
             self.k[li] = self.k[li].repeat_interleave(k, dim=0)
             self.v[li] = self.v[li].repeat_interleave(k, dim=0)
+        if self.mask is not None:
+            self.mask = self.mask.repeat_interleave(k, dim=0).contiguous()
         return self
 
     def reorder(self, beam_idx):
@@ -341,6 +356,8 @@ class KVCache:
             idx = beam_idx.to(self.k[li].device)
             self.k[li][:, :L] = self.k[li][:, :L].index_select(0, idx)
             self.v[li][:, :L] = self.v[li][:, :L].index_select(0, idx)
+        if self.mask is not None:
+            self.mask = self.mask.index_select(0, beam_idx.to(self.mask.device)).contiguous()
         return self
 
 
@@ -421,7 +438,7 @@ class DreamLLMDecoderLayer(nn.Module):
         q4 = qkv.view(B, S, 3, nh, d)
         cache.k[li][:, start:start + S].copy_(q4[:, :, 1])
         cache.v[li][:, start:start + S].copy_(q4[:, :, 2])
-        ao = ops.attn_fwd_cache(q4[:, :, 0], cache.k[li], cache.v[li], start + S, causal=True)
+        ao = ops.attn_fwd_cache(q4[:, :, 0], cache.k[li], cache.v[li], start + S, causal=True, kv_mask=cache.mask)
         o = ops.linear(ao.view(B * S, H), att.o_proj.weight)
         h2, _, xmid = ops.rmsnorm_fwd(x2, self.post_attention_layernorm.weight, eps, add=o)
         gu = ops.linear(h2, _fuse_rows([mlp.gate_proj.weight, mlp.up_proj.weight]))
@@ -718,13 +735,22 @@ class DreamLLMModel(DreamLLMPreTrainedModel):
         if use_cache or past_key_values is not None:
             if torch.is_grad_enabled() and hidden_states.requires_grad:
                 raise ValueError("kv-cache inference runs under torch.no_grad()")
-            if attention_mask is not None and attention_mask_has_padding is not False and not bool(attention_mask.all()):
-                raise NotImplementedError("kv-cache path does not support padded batches (pad positions inside the cache); "
-                                          "run prompts of different lengths one at a time")
             B, S, _ = hidden_states.shape
             att = self.layers[0].self_attn
             cache = past_key_values if past_key_values is not None else KVCache(
                 len(self.layers), B, self.config.max_position_embeddings, att.num_heads, att.head_dim, hidden_states.device)
+            if attention_mask is not None and attention_mask_has_padding is not False:
+                # padded batch inside the cache (reference :960-962 keeps the 2-D mask for the flash path, whose `_upad_input` drops the
+                # pad keys; positions come from the mask, :1521-1526).  No host sync: the mask is applied whether or not it has zeros.
+                total = cache.len + S
+                if attention_mask.dim() != 2 or attention_mask.shape[1] not in (S, total):
+                    raise ValueError(f"attention_mask must be [batch, {total}] (cache + new tokens), got {tuple(attention_mask.size())}")
+                if attention_mask.shape[1] == S and cache.len > 0:
+                    raise ValueError("with a non-empty kv-cache pass the FULL attention_mask (past + new tokens), as HF generate does")
+                cache.set_mask(attention_mask)
+                if position_ids is None:
+                    position_ids = attention_mask.long().cumsum(-1) - 1
+                    position_ids = position_ids.masked_fill(attention_mask == 0, 1)[:, -S:]
         pos_i32 = None
         if cache is None:
             # once per forward instead of once per layer: valid lengths for the attention kernels and the int32 RoPE positions
@@ -1023,9 +1049,9 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
         if num_beams > 1:                                      # the reference's default VQA eval: num_beams=5 (vqa_inference.py:111-119)
             if do_sample:
                 raise NotImplementedError("beam sampling (num_beams > 1 with do_sample=True) is not built")
-            if attention_mask is not None and not bool(attention_mask.all()):
+            if attention_mask is not None and not bool(attention_mask.all()) and not bool(attention_mask[:, -1].all()):
                 if images is not None:
-                    raise NotImplementedError("padded prompt batches with images: pass the prompts one at a time")
+                    raise NotImplementedError("right-padded prompt batches with images: left-pad them or pass the prompts one at a time")
                 from .generation import ragged
                 kw = dict(kwargs)
                 return ragged(lambda ids: self.generate(ids, max_new_tokens=max_new_tokens, eos_token_id=eos_token_id, pad_token_id=pad_token_id,
@@ -1034,7 +1060,7 @@ class DreamLLMForCausalMLM(DreamLLMPreTrainedModel):
             return beam_search(self, input_ids, images=images, num_beams=num_beams, max_new_tokens=max_new_tokens,
                                length_penalty=kwargs.get("length_penalty", 1.0), early_stopping=kwargs.get("early_stopping", False),
                                eos_token_id=eos_token_id, pad_token_id=pad_token_id, stopping_criteria=stopping_criteria,
-                               length_normalization=kwargs.get("length_normalization", "generated"))
+                               length_normalization=kwargs.get("length_normalization", "generated"), attention_mask=attention_mask)
         return generate(self, input_ids, images=images, max_new_tokens=max_new_tokens, do_sample=do_sample, temperature=temperature,
                         top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty, eos_token_id=eos_token_id,
                         pad_token_id=pad_token_id, generator=generator, attention_mask=attention_mask,

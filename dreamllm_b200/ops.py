@@ -613,17 +613,24 @@ def vae_sample(h_nchw_f32, wq, bq, z_f32, scaling):
     return out
 
 
-def attn_fwd_cache(q, k_cache, v_cache, kv_len, causal=True, scale=None):
-    """q [B,Sq,nh,d] view; k_cache/v_cache [B, max_len, nh, d] (contiguous rows of nh*d), first kv_len rows valid."""
-    _chk_cuda(q, k_cache, v_cache)
+def attn_fwd_cache(q, k_cache, v_cache, kv_len, causal=True, scale=None, kv_mask=None):
+    """q [B,Sq,nh,d] view; k_cache/v_cache [B, max_len, nh, d] (contiguous rows of nh*d), first kv_len rows valid.
+    kv_mask: optional uint8 [B, mask_ld] (0 = padded key position), mask_ld a multiple of 64 covering kv_len."""
+    _chk_cuda(q, k_cache, v_cache, kv_mask)
     B, Sq, nh, d = q.shape
     kv_rows = k_cache.shape[1]
     assert k_cache.stride(1) == v_cache.stride(1) and k_cache.stride(0) == kv_rows * k_cache.stride(1)
     out = torch.empty((B, Sq, nh * d), device=q.device, dtype=BF16)
     lse = torch.empty((B, nh, Sq), device=q.device, dtype=torch.float32)
     scale = float(d) ** -0.5 if scale is None else float(scale)
-    check(lib().dllm_attn_fwd_cache(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(lse), B, Sq, int(kv_len), kv_rows, nh, d, q.stride(1),
-                                    k_cache.stride(1), nh * d, int(causal), scale, _stream()), "dllm_attn_fwd_cache")
+    if kv_mask is not None:
+        assert kv_mask.dtype == torch.uint8 and kv_mask.dim() == 2 and kv_mask.shape[0] == B and kv_mask.stride(1) == 1
+        check(lib().dllm_attn_fwd_cache_mask(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(lse), _p(kv_mask), kv_mask.stride(0), B, Sq,
+                                             int(kv_len), kv_rows, nh, d, q.stride(1), k_cache.stride(1), nh * d, int(causal), scale,
+                                             _stream()), "dllm_attn_fwd_cache_mask")
+    else:
+        check(lib().dllm_attn_fwd_cache(_p(q), _p(k_cache), _p(v_cache), _p(out), _p(lse), B, Sq, int(kv_len), kv_rows, nh, d, q.stride(1),
+                                        k_cache.stride(1), nh * d, int(causal), scale, _stream()), "dllm_attn_fwd_cache")
     LAUNCHES.add(1)
     return out
 

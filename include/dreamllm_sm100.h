@@ -116,6 +116,12 @@ int dllm_attn_fwd_ex(const void* q, const void* k, const void* v, void* out, flo
  * rows; causal uses the bottom-right aligned mask (query i is at absolute position Skv - Sq + i). */
 int dllm_attn_fwd_cache(const void* q, const void* k, const void* v, void* out, float* lse, int B, int Sq, int Skv, int kv_rows, int nh,
                         int d, long ld_q, long ld_kv, long ld_o, int causal, float scale, void* stream);
+/* same, for a PADDED prompt batch held in the cache: kv_mask [B, mask_ld] bytes, 0 = pad key (the 2-D `attention_mask` HF `generate` keeps
+ * extending, modeling_dreamllm.py:1511-1547; the reference's flash path drops those tokens with `_upad_input`, :553-583).  Pad QUERY rows
+ * whose keys are all masked come back as zeros, as `pad_input` re-inserts them (:545).  mask_ld % 16 == 0, >= round_up(Skv, 64). */
+int dllm_attn_fwd_cache_mask(const void* q, const void* k, const void* v, void* out, float* lse, const void* kv_mask, int mask_ld, int B,
+                             int Sq, int Skv, int kv_rows, int nh, int d, long ld_q, long ld_kv, long ld_o, int causal, float scale,
+                             void* stream);
 /* ResnetBlock2D / Upsample2D conv: implicit-GEMM 3x3 stride-1 pad-1 on tcgen05 (4-D TMA im2col, zero-fill padding).
  * y = conv(x, w) + bias[c] + rowbias[n, c] (+ residual);  w is [Cout, 3, 3, Cin]. */
 int dllm_conv3x3_nhwc(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, const void* bias,

@@ -69,21 +69,42 @@ def causal_additive_mask(bsz, seq, dtype, attention_mask_2d=None):
     return m
 
 
-def attention_eager(x, wq, wk, wv, wo, num_heads, cos, sin, position_ids, mask4d):
-    """DreamLLMAttention.forward (eager path), :309-400, pretraining_tp == 1, no kv-cache."""
+def causal_additive_mask_past(bsz, q_len, past_len, dtype, attention_mask_2d=None):
+    """What `_prepare_4d_causal_attention_mask(mask, (bsz, q_len), embeds, past_len)` yields (:965-967) with a kv-cache: [B, 1, q_len,
+    past_len + q_len], query i sits at absolute position past_len + i (bottom-right aligned causal), finfo.min on padded key columns of
+    the FULL-length 2-D mask (HF generate keeps extending it, :1511-1547)."""
+    mn = torch.finfo(dtype).min
+    total = past_len + q_len
+    qpos = torch.arange(past_len, total)[:, None]
+    kpos = torch.arange(total)[None, :]
+    m = torch.zeros(q_len, total, dtype=dtype).masked_fill(kpos > qpos, mn)[None, None].expand(bsz, 1, q_len, total).clone()
+    if attention_mask_2d is not None:
+        assert attention_mask_2d.shape == (bsz, total)
+        m = m.masked_fill((attention_mask_2d == 0)[:, None, None, :], mn)
+    return m
+
+
+def attention_eager(x, wq, wk, wv, wo, num_heads, cos, sin, position_ids, mask4d, past_kv=None, return_kv=False):
+    """DreamLLMAttention.forward (eager path), :309-400, pretraining_tp == 1.  `past_kv` = (k, v) [B, nh, past, d] already rotated:
+    the new keys / values are concatenated behind them (:344-355) and `(k, v)` is the present (`use_cache`, :355)."""
     bsz, q_len, hidden = x.shape
     d = hidden // num_heads
     q = F.linear(x, wq).view(bsz, q_len, num_heads, d).transpose(1, 2)
     k = F.linear(x, wk).view(bsz, q_len, num_heads, d).transpose(1, 2)
     v = F.linear(x, wv).view(bsz, q_len, num_heads, d).transpose(1, 2)
     q, k = apply_rope(q, k, cos.to(x.dtype), sin.to(x.dtype), position_ids)
+    if past_kv is not None:
+        k = torch.cat([past_kv[0], k], dim=2)
+        v = torch.cat([past_kv[1], v], dim=2)
+    present = (k, v)
     w = torch.matmul(q, k.transpose(2, 3)) / math.sqrt(d)
     if mask4d is not None:
         w = w + mask4d
         w = torch.max(w, torch.tensor(torch.finfo(w.dtype).min, dtype=w.dtype))  # :373-375
     w = F.softmax(w, dim=-1, dtype=torch.float32).to(q.dtype)  # :378
     o = torch.matmul(w, v).transpose(1, 2).contiguous().reshape(bsz, q_len, hidden)
-    return F.linear(o, wo)
+    out = F.linear(o, wo)
+    return (out, present) if return_kv else out
 
 
 # --------------------------------------------------------------------------- a6
@@ -106,9 +127,9 @@ LAYER_KEYS = (
 )
 
 
-def decoder_layer(x, p: dict, num_heads, cos, sin, position_ids, mask4d, eps=1e-6):
+def decoder_layer(x, p: dict, num_heads, cos, sin, position_ids, mask4d, eps=1e-6, past_kv=None, return_kv=False):
     """DreamLLMDecoderLayer.forward, :599-654 (pre-norm residual block). `p` uses the
-    reference's state-dict key names (LAYER_KEYS)."""
+    reference's state-dict key names (LAYER_KEYS).  With `return_kv` returns (hidden, present_key_value) as `use_cache=True` does."""
     res = x
     h = rmsnorm(x, p["input_layernorm.weight"], eps)
     h = attention_eager(
@@ -122,12 +143,51 @@ def decoder_layer(x, p: dict, num_heads, cos, sin, position_ids, mask4d, eps=1e-
         sin,
         position_ids,
         mask4d,
+        past_kv=past_kv,
+        return_kv=return_kv,
     )
+    present = None
+    if return_kv:
+        h, present = h
     x = res + h
     res = x
     h = rmsnorm(x, p["post_attention_layernorm.weight"], eps)
     h = mlp(h, p["mlp.gate_proj.weight"], p["mlp.up_proj.weight"], p["mlp.down_proj.weight"])
-    return res + h
+    return (res + h, present) if return_kv else res + h
+
+
+def cached_decode_scenario(hidden=256, inter=512, heads=2, seed=21, lens=(37, 50), steps=3):
+    """A LEFT-padded prompt batch pushed through one decoder layer with a kv-cache: prefill, then `steps` single-token decode steps, driven
+    the way HF generate drives the reference (full 2-D mask every call, position_ids = cumsum(mask) - 1 with 1 at pads, :1511-1547).
+    Returns (params, list of (x [B, S_i, H], attention_mask [B, total_i], position_ids [B, S_i])) — deterministic CPU RNG."""
+    p = init_layer_params(hidden, inter, seed)
+    g = torch.Generator().manual_seed(seed + 500)
+    B, S0 = len(lens), max(lens)
+    am = torch.zeros(B, S0, dtype=torch.long)
+    for b, n in enumerate(lens):
+        am[b, S0 - n:] = 1
+    calls = []
+    x0 = torch.randn(B, S0, hidden, generator=g)
+    pos = (am.cumsum(-1) - 1).masked_fill(am == 0, 1)
+    calls.append((x0, am.clone(), pos))
+    for _ in range(steps):
+        am = torch.cat([am, torch.ones(B, 1, dtype=torch.long)], 1)
+        calls.append((torch.randn(B, 1, hidden, generator=g), am.clone(), am.sum(-1, keepdim=True) - 1))
+    return p, calls
+
+
+def run_cached_scenario(p, calls, heads, dtype=torch.float32):
+    """Oracle outputs of `cached_decode_scenario`: list of hidden states [B, S_i, H] (pad rows included; compare valid rows only)."""
+    pp = {k: v.to(dtype) for k, v in p.items()}
+    d = calls[0][0].shape[-1] // heads
+    cos, sin = rope_tables(d, 2048, dtype=dtype)
+    past, outs = None, []
+    for x, am, pos in calls:
+        past_len = 0 if past is None else past[0].shape[2]
+        mask = causal_additive_mask_past(x.shape[0], x.shape[1], past_len, dtype, am)
+        y, past = decoder_layer(x.to(dtype), pp, heads, cos, sin, pos, mask, past_kv=past, return_kv=True)
+        outs.append(y)
+    return outs
 
 
 def init_layer_params(hidden, inter, seed, dtype=torch.float32, std=0.02):

@@ -81,6 +81,28 @@ def run_reference(ns, name, hidden, inter, heads, bsz, seq, seed, pad):
     return out
 
 
+def run_reference_cached(ns):
+    """The reference layer (eager attention, :309-400) driven with `past_key_value` / `use_cache=True` over `cached_decode_scenario`:
+    a LEFT-padded batch, prefill + single-token decode steps, 4-D masks from the reference's own `_prepare_4d_causal_attention_mask`."""
+    from transformers.modeling_attn_mask_utils import _prepare_4d_causal_attention_mask
+    hidden, inter, heads = 256, 512, 2
+    p, calls = O.cached_decode_scenario(hidden, inter, heads)
+    layer = ns["DreamLLMDecoderLayer"](ref_exec.make_config(hidden, inter, heads)).float()
+    sd = {k: v.clone() for k, v in p.items()}
+    sd["self_attn.rotary_emb.inv_freq"] = layer.self_attn.rotary_emb.inv_freq.clone()
+    layer.load_state_dict(sd)
+    past, out = None, {"shape": np.array([hidden, inter, heads], dtype=np.int64)}
+    with torch.no_grad():
+        for i, (x, am, pos) in enumerate(calls):
+            past_len = 0 if past is None else past[0].shape[2]
+            mask = _prepare_4d_causal_attention_mask(am, (x.shape[0], x.shape[1]), x, past_len)
+            y, past = layer(x, attention_mask=mask, position_ids=pos, past_key_value=past, use_cache=True)
+            out[f"y{i}"] = y.numpy().astype(np.float32)
+            out[f"mask{i}"] = am.numpy()
+    out["k_final"] = past[0][:, :, -4:].numpy().astype(np.float32)          # last rotated keys of the final cache
+    return out
+
+
 def main():
     assert ref_exec.available(), "needs /root/reference (build container only)"
     os.makedirs(OUT, exist_ok=True)
@@ -93,6 +115,10 @@ def main():
         out = run_reference(ns, *case)
         path = os.path.join(OUT, f"decoder_layer_{case[0]}.npz")
         np.savez_compressed(path, **out)
+        print(path, os.path.getsize(path) // 1024, "KiB")
+    if not only or "kvcache" in only:
+        path = os.path.join(OUT, "kvcache_layer.npz")
+        np.savez_compressed(path, **run_reference_cached(ns))
         print(path, os.path.getsize(path) // 1024, "KiB")
 
 

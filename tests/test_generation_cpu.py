@@ -188,28 +188,52 @@ def test_beam_search_modes_and_kvcache_beam_ops():
     assert DreamLLMForCausalMLM._reorder_cache(c, torch.arange(6)) is c
 
 
-def test_ragged_batches_are_decoded_row_by_row():
-    """Padded prompt batches: each row's valid tokens are decoded on their own (batch 1) and re-padded on the input's padding side."""
+def test_padded_prompt_batches_keep_the_hf_output_layout():
+    """Padded prompt batches.  Left-padded (HF's convention for decoder-only models): ONE batched prefill + batched decode with the 2-D
+    attention_mask and mask-derived position_ids handed to the model every step (modeling_dreamllm.py:1511-1547).  Right-padded: each row
+    decoded on its own.  Either way the output is `[original padded prompt | new tokens | pad]` — `out[:, :S] == input_ids` and
+    `out[:, S:]` holds only generated tokens, also when rows stop at different lengths (the old re-padding shifted prompts)."""
+    from types import SimpleNamespace
+
     from dreamllm_b200.generation import generate
 
-    class ByLength:                       # emits (prompt length + step) % 50: the answer depends on the un-padded prompt only
-        def __call__(self, input_ids=None, images=None, past_key_values=None, use_cache=None, last_token_logits_only=None):
-            from types import SimpleNamespace
-            assert input_ids.shape[0] == 1
+    class ByLength:          # row b emits (number of REAL prompt tokens + step) % 50; token 9 = EOS for rows whose real length is 2
+        def __init__(self):
+            self.calls = []
+
+        def __call__(self, input_ids=None, images=None, past_key_values=None, use_cache=None, last_token_logits_only=None,
+                     attention_mask=None, position_ids=None):
+            B = input_ids.shape[0]
+            self.calls.append((tuple(input_ids.shape), None if attention_mask is None else tuple(attention_mask.shape),
+                               None if position_ids is None else position_ids[:, -1].tolist()))
             if past_key_values is None:
-                past_key_values = {"n": input_ids.shape[1]}
+                real = attention_mask.sum(-1) if attention_mask is not None else torch.full((B,), input_ids.shape[1])
+                past_key_values = {"n": real.clone(), "len0": real.clone()}
             else:
-                past_key_values["n"] += 1
-            logits = torch.full((1, 1, 50), -10.0)
-            logits[0, 0, past_key_values["n"] % 50] = 10.0
+                past_key_values["n"] = past_key_values["n"] + 1
+            logits = torch.full((B, 1, 50), -10.0)
+            for b in range(B):
+                tok = int(past_key_values["n"][b]) % 50
+                if int(past_key_values["len0"][b]) == 2 and int(past_key_values["n"][b]) == 3:
+                    tok = 9                                   # the short row stops after one token
+                logits[b, 0, tok] = 10.0
             return SimpleNamespace(logits=logits, past_key_values=past_key_values)
+
     ids = torch.tensor([[0, 0, 7, 8], [5, 6, 7, 8]])
     mask = torch.tensor([[0, 0, 1, 1], [1, 1, 1, 1]])
-    out = generate(ByLength(), ids, attention_mask=mask, max_new_tokens=3, pad_token_id=0)
-    assert out.tolist() == [[0, 0, 7, 8, 2, 3, 4], [5, 6, 7, 8, 4, 5, 6]]            # left-padded in, left-padded out
+    m = ByLength()
+    out = generate(m, ids, attention_mask=mask, max_new_tokens=3, pad_token_id=0, eos_token_id=9)
+    assert out[:, :4].tolist() == ids.tolist()                                   # the prompt block is untouched
+    assert out[:, 4:].tolist() == [[2, 9, 0], [4, 5, 6]]                         # row 0: EOS after 2 tokens, then pad; row 1 runs on
+    assert m.calls[0] == ((2, 4), (2, 4), [1, 3])                                # batched prefill, positions from the mask
+    assert m.calls[1] == ((2, 1), (2, 5), [2, 4]) and m.calls[2] == ((2, 1), (2, 6), [3, 5])   # full mask + next position every step
+    # right-padded: row-by-row fallback, same output layout
     ids_r = torch.tensor([[7, 8, 0, 0], [5, 6, 7, 8]])
-    out = generate(ByLength(), ids_r, attention_mask=mask.flip(1)[[0, 1]] * 0 + torch.tensor([[1, 1, 0, 0], [1, 1, 1, 1]]), max_new_tokens=3,
-                   pad_token_id=0)
-    assert out.tolist() == [[7, 8, 2, 3, 4, 0, 0], [5, 6, 7, 8, 4, 5, 6]]            # right-padded in, right-padded out
+    mask_r = torch.tensor([[1, 1, 0, 0], [1, 1, 1, 1]])
+    m = ByLength()
+    out = generate(m, ids_r, attention_mask=mask_r, max_new_tokens=3, pad_token_id=0, eos_token_id=9)
+    assert out[:, :4].tolist() == ids_r.tolist()
+    assert out[:, 4:].tolist() == [[2, 9, 0], [4, 5, 6]]
+    assert all(c[0][0] == 1 for c in m.calls)                                    # batch 1 at a time
     with pytest.raises(NotImplementedError):
-        generate(ByLength(), ids, images="x", attention_mask=mask, max_new_tokens=1)
+        generate(ByLength(), ids_r, images="x", attention_mask=mask_r, max_new_tokens=1)

@@ -93,3 +93,43 @@ def test_lm_loss_masked_mean():
     assert torch.allclose(O.lm_loss(logits, labels), want, atol=1e-6)
     # no valid label: plain mean of (zero) CE terms — reference :1468-1469
     assert float(O.lm_loss(logits, torch.full((2, 7), -100))) == 0.0
+
+
+def test_kvcache_oracle_matches_reference_golden():
+    """kv-cache decode: the oracle's `past_kv` path (restating :344-355 + the past-aware 4-D mask of :965-967) against
+    tests/golden/kvcache_layer.npz — the reference's own DreamLLMDecoderLayer driven with `past_key_value` / `use_cache=True` over a
+    LEFT-padded batch (prefill + 3 single-token steps), minted by oracle/gen_golden.py::run_reference_cached."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "kvcache_layer.npz"))
+    hidden, inter, heads = [int(v) for v in g["shape"]]
+    p, calls = O.cached_decode_scenario(hidden, inter, heads)
+    outs = O.run_cached_scenario(p, calls, heads)
+    assert len(outs) == 4
+    for i, ((x, am, pos), y) in enumerate(zip(calls, outs)):
+        assert np.array_equal(am.numpy(), g[f"mask{i}"])
+        valid = am[:, -x.shape[1]:].bool()                 # rows of this call that are real tokens
+        np.testing.assert_allclose(y.detach()[valid].numpy(), g[f"y{i}"][valid.numpy()], rtol=1e-5, atol=1e-6, err_msg=f"call {i}")
+    # pad QUERY rows differ by design between the reference's two paths (SURVEY §8 row a3'): eager = uniform attention, flash = zeros
+
+
+@pytest.mark.skipif(not ref_exec.available(), reason="/root/reference only exists in the build container")
+def test_kvcache_oracle_matches_live_reference_bf16():
+    """Same scenario, bf16, against the live reference: shared rounding points => identical outputs on the valid rows."""
+    from transformers.modeling_attn_mask_utils import _prepare_4d_causal_attention_mask
+    BF = torch.bfloat16
+    hidden, inter, heads = 256, 512, 2
+    p, calls = O.cached_decode_scenario(hidden, inter, heads)
+    ns = ref_exec.load_reference_namespace()
+    layer = ns["DreamLLMDecoderLayer"](ref_exec.make_config(hidden, inter, heads)).float()
+    sd = {k: v.clone() for k, v in p.items()}
+    sd["self_attn.rotary_emb.inv_freq"] = layer.self_attn.rotary_emb.inv_freq.clone()
+    layer.load_state_dict(sd)
+    layer = layer.to(BF)
+    outs = O.run_cached_scenario(p, calls, heads, dtype=BF)
+    past = None
+    with torch.no_grad():
+        for (x, am, pos), y in zip(calls, outs):
+            past_len = 0 if past is None else past[0].shape[2]
+            mask = _prepare_4d_causal_attention_mask(am, (x.shape[0], x.shape[1]), x.to(BF), past_len)
+            yr, past = layer(x.to(BF), attention_mask=mask, position_ids=pos, past_key_value=past, use_cache=True)
+            valid = am[:, -x.shape[1]:].bool()
+            assert torch.equal(yr[valid], y[valid])
