@@ -115,6 +115,15 @@ class ClockSampler:
         return self.summary()
 
 
+_T0 = time.time()
+
+
+def log(msg):
+    """progress on stderr (stdout carries exactly one JSON line)"""
+    if int(os.environ.get("RANK", 0)) == 0:
+        print(f"[bench {time.time() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -204,7 +213,9 @@ def cpu_reference_c5(warm=1, iters=3):
     cores = _cpu_threads()
     S = 1 + C5["txt"] + 1 + C5["Q"] + 1 + 1
     t_layer, _ = cpu_llm_layer(S, frozen=True, warm=warm, iters=iters)
+    log(f"  cpu: decoder layer {t_layer:.3f}s ({cores} threads)")
     t_head, _ = cpu_lm_head(S, frozen=True, warm=warm, iters=iters)
+    log(f"  cpu: lm_head {t_head:.3f}s")
     with torch.device("meta"):
         unet, vae = UO.UNet2DConditionModel(), VO.AutoencoderKLEncoder()
     unet, vae = _fast_init(unet), _fast_init(vae)
@@ -223,8 +234,11 @@ def cpu_reference_c5(warm=1, iters=3):
         cond.grad = None
         lat = torch.randn(1, 4, 64, 64, generator=g)
         unet(lat, tt, cond).float().pow(2).mean().backward()
+    log("  cpu: UNet / VAE oracles built")
     t_vae, _ = _median_time(vae_step, warm, iters)
+    log(f"  cpu: VAE encode {t_vae:.2f}s")
     t_unet, _ = _median_time(unet_step, warm, iters)
+    log(f"  cpu: UNet fwd+bwd {t_unet:.2f}s")
     t_sample = L * t_layer + t_head + t_vae + t_unet
     units = S + C5["res"] * C5["res"]
     return {"value": units / t_sample, "unit": UNIT, "cores": cores, "kind": "port",
@@ -404,6 +418,7 @@ def run_c5(env, model, steps, warmup):
 
     graph, mode = None, "eager launches"
     ops.LAUNCHES.reset()
+    log("  c5: first eager step")
     compute()
     optimizer()
     launches_per_step = ops.LAUNCHES.count
@@ -439,6 +454,7 @@ def run_c5(env, model, steps, warmup):
         step_dev()
         return float(loss_static.item())                          # D2H every step
 
+    log(f"  c5: {mode}")
     for _ in range(2):
         step_e2e()
     total = env.timed(step_dev, steps)
@@ -577,8 +593,10 @@ def run_c4(env, steps_inf=50, bs=16, Q=77, guidance=7.5, runs=3):
     cond = torch.cat([head.projector(neg)[-1], head.projector(pos)[-1]])
     loop = DenoiseLoop(head.unet, cond, steps_inf, guidance, "ddim", height=512, width=512, whole_loop_graph=True)
     ops.LAUNCHES.reset()
+    log("  c4: capturing the whole 50-step loop into one CUDA graph")
     loop.run()
     torch.cuda.synchronize()
+    log("  c4: captured + first replay done")
     launches = ops.LAUNCHES.count
     times = []
     for _ in range(runs):
@@ -707,7 +725,9 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device: dreamllm_b200 has no CPU fallback")
     env = Env(args)
     only = set(filter(None, args.only.split(","))) or {"c5", "c2", "c4", "c3", "c1"}
+    log("building the 7B LLM")
     model = build_llm(env, args.layers)
+    log("LLM built")
     sampler = ClockSampler(env.local)
     if rank == 0:
         sampler.start()
@@ -722,8 +742,10 @@ def main():
         if name not in only:
             continue
         lo = sampler.mark()
+        log(f"{name}: start")
         try:
             rec[name] = fn()
+            log(f"{name}: done")
         except Exception as ex:  # noqa: BLE001  (a failing secondary record must not lose the headline line)
             if name == "c5":
                 raise
@@ -760,7 +782,9 @@ def main():
             if k in marks:
                 line[k]["clocks"] = sampler.summary(*marks[k])
     if env.world == 1 and not args.no_cpu_baseline:
+        log("cpu_baseline (oracle port, one sample of the headline workload): start")
         cb = cpu_reference_c5(warm=1, iters=3)
+        log("cpu_baseline: done")
         line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         if not args.fast:
             if "c1" in line and "error" not in line["c1"]:

@@ -10,6 +10,8 @@
 //   warp 4     TMA producer (one lane)
 //   warp 5     TMEM allocator + MMA issuer (one lane): tcgen05.mma, S/dP tiles double-buffered in TMEM
 // All inter-role hand-offs are mbarriers; tcgen05.commit signals MMA completion.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_sm100.h"
 #include "ops.h"
@@ -95,17 +97,22 @@ __device__ __forceinline__ void store_acc_tile(uint32_t tmem_acc, uint8_t* stage
 }
 
 // ================================================================================================ forward
-template <int D>
+// kPT = true (default): P never touches shared memory.  The softmax warps write bf16 P back into the TMEM columns S occupied
+// (tcgen05.st) and the PV tile-GEMM reads its A operand from tensor memory (tcgen05.mma with [a_tmem]).  Because S is double-buffered, so
+// is P: softmax(j+1) no longer waits for PV(j), and the per-tile STS burst + fence.proxy.async + 16 KB of smem are gone (round 1 kept P in
+// a single smem buffer and every softmax warp stalled on `pv_done` once per KV tile: 733 TF/s, tensor pipe 31 %).
+// kPT = false: the round-1 data path (P staged in swizzled smem), kept selectable with DLLM_ATTN_LEGACY=1 for same-box A/B runs.
+template <int D, bool kPT>
 struct FwdSmem {
   static constexpr int NCH = D / 64;
   static constexpr int kQ = NCH * 16384;       // [NCH][128][128B]
   static constexpr int kKV = NCH * 8192;       // [NCH][64][128B]
-  static constexpr int kP = 16384;             // [128][128B]
+  static constexpr int kP = kPT ? 0 : 16384;   // [128][128B]
   static constexpr int oQ = 0, oK = kQ, oV = oK + 2 * kKV, oP = oV + 2 * kKV, oBar = oP + kP;
   static constexpr int kBytes = oBar + 256;
 };
 
-template <int D, bool kCausal>
+template <int D, bool kCausal, bool kPT>
 __global__ void __launch_bounds__(kAttnThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
                 const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, float* __restrict__ lse,
@@ -116,7 +123,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   // causal with Skv > S = kv-cache decode / continuation (reference :344-355, :444-449): query i sits at absolute position
   // (Skv - S) + i, i.e. the mask is bottom-right aligned:  kv <= q + coff
   const int coff = kCausal ? (Skv - S) : 0;
-  using L = FwdSmem<D>;
+  using L = FwdSmem<D, kPT>;
   constexpr int NCH = L::NCH;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
@@ -126,9 +133,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   uint64_t* v_full = bars + 5;   // [2]
   uint64_t* v_empty = bars + 7;  // [2]
   uint64_t* s_full = bars + 9;   // [2]
-  uint64_t* p_full = bars + 11;
-  uint64_t* pv_done = bars + 12;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* p_full = bars + 11;  // [2]  (kPT: P(j) lives in S buffer j & 1; legacy: only [0] is used)
+  uint64_t* pv_done = bars + 13; // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -144,9 +151,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&pv_done[i], 1);
     }
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
     fence_mbar_init();
   }
   if (warp == 5) { tmem_alloc<1>(tmem_ptr, 256); tmem_relinquish<1>(); }
@@ -178,6 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);
     const uint32_t sQ = smem_u32(smem + L::oQ), sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV),
                    sP = smem_u32(smem + L::oP);
+    (void)sP;
     auto issue_qk = [&](int j) {
       const int st = j & 1;
       mbar_wait(&k_full[st], (j >> 1) & 1, 12);
@@ -192,11 +200,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       if (j + 1 < n_kv) issue_qk(j + 1);
       const int st = j & 1;
       mbar_wait(&v_full[st], (j >> 1) & 1, 14);
-      mbar_wait(p_full, j & 1, 15);
-      tc_fence_after();
-      mma_tile(tmem_O, sP, false, 0, sV + st * L::kKV, true, 8192, 4, idesc_pv, j > 0);
+      if constexpr (kPT) {
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1, 15);
+        tc_fence_after();
+        // O += P V_j with P read from TMEM: [128 lanes x 64 kv] bf16 = 32 columns at the base of S buffer j & 1, 8 columns per UMMA_K
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_ts(tmem_O, tmem_S + (j & 1) * 64 + ks * 8, op_desc(sV + st * L::kKV, true, 8192, ks), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+      } else {
+        mbar_wait(&p_full[0], j & 1, 15);
+        tc_fence_after();
+        mma_tile(tmem_O, sP, false, 0, sV + st * L::kKV, true, 8192, 4, idesc_pv, j > 0);
+      }
       umma_commit(&v_empty[st]);
-      umma_commit(pv_done);
+      umma_commit(&pv_done[kPT ? (j & 1) : 0]);
     }
   } else if (warp < 4) {
     // ---------------- softmax rows ----------------
@@ -236,14 +253,27 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
           mx = fmaxf(mx, s);
         }
       } else {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // four independent chains (was one 32-deep FMNMX3 chain)
 #pragma unroll
-        for (int c = 0; c < 64; ++c) mx = fmaxf(mx, __uint_as_float(sv[c]));
+        for (int c = 0; c < 64; c += 4) {
+          m0 = fmaxf(m0, __uint_as_float(sv[c]));
+          m1 = fmaxf(m1, __uint_as_float(sv[c + 1]));
+          m2 = fmaxf(m2, __uint_as_float(sv[c + 2]));
+          m3 = fmaxf(m3, __uint_as_float(sv[c + 3]));
+        }
+        mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       const float m_new = fmaxf(m_run, mx * scale_log2);
       // lazy rescale: only move the reference max when it grew by more than 2^8 (keeps P <= 256, exact after 1/l)
       const bool need = (m_new - m_run) > 8.0f;
       const bool any = __any_sync(0xffffffffu, need);
-      if (j > 0) mbar_wait(pv_done, (j - 1) & 1, 17);  // P buffer free, O quiescent
+      if constexpr (!kPT) {
+        if (j > 0) mbar_wait(&pv_done[0], (j - 1) & 1, 17);  // P buffer free, O quiescent
+      } else {
+        // P(j) goes to TMEM buffer j & 1, which PV(j-2) finished reading before QK(j) could overwrite it with S(j) (in-order tensor pipe):
+        // nothing to wait for unless O itself is about to be rescaled
+        if (any && j > 0) mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1, 17);
+      }
       if (any) {
         const float m_tgt = (m_new == -INFINITY) ? m_run : m_new;
         const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_tgt);
@@ -264,24 +294,42 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         m_run = m_tgt;
       }
       const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-      float lsum = 0.f;
+      float ls0 = 0.f, ls1 = 0.f;
+      if constexpr (kPT) {
+        uint32_t pw[32];
 #pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        float p[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          p[e] = exp2f(__uint_as_float(sv[jj * 8 + e]) * scale_log2 - m_use);
-          lsum += p[e];
+        for (int c = 0; c < 32; ++c) {
+          const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - m_use);
+          const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - m_use);
+          ls0 += p0;
+          ls1 += p1;
+          pw[c] = pack_bf16(p0, p1);          // K elements 2c, 2c+1 of this row share one 32-bit TMEM column
         }
-        store_row_chunk(smem + L::oP, row, jj, p);
+        tmem_st32(tmem_S + lane_off + (j & 1) * 64, pw);
+        tmem_st_wait();
+        l_run += ls0 + ls1;
+        tc_fence_before();
+        mbar_arrive(&p_full[j & 1]);
+      } else {
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          float p[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            p[e] = exp2f(__uint_as_float(sv[jj * 8 + e]) * scale_log2 - m_use);
+            ls0 += p[e];
+          }
+          store_row_chunk(smem + L::oP, row, jj, p);
+        }
+        l_run += ls0;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&p_full[0]);
       }
-      l_run += lsum;
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(p_full);
     }
     if (n_kv > 0) {
-      mbar_wait(pv_done, (n_kv - 1) & 1, 18);
+      if constexpr (kPT) mbar_wait(&pv_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1, 18);
+      else mbar_wait(&pv_done[0], (n_kv - 1) & 1, 18);
       tc_fence_after();
     }
     const bool valid_row = (q_row < q_len) && n_kv > 0 && l_run > 0.f;
@@ -729,26 +777,425 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   if (warp == 9) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ================================================================================================ backward, TS flavour (default)
+// Same two deterministic kernels and the same tile algebra as above, with the three changes the round-1 profile asked for
+// (row warps were the critical path: tensor pipe 27 % / 9 %, profiles/r01c_ncu_full_summary.csv):
+//   * P^T / dS^T (dkdv) and dS (dq) never touch shared memory: the row warps write the bf16 pairs back into the TMEM columns they just
+//     read S / dP from (tcgen05.st) and the accumulating tile-GEMMs take their A operand from tensor memory.  Warp `part` owns fp32
+//     columns [16 part, 16 part + 16) of a 64-column tile and stores its 8 packed words at columns [16 part, 16 part + 8): nobody
+//     overwrites a column another warp still has to read, and UMMA_K step ks simply starts at column 16 ks.
+//     No STS bursts, no fence.proxy.async, no wait for the previous iteration's accumulate MMAs (the in-order tensor pipe orders them
+//     against the next S / dP overwrite);
+//   * 16 row warps instead of 8 (four per TMEM lane quarter, 16 columns each): the per-iteration row phase is latency-bound, so the
+//     work per warp is halved and four warps per scheduler hide each other's LDTM / MUFU latency;
+//   * lse / delta of the q tile are staged in shared memory by the TMA producer (one 256-byte bulk copy each, riding on the Q/dO
+//     barrier) instead of 16 broadcast __ldg per thread per iteration from L2.
+constexpr int kBwdRowWarps = 16;
+constexpr int kBwdTsThreads = (kBwdRowWarps + 2) * 32;   // + TMA producer warp + MMA warp
+
+// 1-D bulk copy global -> shared, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int D>
+struct BwdKVTsSmem {
+  static constexpr int NCH = D / 64;
+  static constexpr int kKV = NCH * 16384;  // [NCH][128][128B]
+  static constexpr int kQ = NCH * 8192;    // [NCH][64][128B]
+  static constexpr int oK = 0, oV = kKV, oQ = 2 * kKV, oDO = oQ + 2 * kQ, oStat = oDO + 2 * kQ, oBar = oStat + 2 * 512;  // stats: [2][lse 64 | delta 64] fp32
+  static constexpr int kBytes = oBar + 256;
+};
+
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kBwdTsThreads, 1)
+attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                        const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                        const __grid_constant__ CUtensorMap tdk, const __grid_constant__ CUtensorMap tdv,
+                        const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ seqlens,
+                        int S, int Skv, int S_pad, int nh, float scale, float scale_log2) {
+  using L = BwdKVTsSmem<D>;
+  constexpr int NCH = L::NCH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* qdo_full = bars + 1;   // [2]
+  uint64_t* qdo_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;   // [2]
+  uint64_t* pds_full = bars + 7;   // [2]
+  uint64_t* acc_done = bars + 9;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int len = seqlens ? min(seqlens[b], S) : S;
+  const int len_kv = seqlens ? len : Skv;
+  const int i_begin = kCausal ? (kv0 / 64) : 0;
+  const int i_end = (len + 63) / 64;
+  const int n_it = (kv0 < len_kv) ? max(i_end - i_begin, 0) : 0;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_bwd_dkdv_ts: smem misaligned\n"); __trap(); }
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&pds_full[i], kBwdRowWarps * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kBwdRowWarps + 1) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_St = tmem_base;         // 2 x 64 (fp32 S^T, then bf16 P^T in the first 8 columns of every 16)
+  const uint32_t tmem_dPt = tmem_base + 128;  // 2 x 64 (fp32 dP^T, then bf16 dS^T likewise)
+  const uint32_t tmem_dV = tmem_base + 256;   // D
+  const uint32_t tmem_dK = tmem_base + 256 + D;
+
+  if (warp == kBwdRowWarps && lane == 0 && n_it > 0) {
+    // ---------------- TMA producer ----------------
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    mbar_arrive_expect_tx(kv_full, 2 * 128 * D * 2);
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem + L::oK + c * 16384, &tk, kv_full, h * D + c * 64, kv0, b);
+      tma_load_3d(smem + L::oV + c * 16384, &tv, kv_full, h * D + c * 64, kv0, b);
+    }
+    const float* lse_bh = lse2 + (static_cast<size_t>(b) * nh + h) * S_pad;
+    const float* del_bh = delta + (static_cast<size_t>(b) * nh + h) * S_pad;
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const int qr0 = (i_begin + it) * 64;
+      mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1, 40);
+      mbar_arrive_expect_tx(&qdo_full[st], 2 * 64 * D * 2 + 512);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smem + L::oQ + st * L::kQ + c * 8192, &tq, &qdo_full[st], h * D + c * 64, qr0, b);
+        tma_load_3d(smem + L::oDO + st * L::kQ + c * 8192, &tdo, &qdo_full[st], h * D + c * 64, qr0, b);
+      }
+      bulk_load_1d(smem + L::oStat + st * 512, lse_bh + qr0, 256, &qdo_full[st]);          // S_pad is a multiple of 64: always in range
+      bulk_load_1d(smem + L::oStat + st * 512 + 256, del_bh + qr0, 256, &qdo_full[st]);
+    }
+  } else if (warp == kBwdRowWarps + 1 && lane == 0 && n_it > 0) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+    const uint32_t sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV), sQ = smem_u32(smem + L::oQ),
+                   sDO = smem_u32(smem + L::oDO);
+    auto issue_s = [&](int it) {
+      const int st = it & 1;
+      mbar_wait(&qdo_full[st], (it >> 1) & 1, 41);
+      tc_fence_after();
+      mma_tile(tmem_St + st * 64, sK, false, 16384, sQ + st * L::kQ, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_dPt + st * 64, sV, false, 16384, sDO + st * L::kQ, false, 8192, D / 16, idesc_s, false);
+      umma_commit(&sdp_full[st]);
+    };
+    mbar_wait(kv_full, 0, 42);
+    issue_s(0);
+    for (int it = 0; it < n_it; ++it) {
+      if (it + 1 < n_it) issue_s(it + 1);
+      const int st = it & 1;
+      mbar_wait(&pds_full[st], (it >> 1) & 1, 43);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)   // dV += P^T dO_i : A = P^T from TMEM (k-step ks = q columns [16 ks, 16 ks + 16) at column 16 ks)
+        umma_ts(tmem_dV, tmem_St + st * 64 + 16 * ks, op_desc(sDO + st * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)   // dK += dS^T Q_i
+        umma_ts(tmem_dK, tmem_dPt + st * 64 + 16 * ks, op_desc(sQ + st * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&qdo_empty[st]);
+      umma_commit(&acc_done[st]);
+    }
+  } else if (warp < kBwdRowWarps) {
+    // ---------------- row warps ----------------
+    const int wq = warp & 3, part = warp >> 2;
+    const int row = wq * 32 + lane;  // kv row within tile
+    const int kv_row = kv0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1;
+      const int qc0 = (i_begin + it) * 64 + part * 16;  // first q index of my 16 columns
+      mbar_wait(&qdo_full[st], (it >> 1) & 1, 45);       // the bulk-copied lse / delta of this q tile are visible to this thread
+      mbar_wait(&sdp_full[st], (it >> 1) & 1, 44);
+      tc_fence_after();
+      uint32_t sv[16], dv[16];
+      tmem_ld16(tmem_St + lane_off + st * 64 + part * 16, sv);
+      tmem_ld16(tmem_dPt + lane_off + st * 64 + part * 16, dv);
+      float lq[16], dq_[16];
+      {
+        const float4* ls = reinterpret_cast<const float4*>(smem + L::oStat + st * 512) + part * 4;
+        const float4* ds4 = reinterpret_cast<const float4*>(smem + L::oStat + st * 512 + 256) + part * 4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float4 a = ls[i], c = ds4[i];
+          lq[4 * i] = a.x; lq[4 * i + 1] = a.y; lq[4 * i + 2] = a.z; lq[4 * i + 3] = a.w;
+          dq_[4 * i] = c.x; dq_[4 * i + 1] = c.y; dq_[4 * i + 2] = c.z; dq_[4 * i + 3] = c.w;
+        }
+      }
+      tmem_ld_wait();
+      uint32_t pw[8], dw[8];
+      const bool full_tile = (qc0 + 15 < len) && (kv0 + 127 < len_kv) && (!kCausal || kv0 + 127 <= qc0);
+      if (full_tile) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - lq[2 * c]);
+          const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - lq[2 * c + 1]);
+          pw[c] = pack_bf16(p0, p1);
+          dw[c] = pack_bf16(p0 * (__uint_as_float(dv[2 * c]) - dq_[2 * c]), p1 * (__uint_as_float(dv[2 * c + 1]) - dq_[2 * c + 1]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float pe[2], de[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int cc = 2 * c + e;
+            const int qi = qc0 + cc;
+            const bool ok = (qi < len) && (kv_row < len_kv) && (!kCausal || kv_row <= qi);
+            pe[e] = ok ? exp2f(__uint_as_float(sv[cc]) * scale_log2 - lq[cc]) : 0.f;
+            de[e] = ok ? pe[e] * (__uint_as_float(dv[cc]) - dq_[cc]) : 0.f;
+          }
+          pw[c] = pack_bf16(pe[0], pe[1]);
+          dw[c] = pack_bf16(de[0], de[1]);
+        }
+      }
+      tmem_st8(tmem_St + lane_off + st * 64 + part * 16, pw);
+      tmem_st8(tmem_dPt + lane_off + st * 64 + part * 16, dw);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&pds_full[st]);
+    }
+    // epilogue: 4 (D = 128) or 2 (D = 64) 64-column chunk jobs {dV, dK} x chunks, one per `part`
+    constexpr int kJobs = 2 * NCH;
+    const bool my_store = part < kJobs;
+    const int acc = part / NCH, ch = part % NCH;
+    if (n_it > 0) {
+      mbar_wait(&acc_done[(n_it - 1) & 1], ((n_it - 1) >> 1) & 1, 46);
+      tc_fence_after();
+      if (my_store) {
+        if (acc == 0) store_acc_tile<D>(tmem_dV, smem + L::oV, 1.f, &tdv, h * D, kv0, b, wq, lane, ch, ch + 1);
+        else store_acc_tile<D>(tmem_dK, smem + L::oK, scale, &tdk, h * D, kv0, b, wq, lane, ch, ch + 1);
+      }
+    } else if (my_store) {
+      uint8_t* stage = smem + (acc == 0 ? L::oV : L::oK) + ch * 16384;
+      for (int jj = 0; jj < 8; ++jj) {
+        float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        store_row_chunk(stage, row, jj, z);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(acc == 0 ? &tdv : &tdk, stage + wq * 4096, h * D + ch * 64, kv0 + wq * 32, b);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBwdRowWarps + 1) tmem_dealloc<1>(tmem_base, 512);
+}
+
+template <int D>
+struct BwdQTsSmem {
+  static constexpr int NCH = D / 64;
+  static constexpr int kQ = NCH * 16384;
+  static constexpr int kKV = NCH * 8192;
+  static constexpr int oQ = 0, oDO = kQ, oK = 2 * kQ, oV = oK + 2 * kKV, oBar = oV + 2 * kKV;
+  static constexpr int kBytes = oBar + 256;
+};
+
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kBwdTsThreads, 1)
+attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                      const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                      const __grid_constant__ CUtensorMap tdq, const float* __restrict__ lse2, const float* __restrict__ delta,
+                      const int* __restrict__ seqlens, int S, int Skv, int S_pad, int nh, float scale, float scale_log2) {
+  using L = BwdQTsSmem<D>;
+  constexpr int NCH = L::NCH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* kv_full = bars + 1;   // [2]
+  uint64_t* kv_empty = bars + 3;  // [2]
+  uint64_t* sdp_full = bars + 5;  // [2]
+  uint64_t* ds_full = bars + 7;   // [2]
+  uint64_t* acc_done = bars + 9;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  const int len = seqlens ? min(seqlens[b], S) : S;
+  const int len_kv = seqlens ? len : Skv;
+  const int kv_end = kCausal ? min(len_kv, q0 + 128) : len_kv;
+  const int n_kv = (q0 < len) ? (kv_end + 63) / 64 : 0;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_bwd_dq_ts: smem misaligned\n"); __trap(); }
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&ds_full[i], kBwdRowWarps * 32);
+    }
+    fence_mbar_init();
+  }
+  if (warp == kBwdRowWarps + 1) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
+
+  if (warp == kBwdRowWarps && lane == 0 && n_kv > 0) {
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    mbar_arrive_expect_tx(q_full, 2 * 128 * D * 2);
+    for (int c = 0; c < NCH; ++c) {
+      tma_load_3d(smem + L::oQ + c * 16384, &tq, q_full, h * D + c * 64, q0, b);
+      tma_load_3d(smem + L::oDO + c * 16384, &tdo, q_full, h * D + c * 64, q0, b);
+    }
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1, 50);
+      mbar_arrive_expect_tx(&kv_full[st], 2 * 64 * D * 2);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smem + L::oK + st * L::kKV + c * 8192, &tk, &kv_full[st], h * D + c * 64, j * 64, b);
+        tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &kv_full[st], h * D + c * 64, j * 64, b);
+      }
+    }
+  } else if (warp == kBwdRowWarps + 1 && lane == 0 && n_kv > 0) {
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+    const uint32_t sQ = smem_u32(smem + L::oQ), sDO = smem_u32(smem + L::oDO), sK = smem_u32(smem + L::oK),
+                   sV = smem_u32(smem + L::oV);
+    auto issue_s = [&](int j) {
+      const int st = j & 1;
+      mbar_wait(&kv_full[st], (j >> 1) & 1, 51);
+      tc_fence_after();
+      mma_tile(tmem_S + st * 64, sQ, false, 16384, sK + st * L::kKV, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_dP + st * 64, sDO, false, 16384, sV + st * L::kKV, false, 8192, D / 16, idesc_s, false);
+      umma_commit(&sdp_full[st]);
+    };
+    mbar_wait(q_full, 0, 52);
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_s(j + 1);
+      const int st = j & 1;
+      mbar_wait(&ds_full[st], (j >> 1) & 1, 53);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)   // dQ += dS K_j : A = dS from TMEM
+        umma_ts(tmem_dQ, tmem_dP + st * 64 + 16 * ks, op_desc(sK + st * L::kKV, true, 8192, ks), idesc_acc, (j > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&kv_empty[st]);
+      umma_commit(&acc_done[st]);
+    }
+  } else if (warp < kBwdRowWarps) {
+    const int wq = warp & 3, part = warp >> 2;
+    const int row = wq * 32 + lane;
+    const int q_row = q0 + row;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const size_t sidx = (static_cast<size_t>(b) * nh + h) * S_pad + min(q_row, S_pad - 1);
+    const float my_lse = lse2[sidx], my_delta = delta[sidx];
+    const bool row_ok = q_row < len;
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1;
+      const int kc0 = j * 64 + part * 16;
+      mbar_wait(&sdp_full[st], (j >> 1) & 1, 54);
+      tc_fence_after();
+      uint32_t sv[16], dv[16];
+      tmem_ld16(tmem_S + lane_off + st * 64 + part * 16, sv);
+      tmem_ld16(tmem_dP + lane_off + st * 64 + part * 16, dv);
+      tmem_ld_wait();
+      uint32_t dw[8];
+      const bool full_tile = (q0 + 127 < len) && (kc0 + 15 < len_kv) && (!kCausal || kc0 + 15 <= q0);
+      if (full_tile) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - my_lse);
+          const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - my_lse);
+          dw[c] = pack_bf16(p0 * (__uint_as_float(dv[2 * c]) - my_delta), p1 * (__uint_as_float(dv[2 * c + 1]) - my_delta));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float de[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int cc = 2 * c + e;
+            const int kvi = kc0 + cc;
+            const bool ok = row_ok && (kvi < len_kv) && (!kCausal || kvi <= q_row);
+            const float pe = ok ? exp2f(__uint_as_float(sv[cc]) * scale_log2 - my_lse) : 0.f;
+            de[e] = ok ? pe * (__uint_as_float(dv[cc]) - my_delta) : 0.f;
+          }
+          dw[c] = pack_bf16(de[0], de[1]);
+        }
+      }
+      tmem_st8(tmem_dP + lane_off + st * 64 + part * 16, dw);
+      tmem_st_wait();
+      tc_fence_before();
+      mbar_arrive(&ds_full[st]);
+    }
+    const bool my_store = part < NCH;
+    if (n_kv > 0) {
+      mbar_wait(&acc_done[(n_kv - 1) & 1], ((n_kv - 1) >> 1) & 1, 56);
+      tc_fence_after();
+      if (my_store) store_acc_tile<D>(tmem_dQ, smem + L::oQ, scale, &tdq, h * D, q0, b, wq, lane, part, part + 1);
+    } else if (my_store) {
+      for (int jj = 0; jj < 8; ++jj) {
+        float z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        store_row_chunk(smem + L::oQ + part * 16384, row, jj, z);
+      }
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_3d(&tdq, smem + L::oQ + part * 16384 + wq * 4096, h * D + part * 64, q0 + wq * 32, b);
+        tma_store_commit();
+        tma_store_wait_all<0>();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBwdRowWarps + 1) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ================================================================================================ host
 template <typename K>
 static int set_smem(K kern, int bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
-template <int D, bool C>
-static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
-                      const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st,
-                      const uint8_t* kv_mask = nullptr, int mask_ld = 0) {
-  auto kern = attn_fwd_kernel<D, C>;
+// DLLM_ATTN_LEGACY=1 selects the round-1 data paths (P / dS staged through shared memory) for same-box A/B runs
+static bool attn_legacy() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DLLM_ATTN_LEGACY");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
+template <int D, bool C, bool PT>
+static int launch_fwd_pt(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
+                         const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st, const uint8_t* kv_mask,
+                         int mask_ld) {
+  auto kern = attn_fwd_kernel<D, C, PT>;
   static bool once = false;
   if (!once) {
-    if (set_smem(kern, FwdSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
+    if (set_smem(kern, FwdSmem<D, PT>::kBytes)) return DLLM_ERR_LAUNCH;
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     once = true;
   }
   dim3 grid((S + 127) / 128, nh, B);
-  kern<<<grid, kAttnThreads, FwdSmem<D>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, Skv, nh, scale_log2, kv_mask, mask_ld);
+  kern<<<grid, kAttnThreads, FwdSmem<D, PT>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, Skv, nh, scale_log2, kv_mask, mask_ld);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+template <int D, bool C>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
+                      const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st,
+                      const uint8_t* kv_mask = nullptr, int mask_ld = 0) {
+  return attn_legacy() ? launch_fwd_pt<D, C, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, scale_log2, st, kv_mask, mask_ld)
+                       : launch_fwd_pt<D, C, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, scale_log2, st, kv_mask, mask_ld);
 }
 
 int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int nh,
@@ -804,9 +1251,12 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
                       int B, int S, int Skv, int nh, long ld_o, float scale, cudaStream_t st) {
   auto k1 = attn_bwd_dkdv_kernel<D, C>;
   auto k2 = attn_bwd_dq_kernel<D, C>;
+  auto k1t = attn_bwd_dkdv_ts_kernel<D, C>;
+  auto k2t = attn_bwd_dq_ts_kernel<D, C>;
   static bool once = false;
   if (!once) {
     if (set_smem(k1, BwdKVSmem<D>::kBytes) || set_smem(k2, BwdQSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
+    if (set_smem(k1t, BwdKVTsSmem<D>::kBytes) || set_smem(k2t, BwdQTsSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
     once = true;
   }
   const int Sp = s_pad(S);
@@ -814,10 +1264,17 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
   attn_bwd_prep_kernel<D><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(dout, out, lse, delta, lse2, B, S,
                                                                                            Sp, nh, ld_o);
   dim3 grid_kv((Skv + 127) / 128, nh, B), grid_q((S + 127) / 128, nh, B);
-  k1<<<grid_kv, kBwdThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Skv, Sp, nh,
-                                                          scale, scale * kLog2e);
-  k2<<<grid_q, kBwdThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, Skv, Sp, nh, scale,
-                                                        scale * kLog2e);
+  if (attn_legacy()) {
+    k1<<<grid_kv, kBwdThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Skv, Sp, nh,
+                                                            scale, scale * kLog2e);
+    k2<<<grid_q, kBwdThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, Skv, Sp, nh, scale,
+                                                          scale * kLog2e);
+  } else {
+    k1t<<<grid_kv, kBwdTsThreads, BwdKVTsSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Skv, Sp,
+                                                                 nh, scale, scale * kLog2e);
+    k2t<<<grid_q, kBwdTsThreads, BwdQTsSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, Skv, Sp, nh,
+                                                               scale, scale * kLog2e);
+  }
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 

@@ -155,15 +155,21 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_partial_kernel(const bf16* _
 #pragma unroll
   for (int j = 0; j < 8; ++j) { sm_s[j] = s[j]; sm_s[C + j] = q[j]; }
   __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    float a = 0.f, c2 = 0.f;
-    for (int l = 0; l < RL; ++l) {
-      const float* p0 = sm + (static_cast<size_t>(l) * 2) * C;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += p0[c]; c2 += p0[C + c]; }
-    }
-    float* p = partial + ((static_cast<size_t>(n) * nchunks + chunk) * G + g) * 2;
-    p[0] = a;
-    p[1] = c2;
+  // stage 1: one thread per (stat, channel) sums the RL row-lane partials (order-fixed, conflict-free: consecutive threads read
+  // consecutive floats); stage 2: one thread per (group, stat) sums its cpg channels.  (A single thread per group walking RL x cpg
+  // values cost ~7k cycles per CTA — more than streaming the CTA's rows.)
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float a = 0.f;
+    for (int l = 0; l < RL; ++l) a += sm[static_cast<size_t>(l) * 2 * C + i];
+    sm[i] = a;                                   // row-lane 0's slot doubles as the reduced vector (each i touched by one thread only)
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+    const int g = i >> 1, which = i & 1;
+    const float* p0 = sm + which * C + g * cpg;
+    float a = 0.f;
+    for (int c = 0; c < cpg; ++c) a += p0[c];
+    partial[((static_cast<size_t>(n) * nchunks + chunk) * G + g) * 2 + which] = a;
   }
 }
 // forward: stats[n, g] = {mean, rstd};  backward (eps < 0): sums[n, g] = {sum g / count, sum g xhat / count}
@@ -276,9 +282,9 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(const bf16* __r
 // pixel rows per partial-sum CTA: 64 for the big UNet planes, more for the VAE's 512x512 planes so that the finalize pass never walks
 // more than 128 partials, fewer for small planes so that the grid still covers the 148 SMs
 static inline int gn_rows(int HW, int N) {
-  int rows = 64;
+  int rows = 256;                                  // enough rows per CTA to amortise the per-CTA prologue / reduction epilogue ...
   while ((HW + rows - 1) / rows > 128) rows *= 2;
-  while (rows > 8 && static_cast<long>(N) * ((HW + rows - 1) / rows) < 2 * 148 && (HW + rows / 2 - 1) / (rows / 2) <= 128) rows /= 2;
+  while (rows > 8 && static_cast<long>(N) * ((HW + rows - 1) / rows) < 4 * 148 && (HW + rows / 2 - 1) / (rows / 2) <= 128) rows /= 2;   // ... but >= 4 CTAs / SM
   return rows;
 }
 size_t groupnorm_workspace(int N, int HW, int G) {
@@ -303,7 +309,7 @@ static int gn_launch_stats(const bf16* x, float* stats, float* partial, int N, i
 static void gn_launch_apply(const bf16* x, const bf16* w, const bf16* b, const float* stats, bf16* y, int N, int HW, int C, int G, int silu,
                             cudaStream_t s) {
   const GnMap m = gn_map(C);
-  int rows = 32;
+  int rows = 128;
   while (rows > m.RL && static_cast<long>(N) * ((HW + rows - 1) / rows) < 4 * 148) rows /= 2;
   gn_apply_kernel<false><<<dim3((HW + rows - 1) / rows, N), m.threads, 0, s>>>(x, nullptr, w, b, stats, nullptr, nullptr, y, HW, C, G, rows,
                                                                                 m.RL, silu);
@@ -611,7 +617,7 @@ int groupnorm_bwd_nhwc(const void* dy, const void* x, const void* w, const void*
   gn_partial_kernel<true><<<dim3(nchunks, N), m.threads, static_cast<size_t>(m.RL) * 2 * C * sizeof(float), s>>>(
       (const bf16*)x, (const bf16*)dy, (const bf16*)w, (const bf16*)b, stats, partial, HW, C, G, rows, m.RL, silu);
   gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, s>>>(partial, sums, nchunks, G, static_cast<float>(HW) * (C / G), -1.f, N * G);
-  int arows = 32;
+  int arows = 128;
   while (arows > m.RL && static_cast<long>(N) * ((HW + arows - 1) / arows) < 4 * 148) arows /= 2;
   gn_apply_kernel<true><<<dim3((HW + arows - 1) / arows, N), m.threads, 0, s>>>((const bf16*)x, (const bf16*)dy, (const bf16*)w,
                                                                                 (const bf16*)b, stats, sums, (const bf16*)dres, (bf16*)dx,
