@@ -108,7 +108,10 @@ struct FwdSmem {
   static constexpr int kQ = NCH * 16384;       // [NCH][128][128B]
   static constexpr int kKV = NCH * 8192;       // [NCH][64][128B]
   static constexpr int kP = kPT ? 0 : 16384;   // [128][128B]
-  static constexpr int oQ = 0, oK = kQ, oV = oK + 2 * kKV, oP = oV + 2 * kKV, oBar = oP + kP;
+  // K ring: the refill of a K stage can only start when the QK^T that read it has retired, and with two stages the next-but-one QK^T
+  // then waited out the L2 round trip; the 16 KB P no longer needs pays for a third K stage (2 CTAs / SM: 2 x (112 KB + 256 B) fits 227 KB)
+  static constexpr int kKStages = kPT ? 3 : 2;
+  static constexpr int oQ = 0, oK = kQ, oV = oK + kKStages * kKV, oP = oV + 2 * kKV, oBar = oP + kP;
   static constexpr int kBytes = oBar + 256;
 };
 
@@ -127,15 +130,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   constexpr int NCH = L::NCH;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  constexpr int KS = L::kKStages;
   uint64_t* q_full = bars + 0;
-  uint64_t* k_full = bars + 1;   // [2]
-  uint64_t* k_empty = bars + 3;  // [2]
-  uint64_t* v_full = bars + 5;   // [2]
-  uint64_t* v_empty = bars + 7;  // [2]
-  uint64_t* s_full = bars + 9;   // [2]
-  uint64_t* p_full = bars + 11;  // [2]  (kPT: P(j) lives in S buffer j & 1; legacy: only [0] is used)
-  uint64_t* pv_done = bars + 13; // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* k_full = bars + 1;        // [KS]  ring: j % KS, phase (j / KS) & 1
+  uint64_t* k_empty = k_full + KS;    // [KS]
+  uint64_t* v_full = k_empty + KS;    // [2]
+  uint64_t* v_empty = v_full + 2;     // [2]
+  uint64_t* s_full = v_empty + 2;     // [2]
+  uint64_t* p_full = s_full + 2;      // [2]  (kPT: P(j) lives in S buffer j & 1; legacy: only [0] is used)
+  uint64_t* pv_done = p_full + 2;     // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -147,8 +151,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_fwd: smem misaligned\n"); __trap(); }
     mbar_init(q_full, 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 128);
@@ -169,12 +173,19 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
     mbar_arrive_expect_tx(q_full, 128 * D * 2);
     for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oQ + c * 16384, &tq, q_full, h * D + c * 64, q0, b);
+    // K runs ahead of V: all K tiles the ring can hold are requested before the producer blocks on the V stage of tile j
+    int jk = 0;
+    auto load_k = [&](int jj) {
+      const int ks = jj % KS;
+      mbar_wait(&k_empty[ks], ((jj / KS) & 1) ^ 1, 10);
+      mbar_arrive_expect_tx(&k_full[ks], 64 * D * 2);
+      for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oK + ks * L::kKV + c * 8192, &tk, &k_full[ks], h * D + c * 64, jj * 64, b);
+    };
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1;
       const uint32_t ph = (j >> 1) & 1;
-      mbar_wait(&k_empty[st], ph ^ 1, 10);
-      mbar_arrive_expect_tx(&k_full[st], 64 * D * 2);
-      for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oK + st * L::kKV + c * 8192, &tk, &k_full[st], h * D + c * 64, j * 64, b);
+      while (jk < n_kv && jk < j + KS - 1) load_k(jk++);     // K(j) .. K(j + KS - 2) need no stage that V(j)'s consumer frees
+      if (jk <= j) load_k(jk++);
       mbar_wait(&v_empty[st], ph ^ 1, 11);
       mbar_arrive_expect_tx(&v_full[st], 64 * D * 2);
       for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &v_full[st], h * D + c * 64, j * 64, b);
@@ -187,11 +198,11 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
                    sP = smem_u32(smem + L::oP);
     (void)sP;
     auto issue_qk = [&](int j) {
-      const int st = j & 1;
-      mbar_wait(&k_full[st], (j >> 1) & 1, 12);
+      const int ks = j % KS;
+      mbar_wait(&k_full[ks], (j / KS) & 1, 12);
       tc_fence_after();
-      mma_tile(tmem_S + (j & 1) * 64, sQ, false, 16384, sK + st * L::kKV, false, 8192, D / 16, idesc_qk, false);
-      umma_commit(&k_empty[st]);
+      mma_tile(tmem_S + (j & 1) * 64, sQ, false, 16384, sK + ks * L::kKV, false, 8192, D / 16, idesc_qk, false);
+      umma_commit(&k_empty[ks]);
       umma_commit(&s_full[j & 1]);
     };
     mbar_wait(q_full, 0, 13);
@@ -800,12 +811,19 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 
+// Operand ring depth.  With two stages the TMA refill of a stage could only start when the accumulate MMAs reading it had retired, and the
+// next S / dP GEMMs — issued right behind those MMAs — then sat out a full L2 round trip every iteration (the r01 kernels measured
+// ~3200 clk per iteration against ~1100 clk of tensor work; both backward kernels, with 4 vs 3 tile-GEMMs, had the SAME time per
+// iteration).  The shared memory freed by moving P / dS to TMEM pays for four stages, so loads run three iterations ahead.
+constexpr int kBwdRing = 4;
+
 template <int D>
 struct BwdKVTsSmem {
   static constexpr int NCH = D / 64;
   static constexpr int kKV = NCH * 16384;  // [NCH][128][128B]
   static constexpr int kQ = NCH * 8192;    // [NCH][64][128B]
-  static constexpr int oK = 0, oV = kKV, oQ = 2 * kKV, oDO = oQ + 2 * kQ, oStat = oDO + 2 * kQ, oBar = oStat + 2 * 512;  // stats: [2][lse 64 | delta 64] fp32
+  static constexpr int oK = 0, oV = kKV, oQ = 2 * kKV, oDO = oQ + kBwdRing * kQ, oStat = oDO + kBwdRing * kQ,
+                       oBar = oStat + kBwdRing * 512;  // stats: [ring][lse 64 | delta 64] fp32
   static constexpr int kBytes = oBar + 256;
 };
 
@@ -821,12 +839,12 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
   uint64_t* kv_full = bars + 0;
-  uint64_t* qdo_full = bars + 1;   // [2]
-  uint64_t* qdo_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;   // [2]
-  uint64_t* pds_full = bars + 7;   // [2]
-  uint64_t* acc_done = bars + 9;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* qdo_full = bars + 1;                  // [kBwdRing]  smem ring: it % kBwdRing, phase (it / kBwdRing) & 1
+  uint64_t* qdo_empty = qdo_full + kBwdRing;      // [kBwdRing]
+  uint64_t* sdp_full = qdo_empty + kBwdRing;      // [2]         TMEM double buffer: it & 1, phase (it >> 1) & 1
+  uint64_t* pds_full = sdp_full + 2;              // [2]
+  uint64_t* acc_done = pds_full + 2;              // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -839,8 +857,9 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_bwd_dkdv_ts: smem misaligned\n"); __trap(); }
     mbar_init(kv_full, 1);
+    for (int i = 0; i < kBwdRing; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
       mbar_init(&pds_full[i], kBwdRowWarps * 32);
     }
     fence_mbar_init();
@@ -866,16 +885,16 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
     const float* lse_bh = lse2 + (static_cast<size_t>(b) * nh + h) * S_pad;
     const float* del_bh = delta + (static_cast<size_t>(b) * nh + h) * S_pad;
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
+      const int rs = it % kBwdRing;
       const int qr0 = (i_begin + it) * 64;
-      mbar_wait(&qdo_empty[st], ((it >> 1) & 1) ^ 1, 40);
-      mbar_arrive_expect_tx(&qdo_full[st], 2 * 64 * D * 2 + 512);
+      mbar_wait(&qdo_empty[rs], ((it / kBwdRing) & 1) ^ 1, 40);
+      mbar_arrive_expect_tx(&qdo_full[rs], 2 * 64 * D * 2 + 512);
       for (int c = 0; c < NCH; ++c) {
-        tma_load_3d(smem + L::oQ + st * L::kQ + c * 8192, &tq, &qdo_full[st], h * D + c * 64, qr0, b);
-        tma_load_3d(smem + L::oDO + st * L::kQ + c * 8192, &tdo, &qdo_full[st], h * D + c * 64, qr0, b);
+        tma_load_3d(smem + L::oQ + rs * L::kQ + c * 8192, &tq, &qdo_full[rs], h * D + c * 64, qr0, b);
+        tma_load_3d(smem + L::oDO + rs * L::kQ + c * 8192, &tdo, &qdo_full[rs], h * D + c * 64, qr0, b);
       }
-      bulk_load_1d(smem + L::oStat + st * 512, lse_bh + qr0, 256, &qdo_full[st]);          // S_pad is a multiple of 64: always in range
-      bulk_load_1d(smem + L::oStat + st * 512 + 256, del_bh + qr0, 256, &qdo_full[st]);
+      bulk_load_1d(smem + L::oStat + rs * 512, lse_bh + qr0, 256, &qdo_full[rs]);          // S_pad is a multiple of 64: always in range
+      bulk_load_1d(smem + L::oStat + rs * 512 + 256, del_bh + qr0, 256, &qdo_full[rs]);
     }
   } else if (warp == kBwdRowWarps + 1 && lane == 0 && n_it > 0) {
     // ---------------- MMA issuer ----------------
@@ -884,27 +903,27 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
     const uint32_t sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV), sQ = smem_u32(smem + L::oQ),
                    sDO = smem_u32(smem + L::oDO);
     auto issue_s = [&](int it) {
-      const int st = it & 1;
-      mbar_wait(&qdo_full[st], (it >> 1) & 1, 41);
+      const int st = it & 1, rs = it % kBwdRing;
+      mbar_wait(&qdo_full[rs], (it / kBwdRing) & 1, 41);
       tc_fence_after();
-      mma_tile(tmem_St + st * 64, sK, false, 16384, sQ + st * L::kQ, false, 8192, D / 16, idesc_s, false);
-      mma_tile(tmem_dPt + st * 64, sV, false, 16384, sDO + st * L::kQ, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_St + st * 64, sK, false, 16384, sQ + rs * L::kQ, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_dPt + st * 64, sV, false, 16384, sDO + rs * L::kQ, false, 8192, D / 16, idesc_s, false);
       umma_commit(&sdp_full[st]);
     };
     mbar_wait(kv_full, 0, 42);
     issue_s(0);
     for (int it = 0; it < n_it; ++it) {
       if (it + 1 < n_it) issue_s(it + 1);
-      const int st = it & 1;
+      const int st = it & 1, rs = it % kBwdRing;
       mbar_wait(&pds_full[st], (it >> 1) & 1, 43);
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)   // dV += P^T dO_i : A = P^T from TMEM (k-step ks = q columns [16 ks, 16 ks + 16) at column 16 ks)
-        umma_ts(tmem_dV, tmem_St + st * 64 + 16 * ks, op_desc(sDO + st * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+        umma_ts(tmem_dV, tmem_St + st * 64 + 16 * ks, op_desc(sDO + rs * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)   // dK += dS^T Q_i
-        umma_ts(tmem_dK, tmem_dPt + st * 64 + 16 * ks, op_desc(sQ + st * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
-      umma_commit(&qdo_empty[st]);
+        umma_ts(tmem_dK, tmem_dPt + st * 64 + 16 * ks, op_desc(sQ + rs * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&qdo_empty[rs]);
       umma_commit(&acc_done[st]);
     }
   } else if (warp < kBwdRowWarps) {
@@ -914,9 +933,9 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
     const int kv_row = kv0 + row;
     const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
     for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1;
+      const int st = it & 1, rs = it % kBwdRing;
       const int qc0 = (i_begin + it) * 64 + part * 16;  // first q index of my 16 columns
-      mbar_wait(&qdo_full[st], (it >> 1) & 1, 45);       // the bulk-copied lse / delta of this q tile are visible to this thread
+      mbar_wait(&qdo_full[rs], (it / kBwdRing) & 1, 45);  // the bulk-copied lse / delta of this q tile are visible to this thread
       mbar_wait(&sdp_full[st], (it >> 1) & 1, 44);
       tc_fence_after();
       uint32_t sv[16], dv[16];
@@ -924,8 +943,8 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
       tmem_ld16(tmem_dPt + lane_off + st * 64 + part * 16, dv);
       float lq[16], dq_[16];
       {
-        const float4* ls = reinterpret_cast<const float4*>(smem + L::oStat + st * 512) + part * 4;
-        const float4* ds4 = reinterpret_cast<const float4*>(smem + L::oStat + st * 512 + 256) + part * 4;
+        const float4* ls = reinterpret_cast<const float4*>(smem + L::oStat + rs * 512) + part * 4;
+        const float4* ds4 = reinterpret_cast<const float4*>(smem + L::oStat + rs * 512 + 256) + part * 4;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float4 a = ls[i], c = ds4[i];
@@ -1002,7 +1021,7 @@ struct BwdQTsSmem {
   static constexpr int NCH = D / 64;
   static constexpr int kQ = NCH * 16384;
   static constexpr int kKV = NCH * 8192;
-  static constexpr int oQ = 0, oDO = kQ, oK = 2 * kQ, oV = oK + 2 * kKV, oBar = oV + 2 * kKV;
+  static constexpr int oQ = 0, oDO = kQ, oK = 2 * kQ, oV = oK + kBwdRing * kKV, oBar = oV + kBwdRing * kKV;
   static constexpr int kBytes = oBar + 256;
 };
 
@@ -1017,12 +1036,12 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
   uint64_t* q_full = bars + 0;
-  uint64_t* kv_full = bars + 1;   // [2]
-  uint64_t* kv_empty = bars + 3;  // [2]
-  uint64_t* sdp_full = bars + 5;  // [2]
-  uint64_t* ds_full = bars + 7;   // [2]
-  uint64_t* acc_done = bars + 9;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* kv_full = bars + 1;                 // [kBwdRing]
+  uint64_t* kv_empty = kv_full + kBwdRing;      // [kBwdRing]
+  uint64_t* sdp_full = kv_empty + kBwdRing;     // [2]
+  uint64_t* ds_full = sdp_full + 2;             // [2]
+  uint64_t* acc_done = ds_full + 2;             // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
@@ -1034,8 +1053,9 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_bwd_dq_ts: smem misaligned\n"); __trap(); }
     mbar_init(q_full, 1);
+    for (int i = 0; i < kBwdRing; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
       mbar_init(&ds_full[i], kBwdRowWarps * 32);
     }
     fence_mbar_init();
@@ -1055,12 +1075,12 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       tma_load_3d(smem + L::oDO + c * 16384, &tdo, q_full, h * D + c * 64, q0, b);
     }
     for (int j = 0; j < n_kv; ++j) {
-      const int st = j & 1;
-      mbar_wait(&kv_empty[st], ((j >> 1) & 1) ^ 1, 50);
-      mbar_arrive_expect_tx(&kv_full[st], 2 * 64 * D * 2);
+      const int rs = j % kBwdRing;
+      mbar_wait(&kv_empty[rs], ((j / kBwdRing) & 1) ^ 1, 50);
+      mbar_arrive_expect_tx(&kv_full[rs], 2 * 64 * D * 2);
       for (int c = 0; c < NCH; ++c) {
-        tma_load_3d(smem + L::oK + st * L::kKV + c * 8192, &tk, &kv_full[st], h * D + c * 64, j * 64, b);
-        tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &kv_full[st], h * D + c * 64, j * 64, b);
+        tma_load_3d(smem + L::oK + rs * L::kKV + c * 8192, &tk, &kv_full[rs], h * D + c * 64, j * 64, b);
+        tma_load_3d(smem + L::oV + rs * L::kKV + c * 8192, &tv, &kv_full[rs], h * D + c * 64, j * 64, b);
       }
     }
   } else if (warp == kBwdRowWarps + 1 && lane == 0 && n_kv > 0) {
@@ -1069,24 +1089,24 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     const uint32_t sQ = smem_u32(smem + L::oQ), sDO = smem_u32(smem + L::oDO), sK = smem_u32(smem + L::oK),
                    sV = smem_u32(smem + L::oV);
     auto issue_s = [&](int j) {
-      const int st = j & 1;
-      mbar_wait(&kv_full[st], (j >> 1) & 1, 51);
+      const int st = j & 1, rs = j % kBwdRing;
+      mbar_wait(&kv_full[rs], (j / kBwdRing) & 1, 51);
       tc_fence_after();
-      mma_tile(tmem_S + st * 64, sQ, false, 16384, sK + st * L::kKV, false, 8192, D / 16, idesc_s, false);
-      mma_tile(tmem_dP + st * 64, sDO, false, 16384, sV + st * L::kKV, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_S + st * 64, sQ, false, 16384, sK + rs * L::kKV, false, 8192, D / 16, idesc_s, false);
+      mma_tile(tmem_dP + st * 64, sDO, false, 16384, sV + rs * L::kKV, false, 8192, D / 16, idesc_s, false);
       umma_commit(&sdp_full[st]);
     };
     mbar_wait(q_full, 0, 52);
     issue_s(0);
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) issue_s(j + 1);
-      const int st = j & 1;
+      const int st = j & 1, rs = j % kBwdRing;
       mbar_wait(&ds_full[st], (j >> 1) & 1, 53);
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks)   // dQ += dS K_j : A = dS from TMEM
-        umma_ts(tmem_dQ, tmem_dP + st * 64 + 16 * ks, op_desc(sK + st * L::kKV, true, 8192, ks), idesc_acc, (j > 0 || ks > 0) ? 1u : 0u);
-      umma_commit(&kv_empty[st]);
+        umma_ts(tmem_dQ, tmem_dP + st * 64 + 16 * ks, op_desc(sK + rs * L::kKV, true, 8192, ks), idesc_acc, (j > 0 || ks > 0) ? 1u : 0u);
+      umma_commit(&kv_empty[rs]);
       umma_commit(&acc_done[st]);
     }
   } else if (warp < kBwdRowWarps) {

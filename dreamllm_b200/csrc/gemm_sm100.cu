@@ -20,7 +20,7 @@
 namespace dllm {
 
 constexpr int BM = 128;  // A rows per CTA == TMEM lanes
-constexpr int BN = 256;  // UMMA N
+constexpr int BN = 256;  // default UMMA N (kBN = 128 is instantiated for outputs whose width tiles badly by 256: see pick_bn)
 constexpr int BK = 64;   // 64 bf16 = one 128-byte swizzle line
 constexpr int UMMA_K = 16;
 // epilogue warps: 4 (one per TMEM lane quarter; 6/4 operand stages) for mainloop-bound shapes, 8 (two per quarter, each draining half
@@ -32,17 +32,19 @@ constexpr int kEpiWarp0 = 4;
 #define DLLM_EPI_BUFS 2   // staging buffers per epilogue warp (TMA stores in flight per warp)
 #endif
 
-template <int kCta, int kEpiWarps = 4>
+template <int kCta, int kEpiWarps = 4, int kBN = BN>
 struct GemmCfg {
-  static constexpr int kBRows = BN / kCta;  // rows of B each CTA loads
+  static constexpr int kBRows = kBN / kCta;  // rows of B each CTA loads
   static constexpr int kABytes = BM * BK * 2;
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kEpiBufs = DLLM_EPI_BUFS;
-  static constexpr int kStages = (kEpiWarps == 8) ? ((kCta == 1) ? 3 : 5) : ((kCta == 1) ? 4 : 6);  // operand stages + store staging <= 227 KB
   static constexpr int kEpiBufBytes = 32 * 128;                // 32 rows x 128 B per warp-store
   static constexpr int kEpiBytes = kEpiWarps * kEpiBufs * kEpiBufBytes;
   static constexpr int kBarBytes = 1024;
+  // operand stages + store staging + barriers <= 227 KB:  kBN 256: 6 / 5 (2-CTA, 4 / 8 epilogue warps), 4 / 3 (1-CTA);  kBN 128: 8 / 6, 6 / 5
+  static constexpr int kStagesFit = (227 * 1024 - kEpiBytes - kBarBytes - 1024) / kStageBytes;
+  static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
   static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kBarBytes + 1024 /*align slack*/;
 };
 
@@ -76,16 +78,16 @@ __device__ __forceinline__ float epi_act(float x, int act) {
 // kEpi: 0 = plain store, 1 = + bias / row-group bias / residual, 2 = 1 + activation.  Compile-time so that the plain and the
 // bias-only epilogues carry none of the (inlined expf / erff) activation code: with a runtime switch every element paid ~78 issue
 // slots of predicated-off instructions and bias GEMMs with small K ran at 200 TF/s (profiles/r01_gemm_smallk_epilogue.md).
-template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEpiWarps = 4>
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEpiWarps = 4, int kBN = BN>
 __global__ void __launch_bounds__(gemm_threads(kEpiWarps), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi, ConvGeom cg,
             int* __restrict__ tile_counter) {
-  using Cfg = GemmCfg<kCta, kEpiWarps>;
+  using Cfg = GemmCfg<kCta, kEpiWarps, kBN>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kOutF32 = sizeof(OutT) == 4;
   constexpr int CH = kOutF32 ? 32 : 64;  // output columns per 128-byte store line
-  constexpr int kChunks = BN / CH;
+  constexpr int kChunks = kBN / CH;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -140,7 +142,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   // ---- persistent tile schedule (identical sequence in every role) ----
   const int tile_m = BM * kCta;
   const int num_m_tiles = (M + tile_m - 1) / tile_m;
-  const int num_n_tiles = (N + BN - 1) / BN;
+  const int num_n_tiles = (N + kBN - 1) / kBN;
   const int num_tiles = num_m_tiles * num_n_tiles;
   const int num_kb = (K + BK - 1) / BK;
   const int tiles_per_group = group_m * num_n_tiles;
@@ -192,7 +194,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int m0 = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
-      const int n0 = n_blk * BN + static_cast<int>(cta_rank) * Cfg::kBRows;
+      const int n0 = n_blk * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
         uint8_t* a_s = smem + stage * Cfg::kStageBytes;
@@ -251,7 +253,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     }
   } else if (warp_idx == 1 && lane == 0 && cta_rank == 0) {
     // ======================= MMA issuer (leader CTA only) =======================
-    constexpr uint32_t idesc = make_idesc_bf16(BM * kCta, BN, kAMN, kBMN);
+    constexpr uint32_t idesc = make_idesc_bf16(BM * kCta, kBN, kAMN, kBMN);
     constexpr uint32_t a_adv = kAMN ? 2048u : 32u;  // bytes per UMMA_K step
     constexpr uint32_t b_adv = kBMN ? 2048u : 32u;
     constexpr uint32_t a_lbo = kAMN ? 8192u : 16u;
@@ -268,7 +270,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const uint32_t aphase = (it >> 1) & 1;
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 2);
       tc_fence_after();
-      const uint32_t tmem_d = tmem_base + as * BN;
+      const uint32_t tmem_d = tmem_base + as * kBN;
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
@@ -310,10 +312,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
       const int row0 = m_blk * tile_m + static_cast<int>(cta_rank) * BM + wq * 32;
-      const int col0 = n_blk * BN;
+      const int col0 = n_blk * kBN;
       mbar_wait(&tmem_full_bar[as], aphase, 4);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * BN;
+      const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * kBN;
 #pragma unroll 1
       for (int c = chalf * (kChunks / kParts); c < (chalf + 1) * (kChunks / kParts); ++c) {
         uint32_t v[kOutF32 ? 32 : 64];
@@ -481,11 +483,18 @@ static int* tile_counter_slot(cudaStream_t stream) {
   return slot;
 }
 
-template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEW = 4>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
-                       const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}) {
-  using Cfg = GemmCfg<kCta, kEW>;
-  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW>;
+// N-tile width: 256 unless 128-wide tiles waste less padded MMA work (N = 128: 1x vs 2x; 320: 384 vs 512; 640: 640 vs 768).  The UNet's
+// 320 / 640-channel levels and the VAE's 128-channel level carry about half of their conv / GEMM FLOPs (tile quantisation).
+static inline int pick_bn(int N) {
+  const int c256 = (N + 255) / 256 * 256, c128 = (N + 127) / 128 * 128;
+  return c128 < c256 ? 128 : 256;
+}
+
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEW = 4, int kBN = BN>
+static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
+                          const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}) {
+  using Cfg = GemmCfg<kCta, kEW, kBN>;
+  auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW, kBN>;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes) != cudaSuccess)
@@ -493,7 +502,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     attr_set = true;
   }
   const int tile_m = BM * kCta;
-  const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + BN - 1) / BN);
+  const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + kBN - 1) / kBN);
   int avail = num_sms() - g_reserved_sms;
   if (avail < 2) avail = 2;
   const int max_clusters = avail / kCta;
@@ -516,6 +525,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi, cg, counter);
   return e == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
+// `bn` must be the value the B tensor map's box was built for (pick_bn(N))
+template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEW = 4>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
+                       const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}, int bn = BN) {
+  if (bn == 128) return launch_gemm_bn<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW, 128>(ta, tb, tc, M, N, K, epi, stream, cg);
+  return launch_gemm_bn<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW, 256>(ta, tb, tc, M, N, K, epi, stream, cg);
+}
 
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
               int b_mn, int out_fp32, int cta_pair, cudaStream_t stream) {
@@ -531,6 +547,8 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return DLLM_ERR_ALIGN;
   GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), ldr, act, nullptr, 1};
   const int kcta = (cta_pair < 0) ? (M > BM ? 2 : 1) : (cta_pair ? 2 : 1);
+  const int bn = pick_bn(N);
+  const ConvGeom nocg{1, 1, 1, 1};
   CUtensorMap ta, tb, tc;
   int rc;
   // A
@@ -538,7 +556,7 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   else rc = make_tmap_2d(&ta, A, 2, K, M, lda, BK, 64);
   if (rc) return rc;
   // B
-  if (!b_mn) rc = make_tmap_2d(&tb, B, 2, N, K, ldb, BN / kcta, BK);
+  if (!b_mn) rc = make_tmap_2d(&tb, B, 2, N, K, ldb, bn / kcta, BK);
   else rc = make_tmap_2d(&tb, B, 2, K, N, ldb, BK, 64);
   if (rc) return rc;
   // C: per-warp store boxes of 32 rows x 128 bytes
@@ -549,19 +567,19 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   if (emode != 0) {
     // fused epilogues exist for the forward (NT, bf16 out) contraction only
     if (a_mn || b_mn || out_fp32) return DLLM_ERR_UNSUPPORTED;
-    if (kcta == 2) return emode == 2 ? launch_gemm<2, false, false, bf16, false, 2, 8>(ta, tb, tc, M, N, K, epi, stream)
-                                     : launch_gemm<2, false, false, bf16, false, 1, 8>(ta, tb, tc, M, N, K, epi, stream);
-    return emode == 2 ? launch_gemm<1, false, false, bf16, false, 2, 8>(ta, tb, tc, M, N, K, epi, stream)
-                      : launch_gemm<1, false, false, bf16, false, 1, 8>(ta, tb, tc, M, N, K, epi, stream);
+    if (kcta == 2) return emode == 2 ? launch_gemm<2, false, false, bf16, false, 2, 8>(ta, tb, tc, M, N, K, epi, stream, nocg, bn)
+                                     : launch_gemm<2, false, false, bf16, false, 1, 8>(ta, tb, tc, M, N, K, epi, stream, nocg, bn);
+    return emode == 2 ? launch_gemm<1, false, false, bf16, false, 2, 8>(ta, tb, tc, M, N, K, epi, stream, nocg, bn)
+                      : launch_gemm<1, false, false, bf16, false, 1, 8>(ta, tb, tc, M, N, K, epi, stream, nocg, bn);
   }
   if (!a_mn && !b_mn && !out_fp32 && K <= 2048) {   // epilogue-bound plain forward GEMMs (UNet / CLIP projections)
-    if (kcta == 2) return launch_gemm<2, false, false, bf16, false, 0, 8>(ta, tb, tc, M, N, K, epi, stream);
-    return launch_gemm<1, false, false, bf16, false, 0, 8>(ta, tb, tc, M, N, K, epi, stream);
+    if (kcta == 2) return launch_gemm<2, false, false, bf16, false, 0, 8>(ta, tb, tc, M, N, K, epi, stream, nocg, bn);
+    return launch_gemm<1, false, false, bf16, false, 0, 8>(ta, tb, tc, M, N, K, epi, stream, nocg, bn);
   }
 #define DLLM_GEMM_CASE(CTA, AMN, BMN)                                                                 \
   if (kcta == CTA && (a_mn != 0) == AMN && (b_mn != 0) == BMN) {                                      \
-    return out_fp32 ? launch_gemm<CTA, AMN, BMN, float>(ta, tb, tc, M, N, K, epi, stream)             \
-                    : launch_gemm<CTA, AMN, BMN, bf16>(ta, tb, tc, M, N, K, epi, stream);             \
+    return out_fp32 ? launch_gemm<CTA, AMN, BMN, float>(ta, tb, tc, M, N, K, epi, stream, nocg, bn)   \
+                    : launch_gemm<CTA, AMN, BMN, bf16>(ta, tb, tc, M, N, K, epi, stream, nocg, bn);   \
   }
   DLLM_GEMM_CASE(1, false, false)
   DLLM_GEMM_CASE(1, false, true)
@@ -607,18 +625,19 @@ int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, 
   }
   const int M = Nimg * HW, K = 9 * Cin;
   const int kcta = (M > BM) ? 2 : 1;
+  const int bn = pick_bn(Cout);
   CUtensorMap ta, tb, tc;
   int rc;
   if ((rc = make_tmap_nhwc(&ta, x, Nimg, H, W, Cin, Wb, Hb, Nb))) return rc;
-  if ((rc = make_tmap_2d(&tb, w, 2, Cout, K, K, BN / kcta, BK))) return rc;
+  if ((rc = make_tmap_2d(&tb, w, 2, Cout, K, K, bn / kcta, BK))) return rc;
   if ((rc = make_tmap_2d(&tc, y, 2, M, Cout, Cout, 32, 64))) return rc;
   GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), Cout, 0, static_cast<const bf16*>(rowbias), HW};
   ConvGeom cg{Cin / 64, W, H, HW};
   const bool any_epi = bias || rowbias || residual;
-  if (kcta == 2) return any_epi ? launch_gemm<2, false, false, bf16, true, 1, 8>(ta, tb, tc, M, Cout, K, epi, stream, cg)
-                                : launch_gemm<2, false, false, bf16, true, 0, 4>(ta, tb, tc, M, Cout, K, epi, stream, cg);
-  return any_epi ? launch_gemm<1, false, false, bf16, true, 1, 8>(ta, tb, tc, M, Cout, K, epi, stream, cg)
-                 : launch_gemm<1, false, false, bf16, true, 0, 4>(ta, tb, tc, M, Cout, K, epi, stream, cg);
+  if (kcta == 2) return any_epi ? launch_gemm<2, false, false, bf16, true, 1, 8>(ta, tb, tc, M, Cout, K, epi, stream, cg, bn)
+                                : launch_gemm<2, false, false, bf16, true, 0, 4>(ta, tb, tc, M, Cout, K, epi, stream, cg, bn);
+  return any_epi ? launch_gemm<1, false, false, bf16, true, 1, 8>(ta, tb, tc, M, Cout, K, epi, stream, cg, bn)
+                 : launch_gemm<1, false, false, bf16, true, 0, 4>(ta, tb, tc, M, Cout, K, epi, stream, cg, bn);
 }
 
 }  // namespace dllm

@@ -12,6 +12,10 @@ SHAPES = [
     (384, 768, 320),        # tails in M (2-CTA), N; K not a multiple of 64
     (200, 264, 72),         # ragged everything (multiples of 8 only)
     (1024, 1408, 512),
+    # widths served by the 128-wide N tile (pick_bn: less padded MMA work than 256): VAE C = 128, UNet C = 320 / 640
+    (512, 128, 1152),
+    (300, 320, 192),
+    (1024, 640, 576),
 ]
 MODES = [(False, False), (False, True), (True, True), (True, False)]
 
