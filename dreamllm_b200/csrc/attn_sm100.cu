@@ -155,7 +155,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     for (int i = 0; i < 2; ++i) {
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 128);
+      mbar_init(&p_full[i], kPT ? 4 : 128);      // kPT: one elected arrive per softmax warp (128 same-address arrives serialise)
       mbar_init(&pv_done[i], 1);
     }
     fence_mbar_init();
@@ -320,7 +320,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         tmem_st_wait();
         l_run += ls0 + ls1;
         tc_fence_before();
-        mbar_arrive(&p_full[j & 1]);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[j & 1]);
       } else {
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
@@ -860,7 +861,7 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
     for (int i = 0; i < kBwdRing; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
-      mbar_init(&pds_full[i], kBwdRowWarps * 32);
+      mbar_init(&pds_full[i], kBwdRowWarps);      // one elected arrive per row warp (512 same-address arrives cost ~500 clk per iteration)
     }
     fence_mbar_init();
   }
@@ -983,7 +984,8 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
       tmem_st8(tmem_dPt + lane_off + st * 64 + part * 16, dw);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&pds_full[st]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&pds_full[st]);
     }
     // epilogue: 4 (D = 128) or 2 (D = 64) 64-column chunk jobs {dV, dK} x chunks, one per `part`
     constexpr int kJobs = 2 * NCH;
@@ -1056,7 +1058,7 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
     for (int i = 0; i < kBwdRing; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
-      mbar_init(&ds_full[i], kBwdRowWarps * 32);
+      mbar_init(&ds_full[i], kBwdRowWarps);
     }
     fence_mbar_init();
   }
@@ -1153,7 +1155,8 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       tmem_st8(tmem_dP + lane_off + st * 64 + part * 16, dw);
       tmem_st_wait();
       tc_fence_before();
-      mbar_arrive(&ds_full[st]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ds_full[st]);
     }
     const bool my_store = part < NCH;
     if (n_kv > 0) {

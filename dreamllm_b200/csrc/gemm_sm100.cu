@@ -14,6 +14,8 @@
 //   warp 1    MMA issuer (one elected thread): tcgen05.mma, accumulators in TMEM, double-buffered (2 x 256 cols)
 //   warp 2    TMEM allocator
 //   warps 4-7 epilogue: tcgen05.ld -> convert -> swizzled smem -> per-warp TMA store (overlaps next tile's MMAs)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_sm100.h"
 
@@ -486,6 +488,12 @@ static int* tile_counter_slot(cudaStream_t stream) {
 // N-tile width: 256 unless 128-wide tiles waste less padded MMA work (N = 128: 1x vs 2x; 320: 384 vs 512; 640: 640 vs 768).  The UNet's
 // 320 / 640-channel levels and the VAE's 128-channel level carry about half of their conv / GEMM FLOPs (tile quantisation).
 static inline int pick_bn(int N) {
+  static int forced = -1;                         // DLLM_GEMM_BN=128|256 forces one width (dev A/B runs); default: by padded work
+  if (forced < 0) {
+    const char* e = getenv("DLLM_GEMM_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 128 || forced == 256) return forced;
   const int c256 = (N + 255) / 256 * 256, c128 = (N + 127) / 128 * 128;
   return c128 < c256 ? 128 : 256;
 }

@@ -14,7 +14,7 @@ SHAPES = [
     (1024, 1408, 512),
     # widths served by the 128-wide N tile (pick_bn: less padded MMA work than 256): VAE C = 128, UNet C = 320 / 640
     (512, 128, 1152),
-    (300, 320, 192),
+    (304, 320, 192),
     (1024, 640, 576),
 ]
 MODES = [(False, False), (False, True), (True, True), (True, False)]
