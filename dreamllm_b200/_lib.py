@@ -98,6 +98,8 @@ SIGNATURES = {
     "dllm_copy_cols": (_i, [_vp, _vp, _l, _i, _i, _i, _vp]),
     "dllm_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dllm_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dllm_im2col_in": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dllm_nhwc_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),
     "dllm_timestep_embedding": (_i, [_vp, _vp, _vp, _i, _i, _vp]),
     "dllm_timestep_embedding_batch": (_i, [_vp, _vp, _i, _i, _vp]),
     "dllm_sampler_step": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _l, _vp]),

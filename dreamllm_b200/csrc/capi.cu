@@ -195,6 +195,14 @@ int dllm_conv_out(const void* x, const void* w, const void* bias, float* y, int 
   ensure_context(x);
   return conv_out_nhwc_to_nchw(x, w, bias, y, B, C, H, W, Cout, S(stream));
 }
+int dllm_im2col_in(const float* x, void* cols, int B, int Bsrc, int Cin, int H, int W, void* stream) {
+  ensure_context(cols);
+  return im2col_in(x, cols, B, Bsrc, Cin, H, W, S(stream));
+}
+int dllm_nhwc_to_nchw_f32(const void* y, float* out, int N, int HW, int Cp, int Cout, void* stream) {
+  ensure_context(y);
+  return nhwc_to_nchw_f32(y, out, N, HW, Cp, Cout, S(stream));
+}
 int dllm_timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, void* stream) {
   ensure_context(out);
   return timestep_embedding(timesteps, step, out, B, dim, S(stream));

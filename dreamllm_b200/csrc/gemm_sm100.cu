@@ -485,17 +485,18 @@ static int* tile_counter_slot(cudaStream_t stream) {
   return slot;
 }
 
-// N-tile width: 256 unless 128-wide tiles waste less padded MMA work (N = 128: 1x vs 2x; 320: 384 vs 512; 640: 640 vs 768).  The UNet's
-// 320 / 640-channel levels and the VAE's 128-channel level carry about half of their conv / GEMM FLOPs (tile quantisation).
+// N-tile width.  Measured on the UNet / VAE shapes (profiles/r02d_gemm_bn_{auto,256}.json): a 128-wide N tile reads the same A bytes
+// from shared memory for half the MMA work, and the 2-CTA kernel then runs at ~0.55-0.7x the MMA rate of the 256-wide one — which
+// more than cancels the padded-work saving at N = 320 / 640 / 960 (conv 320->320: 388 us at 128 vs 275 us at 256).  So 256 everywhere
+// except outputs that fit ONE 128-wide tile (VAE C = 128: 459 vs 476 us).  DLLM_GEMM_BN=128|256 forces a width for A/B runs.
 static inline int pick_bn(int N) {
-  static int forced = -1;                         // DLLM_GEMM_BN=128|256 forces one width (dev A/B runs); default: by padded work
+  static int forced = -1;
   if (forced < 0) {
     const char* e = getenv("DLLM_GEMM_BN");
     forced = e ? atoi(e) : 0;
   }
   if (forced == 128 || forced == 256) return forced;
-  const int c256 = (N + 255) / 256 * 256, c128 = (N + 127) / 128 * 128;
-  return c128 < c256 ? 128 : 256;
+  return N <= 128 ? 128 : 256;
 }
 
 template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEW = 4, int kBN = BN>

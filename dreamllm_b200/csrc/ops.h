@@ -45,6 +45,8 @@ int conv_in_nchw_to_nhwc(const float* x, const void* w, const void* bias, void* 
                          int Cout, cudaStream_t s);
 int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float* y, int B, int C, int H, int W, int Cout,
                           cudaStream_t s);
+int im2col_in(const float* x, void* cols, int B, int Bsrc, int Cin, int H, int W, cudaStream_t s);
+int nhwc_to_nchw_f32(const void* y, float* out, int N, int HW, int Cp, int Cout, cudaStream_t s);
 int timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, cudaStream_t s);
 int timestep_embedding_batch(const int* t, void* out, int B, int dim, cudaStream_t s);
 int sampler_step(const float* eps, float* latents, const float* noise, const float* coef, int* step, float guidance, int use_cfg,

@@ -535,6 +535,62 @@ int conv_out_nhwc_to_nchw(const void* x, const void* w, const void* bias, float*
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 
+// ---- conv_in / conv_out on the tensor cores (round 2).  The direct kernels above cost 1.36 ms (conv_in, 4 -> 320 @ 64x64 x 32) and
+// 0.68 ms (conv_out) of a 42 ms UNet step, and 0.95 ms per VAE conv_in at 512x512 (profiles/r02d_unet_launch_list_summary.md):
+//   conv_in  = im2col of the tiny-Cin fp32 NCHW input into bf16 rows [M, 64] (k = (c*3 + r)*3 + s, zero padded to one 64-wide K block)
+//              + the tcgen05 GEMM with the bias epilogue against the [Cout, 64] weight matrix          (dllm_im2col_in + dllm_gemm_bf16_ex)
+//   conv_out = the implicit-GEMM conv3x3 with Cout zero-padded to 8 + a channel-slicing NHWC bf16 -> NCHW fp32 pass
+//                                                                                                    (dllm_conv3x3_nhwc + dllm_nhwc_to_nchw_f32)
+__global__ void im2col_in_kernel(const float* __restrict__ x, bf16* __restrict__ cols, long total_vec, int Bsrc, int Cin, int H, int W) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total_vec) return;
+  const int v = static_cast<int>(gid & 7);
+  long p = gid >> 3;
+  const int wx = static_cast<int>(p % W); p /= W;
+  const int hy = static_cast<int>(p % H);
+  const int n = static_cast<int>(p / H) % Bsrc;        // CFG: image n reads latents[n % Bsrc]
+  const int K = Cin * 9;
+  float f[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = v * 8 + j;
+    float val = 0.f;
+    if (k < K) {
+      const int c = k / 9, rs = k - 9 * c, r = rs / 3, sx = rs - 3 * r;
+      const int h = hy + r - 1, ww = wx + sx - 1;
+      if (h >= 0 && h < H && ww >= 0 && ww < W) val = x[((static_cast<size_t>(n) * Cin + c) * H + h) * W + ww];
+    }
+    f[j] = val;
+  }
+  reinterpret_cast<V8*>(cols)[gid] = pk8(f);
+}
+int im2col_in(const float* x, void* cols, int B, int Bsrc, int Cin, int H, int W, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(cols);
+  if (B <= 0 || Bsrc <= 0 || Cin * 9 > 64) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(B) * H * W * 8;
+  im2col_in_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>(x, (bf16*)cols, total, Bsrc, Cin, H, W);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+// y [N*HW, Cp] bf16 (Cp = 8: one 16-byte vector per pixel) -> out fp32 NCHW [N, Cout, HW], Cout <= Cp
+__global__ void nhwc_to_nchw_f32_kernel(const bf16* __restrict__ y, float* __restrict__ out, long total, int HW, int Cout) {
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= total) return;
+  const long n = gid / HW;
+  const int p = static_cast<int>(gid - n * HW);
+  float f[8];
+  up8(reinterpret_cast<const V8*>(y)[gid], f);
+#pragma unroll
+  for (int o = 0; o < 8; ++o)
+    if (o < Cout) out[(static_cast<size_t>(n) * Cout + o) * HW + p] = f[o];
+}
+int nhwc_to_nchw_f32(const void* y, float* out, int N, int HW, int Cp, int Cout, cudaStream_t s) {
+  DLLM_REQUIRE_ALIGN16(y);
+  if (Cp != 8 || Cout > 8 || Cout <= 0 || N <= 0) return DLLM_ERR_SHAPE;
+  const long total = static_cast<long>(N) * HW;
+  nhwc_to_nchw_f32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, s>>>((const bf16*)y, out, total, HW, Cout);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
 // ------------------------------------------------------------------------------------------------ time embedding / sampler
 // Timesteps(320, flip_sin_to_cos=True, shift 0): emb[b] = [cos(t*f_i) | sin(t*f_i)], f_i = exp(-ln(10000) i / half).
 // t is read from the device-side schedule: timesteps[*step] (so one captured CUDA graph serves every step).

@@ -138,6 +138,12 @@ int dllm_copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int co
 int dllm_conv_in(const float* x_nchw, const void* w, const void* bias, void* y_nhwc, int B, int Bsrc, int Cin, int H, int W, int Cout,
                  void* stream);
 int dllm_conv_out(const void* x_nhwc, const void* w, const void* bias, float* y_nchw, int B, int C, int H, int W, int Cout, void* stream);
+/* tensor-core forms of the two tiny-channel convolutions (conv_in: Conv2d(4|3, C, 3, pad 1) of UNet2DConditionModel / AutoencoderKL;
+ * conv_out: Conv2d(C, 4|8|3, 3, pad 1)):
+ *   cols [B*H*W, 64] bf16 = im2col(x_nchw fp32), k = (c*3 + r)*3 + s zero-padded to 64  ->  dllm_gemm_bf16_ex(cols, Wk [Cout, 64], bias)
+ *   y8 [N*H*W, 8] bf16 = dllm_conv3x3_nhwc(x, W8 [8, 9*C])                                ->  out fp32 NCHW [N, Cout, H*W] (first Cout channels) */
+int dllm_im2col_in(const float* x_nchw, void* cols, int B, int Bsrc, int Cin, int H, int W, void* stream);
+int dllm_nhwc_to_nchw_f32(const void* y_nhwc8, float* out_nchw, int N, int HW, int Cp, int Cout, void* stream);
 /* timestep = timesteps[*step] (device-side schedule so one captured CUDA graph serves every step) */
 int dllm_timestep_embedding(const int* timesteps, const int* step, void* out, int B, int dim, void* stream);
 int dllm_timestep_embedding_batch(const int* t_per_sample, void* out, int B, int dim, void* stream);
