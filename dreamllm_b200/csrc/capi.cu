@@ -195,6 +195,11 @@ int dllm_conv_out(const void* x, const void* w, const void* bias, float* y, int 
   ensure_context(x);
   return conv_out_nhwc_to_nchw(x, w, bias, y, B, C, H, W, Cout, S(stream));
 }
+int dllm_gemm_bf16_geglu(const void* A, const void* Wp, const void* bias_p, void* out, int M, int N, int K, long lda, long ldb, long ldc,
+                         void* stream) {
+  ensure_context(A);
+  return gemm_bf16_geglu(A, Wp, bias_p, out, M, N, K, lda, ldb, ldc, S(stream));
+}
 int dllm_im2col_in(const float* x, void* cols, int B, int Bsrc, int Cin, int H, int W, void* stream) {
   ensure_context(cols);
   return im2col_in(x, cols, B, Bsrc, Cin, H, W, S(stream));

@@ -318,6 +318,69 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_wait(&tmem_full_bar[as], aphase, 4);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(wq * 32) << 16) + as * kBN;
+      if constexpr (kEpi == 3) {
+        // GEGLU epilogue (diffusers FeedForward: h, gate = proj(x).chunk(2); out = h * gelu(gate)).  The weight rows were permuted at
+        // load time so that every 128-column group of this GEMM's N space is [64 value columns | their 64 gate columns]; one warp turns
+        // such a pair of accumulator chunks into ONE 64-column chunk of the [M, N/2] output — the [M, N] projection is never written.
+        // Rounding points = the unfused sequence (Linear output to bf16, gelu(gate) to bf16, product to bf16): bit-identical results.
+        static_assert(kEpi != 3 || (!kOutF32 && (kChunks % (2 * kParts)) == 0), "GEGLU epilogue: bf16 out, whole chunk pairs per warp");
+        constexpr int kPairsPerWarp = kChunks / 2 / kParts;
+#pragma unroll 1
+        for (int pr = chalf * kPairsPerWarp; pr < (chalf + 1) * kPairsPerWarp; ++pr) {
+          uint32_t va[64], vg[64];
+          tmem_ld32(taddr0 + pr * 128, va);
+          tmem_ld32(taddr0 + pr * 128 + 32, va + 32);
+          tmem_ld32(taddr0 + pr * 128 + 64, vg);
+          tmem_ld32(taddr0 + pr * 128 + 96, vg + 32);
+          tmem_ld_wait();
+          const int gcol = col0 + pr * 128;   // column of the value chunk in the permuted N space (gate chunk at +64)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int cj = gcol + j * 8;
+            float bv[8], bg[8];
+            if (epi.bias != nullptr && cj + 128 <= N + 64) {
+              const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(epi.bias + cj));
+              const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(epi.bias + cj + 64));
+              const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&q0);
+              const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&q1);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f0 = __bfloat1622float2(h0[e]), f1 = __bfloat1622float2(h1[e]);
+                bv[2 * e] = f0.x; bv[2 * e + 1] = f0.y; bg[2 * e] = f1.x; bg[2 * e + 1] = f1.y;
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) bv[e] = bg[e] = 0.f;
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float a = __bfloat162float(__float2bfloat16_rn(__uint_as_float(va[j * 8 + e]) + bv[e]));
+              const float gte = __bfloat162float(__float2bfloat16_rn(__uint_as_float(vg[j * 8 + e]) + bg[e]));
+              const float gel = __bfloat162float(__float2bfloat16_rn(0.5f * gte * (1.f + erff(gte * 0.70710678118654752f))));
+              va[j * 8 + e] = __float_as_uint(a * gel);
+            }
+          }
+          if (lane == 0) tma_store_wait_read<Cfg::kEpiBufs - 1>();
+          __syncwarp();
+          uint8_t* dst = my_epi + buf * Cfg::kEpiBufBytes + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint4 q;
+            q.x = pack_bf16(__uint_as_float(va[8 * j + 0]), __uint_as_float(va[8 * j + 1]));
+            q.y = pack_bf16(__uint_as_float(va[8 * j + 2]), __uint_as_float(va[8 * j + 3]));
+            q.z = pack_bf16(__uint_as_float(va[8 * j + 4]), __uint_as_float(va[8 * j + 5]));
+            q.w = pack_bf16(__uint_as_float(va[8 * j + 6]), __uint_as_float(va[8 * j + 7]));
+            *reinterpret_cast<uint4*>(dst + ((j ^ (lane & 7)) << 4)) = q;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (row0 < M && gcol < N) tma_store_2d(&tma_c, my_epi + buf * Cfg::kEpiBufBytes, (col0 >> 1) + pr * 64, row0);
+            tma_store_commit();
+          }
+          buf = (buf + 1 == Cfg::kEpiBufs) ? 0 : buf + 1;
+        }
+      } else
 #pragma unroll 1
       for (int c = chalf * (kChunks / kParts); c < (chalf + 1) * (kChunks / kParts); ++c) {
         uint32_t v[kOutF32 ? 32 : 64];
@@ -600,6 +663,23 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
   DLLM_GEMM_CASE(2, true, false)
 #undef DLLM_GEMM_CASE
   return DLLM_ERR_SHAPE;
+}
+
+// out[M, N/2] = GEGLU(A @ Wp^T + bias_p): Wp / bias_p are the FeedForward's `proj` weight / bias with rows permuted so that every
+// 128-row group is [64 value rows | the 64 matching gate rows] (dreamllm_b200/unet.py builds them once per frozen UNet).
+int gemm_bf16_geglu(const void* A, const void* Wp, const void* bias_p, void* out, int M, int N, int K, long lda, long ldb, long ldc,
+                    cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0 || (N % 128)) return DLLM_ERR_SHAPE;
+  if (bias_p && (reinterpret_cast<uintptr_t>(bias_p) & 15)) return DLLM_ERR_ALIGN;
+  GemmEpi epi{static_cast<const bf16*>(bias_p), nullptr, 0, 2, nullptr, 1};
+  const int kcta = (M > BM) ? 2 : 1;
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, A, 2, M, K, lda, BM, BK))) return rc;
+  if ((rc = make_tmap_2d(&tb, Wp, 2, N, K, ldb, BN / kcta, BK))) return rc;
+  if ((rc = make_tmap_2d(&tc, out, 2, M, N / 2, ldc, 32, 64))) return rc;
+  if (kcta == 2) return launch_gemm_bn<2, false, false, bf16, false, 3, 8, 256>(ta, tb, tc, M, N, K, epi, stream);
+  return launch_gemm_bn<1, false, false, bf16, false, 3, 8, 256>(ta, tb, tc, M, N, K, epi, stream);
 }
 
 // 4-D NHWC activation map: dims {C, W, H, N}, box {64, Wb, Hb, Nb}, 128B swizzle.

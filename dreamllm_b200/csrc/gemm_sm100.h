@@ -29,6 +29,10 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
                  int b_mn, int out_fp32, int cta_pair, const void* bias, const void* residual, long ldr, int act,
                  cudaStream_t stream);
 
+// FeedForward-in projection with the GEGLU fused into the epilogue (weight rows pre-permuted: [64 value | 64 gate] per 128-row group)
+int gemm_bf16_geglu(const void* A, const void* Wp, const void* bias_p, void* out, int M, int N, int K, long lda, long ldb, long ldc,
+                    cudaStream_t stream);
+
 // implicit-GEMM 3x3 stride-1 pad-1 convolution, NHWC bf16 (see gemm_sm100.cu)
 int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, const void* bias,
                  const void* rowbias, const void* residual, cudaStream_t stream);

@@ -120,6 +120,38 @@ def linear(x2d: torch.Tensor, weight: torch.Tensor, out=None, out_dtype=BF16, bi
     return gemm(x2d, weight, out=out, out_dtype=out_dtype, bias=bias, residual=residual, act=act)
 
 
+def geglu_permute(weight: torch.Tensor, bias: torch.Tensor | None):
+    """`GEGLU.proj` weight [2I, K] / bias [2I] -> row order [64 value rows | their 64 gate rows] per 128-row group (what `linear_geglu`
+    expects).  I % 64 == 0."""
+    I2, K = weight.shape
+    inner = I2 // 2
+    assert inner % 64 == 0
+    wp = torch.stack([weight[:inner].view(inner // 64, 64, K), weight[inner:].view(inner // 64, 64, K)], dim=1).reshape(I2, K).contiguous()
+    bp = None
+    if bias is not None:
+        bp = torch.stack([bias[:inner].view(inner // 64, 64), bias[inner:].view(inner // 64, 64)], dim=1).reshape(I2).contiguous()
+    return wp, bp
+
+
+def linear_geglu(x2d: torch.Tensor, w_perm: torch.Tensor, b_perm: torch.Tensor | None) -> torch.Tensor:
+    """out[M, I] = h * gelu(gate), [h | gate] = x @ W^T + b, fused into the GEMM epilogue (weights from `geglu_permute`)."""
+    _chk_cuda(x2d, w_perm, b_perm)
+    M, K = x2d.shape
+    N = w_perm.shape[0]
+    assert x2d.dtype == BF16 and w_perm.dtype == BF16 and x2d.stride(1) == 1 and w_perm.is_contiguous() and w_perm.shape[1] == K
+    out = torch.empty((M, N // 2), device=x2d.device, dtype=BF16)
+    if PROFILE.enabled:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+    check(lib().dllm_gemm_bf16_geglu(_p(x2d), _p(w_perm), _p(b_perm), _p(out), M, N, K, x2d.stride(0), w_perm.stride(0), out.stride(0),
+                                     _stream()), "dllm_gemm_bf16_geglu")
+    if PROFILE.enabled:
+        e1.record()
+        PROFILE.records.append((e0, e1, 2.0 * M * N * K))
+    LAUNCHES.add(1)
+    return out
+
+
 def linear_dgrad(dy2d: torch.Tensor, weight: torch.Tensor, out=None) -> torch.Tensor:
     """dx = dy @ W."""
     return gemm(dy2d, weight, b_mn=True, out=out)

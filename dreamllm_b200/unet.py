@@ -212,10 +212,20 @@ class UNet2DConditionModel(nn.Module):
         h = ops.linear(ao.view(T, C), blk.attn2.to_out[0].weight, bias=blk.attn2.to_out[0].bias, residual=h)
         # GEGLU feed-forward
         y = ops.layernorm_fwd(h, blk.norm3.weight, blk.norm3.bias, blk.norm3.eps)
-        f = ops.linear(y, blk.ff.net[0].proj.weight, bias=blk.ff.net[0].proj.bias)
-        g = ops.geglu(f)
+        g = ops.linear_geglu(y, *self._geglu_w(blk.ff.net[0].proj))       # FF-in GEMM with h * gelu(gate) in its epilogue
         h = ops.linear(g, blk.ff.net[2].weight, bias=blk.ff.net[2].bias, residual=h)
         return ops.linear(h, t.proj_out.weight, bias=t.proj_out.bias, residual=x2).view(N, H, W, C)
+
+    def _geglu_w(self, proj: nn.Linear):
+        """Row-permuted copy of `GEGLU.proj` ([64 value | 64 gate] per 128 rows) for the fused epilogue; the parameter itself keeps the
+        diffusers layout (state-dict compatible).  Frozen tower: built once."""
+        key = ("geglu", id(proj))
+        w = proj.weight
+        ent = self._wcache.get(key)
+        if ent is None or ent[0] != (w.data_ptr(), w._version):
+            ent = ((w.data_ptr(), w._version), ops.geglu_permute(w.detach(), proj.bias.detach()))
+            self._wcache[key] = ent
+        return ent[1]
 
     @torch.no_grad()
     def precompute_cross_kv(self, encoder_hidden_states):

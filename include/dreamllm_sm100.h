@@ -138,6 +138,11 @@ int dllm_copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int co
 int dllm_conv_in(const float* x_nchw, const void* w, const void* bias, void* y_nhwc, int B, int Bsrc, int Cin, int H, int W, int Cout,
                  void* stream);
 int dllm_conv_out(const void* x_nhwc, const void* w, const void* bias, float* y_nchw, int B, int C, int H, int W, int Cout, void* stream);
+/* UNet FeedForward-in projection with GEGLU in the GEMM epilogue (diffusers `GEGLU.forward`: h, gate = proj(x).chunk(2); h * gelu(gate)):
+ * out[M, N/2] = h * gelu(gate) where [h | gate] = A @ W^T + b and Wp / bias_p hold W / b with rows permuted to [64 h rows | 64 gate rows]
+ * per 128-row group; the [M, N] projection is never written.  N % 128 == 0. */
+int dllm_gemm_bf16_geglu(const void* A, const void* Wp, const void* bias_p, void* out, int M, int N, int K, long lda, long ldb, long ldc,
+                         void* stream);
 /* tensor-core forms of the two tiny-channel convolutions (conv_in: Conv2d(4|3, C, 3, pad 1) of UNet2DConditionModel / AutoencoderKL;
  * conv_out: Conv2d(C, 4|8|3, 3, pad 1)):
  *   cols [B*H*W, 64] bf16 = im2col(x_nchw fp32), k = (c*3 + r)*3 + s zero-padded to 64  ->  dllm_gemm_bf16_ex(cols, Wk [Cout, 64], bias)

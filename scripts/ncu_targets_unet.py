@@ -25,5 +25,13 @@ for _ in range(2):
     qkv = r(N, H * W, 3, 5, 64)
     ops.attn_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False)
     ops.linear(t2, r(2560, C) * 0.02, bias=r(2560))
+    wp, bp = ops.geglu_permute(r(2560, C) * 0.02, r(2560))
+    ops.linear_geglu(t2, wp, bp)                                                # FF-in GEMM with the GEGLU epilogue
+    # fused CFG + DDIM update (sampler_step + step counter) on the 16 x 4 x 64 x 64 latents
+    eps = torch.randn(32, 4, 64, 64, device="cuda", generator=g)
+    lat = torch.randn(16, 4, 64, 64, device="cuda", generator=g)
+    coef = torch.rand(50, 5, device="cuda", generator=g) + 0.1
+    step = torch.zeros(1, device="cuda", dtype=torch.int32)
+    ops.sampler_step_(eps, lat, coef, step, 7.5, True, 0)
 torch.cuda.synchronize()
 print("done")

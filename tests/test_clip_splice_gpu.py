@@ -50,8 +50,10 @@ def test_clip_tower_vs_transformers(cfg_kw, n_img):
     # select_layer semantics: hidden_states[0] is the post-pre_layrnorm embedding
     with torch.no_grad():
         ref0 = hf(img, output_hidden_states=True).hidden_states[0]
+        ref0b = hfb(img.to(BF), output_hidden_states=True).hidden_states[0].float()
     got0 = ours.hidden_state(img.cuda().to(BF), 0).cpu().float()
-    torch.testing.assert_close(got0, ref0, rtol=3e-2, atol=3e-2)
+    e0_o, e0_r = float((got0 - ref0).abs().mean()), float((ref0b - ref0).abs().mean())
+    assert e0_o <= 1.3 * e0_r + 1e-3 * float(ref0.abs().mean()), (e0_o, e0_r)          # like-for-like, as for the selected layer
 
 
 @pytest.mark.parametrize("kind,depth,bias", [("linear", 1, True), ("linear", 1, False), ("mlp", 2, True)])

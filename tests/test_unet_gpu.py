@@ -160,3 +160,23 @@ def test_unet_train_path_cond_gradient_vs_oracle_autograd(B, HW, Q):
     t1 = torch.full((B,), int(t[0]), dtype=torch.int32, device="cuda")
     eps1, _ = ours.forward_train(noisy_c, t1, cond.cuda().to(BF))
     assert torch.equal(eps1, ours(noisy_c, int(t[0]), cond.cuda().to(BF)))
+
+
+@pytest.mark.parametrize("M,C", [(300, 64), (4096, 320), (1000, 640)])
+def test_geglu_fused_epilogue_is_bit_identical_to_the_unfused_sequence(M, C):
+    """FeedForward-in projection with GEGLU in the GEMM epilogue (row-permuted weights) == Linear -> geglu kernel, bit for bit: same
+    rounding points (Linear output, gelu(gate), product all rounded to bf16), so the inference path may use it without changing parity."""
+    from dreamllm_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + C)
+    x = (torch.randn(M, C, device="cuda", generator=g)).to(BF)
+    w = (torch.randn(8 * C, C, device="cuda", generator=g) * 0.05).to(BF)
+    b = (torch.randn(8 * C, device="cuda", generator=g) * 0.1).to(BF)
+    want = ops.geglu(ops.linear(x, w, bias=b))
+    wp, bp = ops.geglu_permute(w, b)
+    got = ops.linear_geglu(x, wp, bp)
+    assert got.shape == want.shape == (M, 4 * C)
+    assert torch.equal(got, want)
+    # and against the fp32 formula (diffusers GEGLU: h * gelu(gate), exact erf gelu)
+    f = x.float() @ w.float().t() + b.float()
+    ref = f[:, :4 * C] * torch.nn.functional.gelu(f[:, 4 * C:])
+    assert float((got.float() - ref).abs().mean()) <= 2e-2 * float(ref.abs().mean())
