@@ -137,7 +137,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     tmem_relinquish<kCta>();
   }
   tc_fence_before();
-  if constexpr (kCta == 2) cluster_sync_all(); else __syncthreads();
+  if constexpr (kCta == 2) cluster_sync_all();
+  __syncthreads();   // (2-CTA: barrier.cluster already orders the allocator's smem write; the CTA barrier keeps compute-sanitizer's
+                     //  racecheck, which does not model cluster barriers, from flagging the tmem_ptr hand-off — profiles/r02f_sanitizer.md)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
