@@ -98,6 +98,10 @@ SIGNATURES = {
     "dllm_copy_cols": (_i, [_vp, _vp, _l, _i, _i, _i, _vp]),
     "dllm_conv_in": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "dllm_conv_out": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dllm_gemm_splitk_workspace_bytes": (_sz, [_i, _i, _i]),
+    "dllm_gemm_bf16_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _i, _vp, _vp, _l, _i, _vp, _sz, _vp]),
+    "dllm_conv3x3_splitk_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "dllm_conv3x3_nhwc_ws": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dllm_gemm_bf16_geglu": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _l, _l, _l, _vp]),
     "dllm_im2col_in": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dllm_nhwc_to_nchw_f32": (_i, [_vp, _vp, _i, _i, _i, _i, _vp]),

@@ -195,6 +195,18 @@ int dllm_conv_out(const void* x, const void* w, const void* bias, float* y, int 
   ensure_context(x);
   return conv_out_nhwc_to_nchw(x, w, bias, y, B, C, H, W, Cout, S(stream));
 }
+size_t dllm_gemm_splitk_workspace_bytes(int M, int N, int K) { return gemm_splitk_workspace(M, N, K); }
+int dllm_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int b_mn, const void* bias,
+                      const void* residual, long ldr, int act, void* ws, size_t ws_bytes, void* stream) {
+  ensure_context(A);
+  return gemm_bf16_ws(A, B, C, M, N, K, lda, ldb, ldc, b_mn, bias, residual, ldr, act, ws, ws_bytes, S(stream));
+}
+size_t dllm_conv3x3_splitk_workspace_bytes(int N, int H, int W, int Cin, int Cout) { return conv3x3_splitk_workspace(N, H, W, Cin, Cout); }
+int dllm_conv3x3_nhwc_ws(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, const void* bias,
+                         const void* rowbias, const void* residual, void* ws, size_t ws_bytes, void* stream) {
+  ensure_context(x);
+  return conv3x3_nhwc_ws(x, w, y, N, H, W, Cin, Cout, bias, rowbias, residual, ws, ws_bytes, S(stream));
+}
 int dllm_gemm_bf16_geglu(const void* A, const void* Wp, const void* bias_p, void* out, int M, int N, int K, long lda, long ldb, long ldc,
                          void* stream) {
   ensure_context(A);

@@ -84,7 +84,10 @@ template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int
 __global__ void __launch_bounds__(gemm_threads(kEpiWarps), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_c, int M, int N, int K, int group_m, GemmEpi epi, ConvGeom cg,
-            int* __restrict__ tile_counter) {
+            int* __restrict__ tile_counter, int ksplit) {
+  // ksplit > 1 (split-K, small-M shapes that would leave most SMs idle): a work unit is (output tile, K slice); unit u covers K blocks
+  // [ks * kb_per, min(num_kb, (ks + 1) * kb_per)) of tile u / ksplit and stores its fp32 partial at rows ks * Mp + ... of the workspace the
+  // C tensor map describes (Mp = M rounded up to whole tiles); splitk_reduce_kernel sums the slices and applies the epilogue.
   using Cfg = GemmCfg<kCta, kEpiWarps, kBN>;
   constexpr int kStages = Cfg::kStages;
   constexpr bool kOutF32 = sizeof(OutT) == 4;
@@ -147,8 +150,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int tile_m = BM * kCta;
   const int num_m_tiles = (M + tile_m - 1) / tile_m;
   const int num_n_tiles = (N + kBN - 1) / kBN;
-  const int num_tiles = num_m_tiles * num_n_tiles;
+  const int num_tiles = num_m_tiles * num_n_tiles * ksplit;       // work units
   const int num_kb = (K + BK - 1) / BK;
+  const int kb_per = (num_kb + ksplit - 1) / ksplit;
+  const int split_rows = num_m_tiles * tile_m;                      // Mp: row pitch between K slices in the partial workspace
   const int tiles_per_group = group_m * num_n_tiles;
   const uint32_t ring_empty0_leader = (kCta == 2) ? mapa_shared(smem_u32(&ring_empty[0]), 0) : 0u;
 
@@ -196,10 +201,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       if (tile >= num_tiles) break;
       int m_blk, n_blk;
-      tile_coords(tile, m_blk, n_blk);
+      tile_coords(tile / ksplit, m_blk, n_blk);
+      const int ks = tile % ksplit;
       const int m0 = m_blk * tile_m + static_cast<int>(cta_rank) * BM;
       const int n0 = n_blk * kBN + static_cast<int>(cta_rank) * Cfg::kBRows;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = ks * kb_per; kb < min(num_kb, (ks + 1) * kb_per); ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1, 1);
         uint8_t* a_s = smem + stage * Cfg::kStageBytes;
         uint8_t* b_s = a_s + Cfg::kABytes;
@@ -275,7 +281,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       mbar_wait(&tmem_empty_bar[as], aphase ^ 1, 2);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + as * kBN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int kb0 = (tile % ksplit) * kb_per, kb1 = min(num_kb, kb0 + kb_per);
+      for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
         const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -284,7 +291,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         for (int k = 0; k < BK / UMMA_K; ++k) {
           const uint64_t adesc = make_smem_desc(a_base + k * a_adv, a_lbo, 1024);
           const uint64_t bdesc = make_smem_desc(b_base + k * b_adv, b_lbo, 1024);
-          umma_ss<kCta>(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          umma_ss<kCta>(tmem_d, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
         }
         if constexpr (kCta == 1) umma_commit(&empty_bar[stage]); else umma_commit_2cta(&empty_bar[stage], 0b11);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -312,10 +319,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       }
       if (tile >= num_tiles) break;
       int m_blk, n_blk;
-      tile_coords(tile, m_blk, n_blk);
+      tile_coords(tile / ksplit, m_blk, n_blk);
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int row0 = m_blk * tile_m + static_cast<int>(cta_rank) * BM + wq * 32;
+      const int row0 = (tile % ksplit) * (ksplit > 1 ? split_rows : 0) + m_blk * tile_m + static_cast<int>(cta_rank) * BM + wq * 32;
       const int col0 = n_blk * kBN;
       mbar_wait(&tmem_full_bar[as], aphase, 4);
       tc_fence_after();
@@ -459,7 +466,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
-          if (row0 < M && col0 + c * CH < N)
+          if ((ksplit > 1 || row0 < M) && col0 + c * CH < N)
             tma_store_2d(&tma_c, my_epi + buf * Cfg::kEpiBufBytes, col0 + c * CH, row0);
           tma_store_commit();
         }
@@ -528,7 +535,10 @@ int num_sms() {
   if (!n) {
     int dev = 0;
     cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return 148;   // no device visible (build host): plan for a B200 so the workspace queries stay meaningful
+    }
   }
   return n;
 }
@@ -566,7 +576,7 @@ static inline int pick_bn(int N) {
 
 template <int kCta, bool kAMN, bool kBMN, typename OutT, bool kConv = false, int kEpi = 0, int kEW = 4, int kBN = BN>
 static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, int M, int N, int K,
-                          const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}) {
+                          const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}, int ksplit = 1) {
   using Cfg = GemmCfg<kCta, kEW, kBN>;
   auto kern = gemm_kernel<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW, kBN>;
   static bool attr_set = false;
@@ -576,7 +586,7 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CU
     attr_set = true;
   }
   const int tile_m = BM * kCta;
-  const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + kBN - 1) / kBN);
+  const int num_tiles = ((M + tile_m - 1) / tile_m) * ((N + kBN - 1) / kBN) * ksplit;
   int avail = num_sms() - g_reserved_sms;
   if (avail < 2) avail = 2;
   const int max_clusters = avail / kCta;
@@ -596,7 +606,7 @@ static int launch_gemm_bn(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   cfg.numAttrs = 1;
   int* counter = tile_counter_slot(stream);
   if (!counter) return DLLM_ERR_LAUNCH;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi, cg, counter);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, M, N, K, group_m, epi, cg, counter, ksplit);
   return e == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
 // `bn` must be the value the B tensor map's box was built for (pick_bn(N))
@@ -605,6 +615,119 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
                        const GemmEpi& epi, cudaStream_t stream, ConvGeom cg = ConvGeom{1, 1, 1, 1}, int bn = BN) {
   if (bn == 128) return launch_gemm_bn<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW, 128>(ta, tb, tc, M, N, K, epi, stream, cg);
   return launch_gemm_bn<kCta, kAMN, kBMN, OutT, kConv, kEpi, kEW, 256>(ta, tb, tc, M, N, K, epi, stream, cg);
+}
+
+// ------------------------------------------------------------------------------------------------ split-K (small-M shapes)
+// A [256 x 1280] output over K = 11520 (UNet conv 1280 -> 1280 on the 8x8 plane of 4 samples) is 5 tiles: 5 of 74 CTA pairs busy for
+// 180 K blocks each.  The stage-1 step (C5) spends 12.8 of its 29.6 ms of GEMM / conv time in launches that fill <= 80 of 148 SMs
+// (profiles/r02f_stage1_launch_list_summary.md).  Split-K hands every (tile, K slice) to its own CTA pair, writes fp32 partials to a
+// caller-provided workspace and lets one small kernel sum them and apply the epilogue with the usual rounding points.
+struct SplitPlan {
+  int kcta, bn, ksplit, mp;   // mp = M rounded up to whole tiles
+  size_t ws_bytes;
+};
+static SplitPlan plan_split(int M, int N, int K, int kcta_hint) {
+  SplitPlan p;
+  p.kcta = kcta_hint;
+  p.bn = pick_bn(N);
+  const int tile_m = BM * p.kcta;
+  const int mt = (M + tile_m - 1) / tile_m, nt = (N + p.bn - 1) / p.bn;
+  const int tiles = mt * nt, num_kb = (K + BK - 1) / BK;
+  int slots = (num_sms() - g_reserved_sms) / p.kcta;
+  if (slots < 1) slots = 1;
+  int ks = 1;
+  static int disabled = -1;
+  if (disabled < 0) { const char* e = getenv("DLLM_GEMM_NO_SPLITK"); disabled = (e && e[0] == '1') ? 1 : 0; }
+  if (!disabled && tiles * 2 <= slots && num_kb >= 8) {
+    ks = slots / tiles;
+    if (ks > num_kb / 4) ks = num_kb / 4;    // at least 4 K blocks per slice
+    if (ks > 16) ks = 16;
+    if (ks < 2) ks = 1;
+  }
+  p.ksplit = ks;
+  p.mp = mt * tile_m;
+  p.ws_bytes = ks > 1 ? static_cast<size_t>(ks) * p.mp * N * sizeof(float) : 0;
+  return p;
+}
+size_t gemm_splitk_workspace(int M, int N, int K) { return plan_split(M, N, K, M > BM ? 2 : 1).ws_bytes; }
+
+// out[m, n] = epilogue( sum_ks ws[ks * mp + m, n] ): bias / row-group bias added in fp32, rounded to bf16, optional activation (rounded),
+// optional residual add (rounded) — the rounding points of gemm_kernel's fused epilogues.  One thread = 8 columns.
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, bf16* __restrict__ out, long ldc, int M, int N, int mp, int ksplit,
+                                     GemmEpi epi) {
+  const int nvec = N >> 3;
+  const long gid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (gid >= static_cast<long>(M) * nvec) return;
+  const int v = static_cast<int>(gid % nvec);
+  const int m = static_cast<int>(gid / nvec);
+  float x[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) x[e] = 0.f;
+  for (int ks = 0; ks < ksplit; ++ks) {
+    const float4* p = reinterpret_cast<const float4*>(ws + (static_cast<size_t>(ks) * mp + m) * N + v * 8);
+    const float4 a = p[0], b = p[1];
+    x[0] += a.x; x[1] += a.y; x[2] += a.z; x[3] += a.w; x[4] += b.x; x[5] += b.y; x[6] += b.z; x[7] += b.w;
+  }
+  auto add8 = [&](const bf16* src) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(src));
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h2[e]); x[2 * e] += f.x; x[2 * e + 1] += f.y; }
+  };
+  if (epi.bias) add8(epi.bias + v * 8);
+  if (epi.rowbias) add8(epi.rowbias + static_cast<size_t>(m / epi.rows_per_group) * N + v * 8);
+  if (epi.act) {
+#pragma unroll
+    for (int e = 0; e < 8; ++e) x[e] = epi_act(__bfloat162float(__float2bfloat16_rn(x[e])), epi.act);
+  }
+  if (epi.residual) {
+    const uint4 q = *reinterpret_cast<const uint4*>(epi.residual + static_cast<size_t>(m) * epi.ldr + v * 8);
+    const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&q);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h2[e]);
+      x[2 * e] = __bfloat162float(__float2bfloat16_rn(x[2 * e])) + f.x;
+      x[2 * e + 1] = __bfloat162float(__float2bfloat16_rn(x[2 * e + 1])) + f.y;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(x[0], x[1]); o.y = pack_bf16(x[2], x[3]); o.z = pack_bf16(x[4], x[5]); o.w = pack_bf16(x[6], x[7]);
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(m) * ldc + v * 8) = o;
+}
+static int launch_splitk_reduce(const void* ws, void* out, long ldc, int M, int N, const SplitPlan& p, const GemmEpi& epi, cudaStream_t st) {
+  const long total = static_cast<long>(M) * (N / 8);
+  splitk_reduce_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>((const float*)ws, (bf16*)out, ldc, M, N, p.mp, p.ksplit, epi);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+
+// bf16-output GEMM (fwd NT or dgrad NN) with the fused-epilogue operands, run as split-K when the shape calls for it and a workspace of
+// gemm_splitk_workspace(M, N, K) bytes is given; otherwise identical to gemm_bf16_ex.
+int gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int b_mn, const void* bias,
+                 const void* residual, long ldr, int act, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  const SplitPlan p = plan_split(M, N, K, M > BM ? 2 : 1);
+  if (p.ksplit <= 1 || !ws || ws_bytes < p.ws_bytes || (N % 8) || (reinterpret_cast<uintptr_t>(ws) & 15) || (ldc % 8))
+    return gemm_bf16_ex(A, B, C, M, N, K, lda, ldb, ldc, 0, b_mn, 0, -1, bias, residual, ldr, act, stream);
+  if (residual && ((reinterpret_cast<uintptr_t>(residual) & 15) || ((ldr * 2) & 15))) return DLLM_ERR_ALIGN;
+  if (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) return DLLM_ERR_ALIGN;
+  CUtensorMap ta, tb, tc;
+  int rc;
+  if ((rc = make_tmap_2d(&ta, A, 2, M, K, lda, BM, BK))) return rc;
+  if (!b_mn) rc = make_tmap_2d(&tb, B, 2, N, K, ldb, p.bn / p.kcta, BK);
+  else rc = make_tmap_2d(&tb, B, 2, K, N, ldb, BK, 64);
+  if (rc) return rc;
+  if ((rc = make_tmap_2d(&tc, ws, 4, static_cast<uint64_t>(p.ksplit) * p.mp, N, N, 32, 32))) return rc;
+  GemmEpi none{nullptr, nullptr, 0, 0, nullptr, 1};
+  const ConvGeom nocg{1, 1, 1, 1};
+#define DLLM_SPLIT_CASE(CTA, BMN_, BNW)                                                                                      \
+  if (p.kcta == CTA && (b_mn != 0) == BMN_ && p.bn == BNW)                                                                   \
+    rc = launch_gemm_bn<CTA, false, BMN_, float, false, 0, 4, BNW>(ta, tb, tc, M, N, K, none, stream, nocg, p.ksplit);
+  rc = DLLM_ERR_SHAPE;
+  DLLM_SPLIT_CASE(1, false, 256) DLLM_SPLIT_CASE(1, true, 256) DLLM_SPLIT_CASE(2, false, 256) DLLM_SPLIT_CASE(2, true, 256)
+  DLLM_SPLIT_CASE(1, false, 128) DLLM_SPLIT_CASE(1, true, 128) DLLM_SPLIT_CASE(2, false, 128) DLLM_SPLIT_CASE(2, true, 128)
+#undef DLLM_SPLIT_CASE
+  if (rc) return rc;
+  GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), ldr, act, nullptr, 1};
+  return launch_splitk_reduce(ws, C, ldc, M, N, p, epi, stream);
 }
 
 int gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int a_mn,
@@ -700,9 +823,18 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* ptr, int Nimg, int H, in
   return r == CUDA_SUCCESS ? 0 : DLLM_ERR_TMAP;
 }
 
-// y[n,h,w,:] = conv3x3(x, w) + bias + rowbias[n] (+ residual);  x NHWC [Nimg,H,W,Cin], w [Cout, 3,3,Cin] (K-major), y NHWC
+size_t conv3x3_splitk_workspace(int Nimg, int H, int W, int Cin, int Cout) {
+  const int M = Nimg * H * W;
+  return plan_split(M, Cout, 9 * Cin, M > BM ? 2 : 1).ws_bytes;
+}
 int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, const void* bias,
                  const void* rowbias, const void* residual, cudaStream_t stream) {
+  return conv3x3_nhwc_ws(x, w, y, Nimg, H, W, Cin, Cout, bias, rowbias, residual, nullptr, 0, stream);
+}
+// y[n,h,w,:] = conv3x3(x, w) + bias + rowbias[n] (+ residual);  x NHWC [Nimg,H,W,Cin], w [Cout, 3,3,Cin] (K-major), y NHWC.
+// With a workspace of conv3x3_splitk_workspace() bytes small planes run split-K (see plan_split).
+int conv3x3_nhwc_ws(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, const void* bias,
+                    const void* rowbias, const void* residual, void* ws, size_t ws_bytes, cudaStream_t stream) {
   if (Nimg <= 0 || Cin % 64 || Cout % 8) return DLLM_ERR_SHAPE;
   if (W > 128 ? (W % 128) : (128 % W)) return DLLM_ERR_SHAPE;
   const int HW = H * W;
@@ -721,9 +853,20 @@ int conv3x3_nhwc(const void* x, const void* w, void* y, int Nimg, int H, int W, 
   int rc;
   if ((rc = make_tmap_nhwc(&ta, x, Nimg, H, W, Cin, Wb, Hb, Nb))) return rc;
   if ((rc = make_tmap_2d(&tb, w, 2, Cout, K, K, bn / kcta, BK))) return rc;
-  if ((rc = make_tmap_2d(&tc, y, 2, M, Cout, Cout, 32, 64))) return rc;
   GemmEpi epi{static_cast<const bf16*>(bias), static_cast<const bf16*>(residual), Cout, 0, static_cast<const bf16*>(rowbias), HW};
   ConvGeom cg{Cin / 64, W, H, HW};
+  const SplitPlan sp = plan_split(M, Cout, K, kcta);
+  if (sp.ksplit > 1 && ws && ws_bytes >= sp.ws_bytes && !(reinterpret_cast<uintptr_t>(ws) & 15)) {
+    if ((rc = make_tmap_2d(&tc, ws, 4, static_cast<uint64_t>(sp.ksplit) * sp.mp, Cout, Cout, 32, 32))) return rc;
+    GemmEpi none{nullptr, nullptr, 0, 0, nullptr, 1};
+    if (kcta == 2) rc = (bn == 128) ? launch_gemm_bn<2, false, false, float, true, 0, 4, 128>(ta, tb, tc, M, Cout, K, none, stream, cg, sp.ksplit)
+                                    : launch_gemm_bn<2, false, false, float, true, 0, 4, 256>(ta, tb, tc, M, Cout, K, none, stream, cg, sp.ksplit);
+    else rc = (bn == 128) ? launch_gemm_bn<1, false, false, float, true, 0, 4, 128>(ta, tb, tc, M, Cout, K, none, stream, cg, sp.ksplit)
+                          : launch_gemm_bn<1, false, false, float, true, 0, 4, 256>(ta, tb, tc, M, Cout, K, none, stream, cg, sp.ksplit);
+    if (rc) return rc;
+    return launch_splitk_reduce(ws, y, Cout, M, Cout, sp, epi, stream);
+  }
+  if ((rc = make_tmap_2d(&tc, y, 2, M, Cout, Cout, 32, 64))) return rc;
   const bool any_epi = bias || rowbias || residual;
   if (kcta == 2) return any_epi ? launch_gemm<2, false, false, bf16, true, 1, 8>(ta, tb, tc, M, Cout, K, epi, stream, cg, bn)
                                 : launch_gemm<2, false, false, bf16, true, 0, 4>(ta, tb, tc, M, Cout, K, epi, stream, cg, bn);

@@ -29,6 +29,14 @@ int gemm_bf16_ex(const void* A, const void* B, void* C, int M, int N, int K, lon
                  int b_mn, int out_fp32, int cta_pair, const void* bias, const void* residual, long ldr, int act,
                  cudaStream_t stream);
 
+// split-K variants for small-M shapes (workspace sized by the *_workspace query; 0 = the shape is not split)
+size_t gemm_splitk_workspace(int M, int N, int K);
+int gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int b_mn, const void* bias,
+                 const void* residual, long ldr, int act, void* ws, size_t ws_bytes, cudaStream_t stream);
+size_t conv3x3_splitk_workspace(int Nimg, int H, int W, int Cin, int Cout);
+int conv3x3_nhwc_ws(const void* x, const void* w, void* y, int Nimg, int H, int W, int Cin, int Cout, const void* bias,
+                    const void* rowbias, const void* residual, void* ws, size_t ws_bytes, cudaStream_t stream);
+
 // FeedForward-in projection with the GEGLU fused into the epilogue (weight rows pre-permuted: [64 value | 64 gate] per 128-row group)
 int gemm_bf16_geglu(const void* A, const void* Wp, const void* bias_p, void* out, int M, int N, int K, long lda, long ldb, long ldc,
                     cudaStream_t stream);

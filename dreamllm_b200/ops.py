@@ -93,7 +93,22 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     if PROFILE.enabled:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-    if bias is None and residual is None and act == 0:
+    wsb = 0
+    if not a_mn and out.dtype == BF16 and cta_pair < 0 and M <= 4096:          # small-M shapes: split-K when the library says it pays
+        wsb = lib().dllm_gemm_splitk_workspace_bytes(M, N, K)
+    if wsb:
+        _chk_cuda(bias, residual)
+        ldr = 0
+        if bias is not None:
+            assert bias.dtype == BF16 and bias.is_contiguous() and bias.numel() == N
+        if residual is not None:
+            assert residual.dtype == BF16 and residual.shape == (M, N) and residual.stride(1) == 1
+            ldr = residual.stride(0)
+        ws = torch.empty(wsb, device=a.device, dtype=torch.uint8)
+        rc = lib().dllm_gemm_bf16_ws(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(b_mn), _p(bias),
+                                     _p(residual), ldr, int(act), _p(ws), wsb, _stream())
+        LAUNCHES.add(1)
+    elif bias is None and residual is None and act == 0:
         rc = lib().dllm_gemm_bf16(_p(a), _p(b), _p(out), M, N, K, a.stride(0), b.stride(0), out.stride(0), int(a_mn),
                                   int(b_mn), int(out.dtype == torch.float32), cta_pair, _stream())
     else:
@@ -399,6 +414,13 @@ def conv3x3(x_nhwc, w_k, bias=None, rowbias=None, residual=None):
         assert residual.is_contiguous() and residual.numel() == y.numel()
     if rowbias is not None:
         assert rowbias.is_contiguous() and rowbias.shape == (N, Cout)
+    wsb = lib().dllm_conv3x3_splitk_workspace_bytes(N, H, W, Cin, Cout) if N * H * W <= 4096 else 0
+    if wsb:                                                    # small planes (8x8 / 16x16 of a few samples): split-K + reduce
+        ws = torch.empty(wsb, device=x_nhwc.device, dtype=torch.uint8)
+        check(lib().dllm_conv3x3_nhwc_ws(_p(x_nhwc), _p(w_k), _p(y), N, H, W, Cin, Cout, _p(bias), _p(rowbias), _p(residual), _p(ws), wsb,
+                                         _stream()), "dllm_conv3x3_nhwc_ws")
+        LAUNCHES.add(2)
+        return y
     check(lib().dllm_conv3x3_nhwc(_p(x_nhwc), _p(w_k), _p(y), N, H, W, Cin, Cout, _p(bias), _p(rowbias), _p(residual), _stream()),
           "dllm_conv3x3_nhwc")
     LAUNCHES.add(1)

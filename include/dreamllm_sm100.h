@@ -138,6 +138,16 @@ int dllm_copy_cols(const void* src, void* dst, long rows, int Cs, int Cd, int co
 int dllm_conv_in(const float* x_nchw, const void* w, const void* bias, void* y_nhwc, int B, int Bsrc, int Cin, int H, int W, int Cout,
                  void* stream);
 int dllm_conv_out(const void* x_nhwc, const void* w, const void* bias, float* y_nchw, int B, int C, int H, int W, int Cout, void* stream);
+/* Split-K forms for small-M shapes (stage-1 steps run the UNet on 4 samples: an 8x8 plane is 256 GEMM rows and would occupy 5 of 74 CTA
+ * pairs).  `*_workspace_bytes` returns 0 when the shape is not worth splitting; otherwise pass that many bytes of 16-byte aligned scratch:
+ * the GEMM writes fp32 K-slice partials there and a reduce kernel applies bias / row-group bias / activation / residual with the fused
+ * epilogue's rounding points.  C = act(bf16(A B^T + bias)) (+ residual) for b_mn = 0 (nn.Linear forward), C = A B for b_mn = 1 (dgrad). */
+size_t dllm_gemm_splitk_workspace_bytes(int M, int N, int K);
+int dllm_gemm_bf16_ws(const void* A, const void* B, void* C, int M, int N, int K, long lda, long ldb, long ldc, int b_mn, const void* bias,
+                      const void* residual, long ldr, int act, void* ws, size_t ws_bytes, void* stream);
+size_t dllm_conv3x3_splitk_workspace_bytes(int N, int H, int W, int Cin, int Cout);
+int dllm_conv3x3_nhwc_ws(const void* x, const void* w, void* y, int N, int H, int W, int Cin, int Cout, const void* bias,
+                         const void* rowbias, const void* residual, void* ws, size_t ws_bytes, void* stream);
 /* UNet FeedForward-in projection with GEGLU in the GEMM epilogue (diffusers `GEGLU.forward`: h, gate = proj(x).chunk(2); h * gelu(gate)):
  * out[M, N/2] = h * gelu(gate) where [h | gate] = A @ W^T + b and Wp / bias_p hold W / b with rows permuted to [64 h rows | 64 gate rows]
  * per 128-row group; the [M, N] projection is never written.  N % 128 == 0. */

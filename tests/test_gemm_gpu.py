@@ -73,3 +73,48 @@ def test_gemm_linearity_full_size():
     torch.testing.assert_close(y2, 2 * y, rtol=0, atol=0)
     rows = torch.randint(0, T, (64,), device="cuda")
     torch.testing.assert_close(y[rows], x[rows].float() @ w.float().t(), rtol=1e-3, atol=2e-3)
+
+
+@pytest.mark.parametrize("M,N,K,b_mn", [(256, 1280, 11520, False), (400, 4096, 4096, False), (400, 4096, 12288, True), (64, 320, 1280, False),
+                                         (130, 264, 2048, True)])
+def test_split_k_small_m_gemm(M, N, K, b_mn):
+    """Small-M shapes run split-K (K slices on separate CTA pairs, fp32 partials in a workspace, epilogue in the reduce kernel): same
+    result as the fp32 reference, and the fused-epilogue rounding points (bias in fp32, round, activation, round, residual, round)."""
+    from dreamllm_b200 import ops
+    from dreamllm_b200._lib import lib
+
+    assert lib().dllm_gemm_splitk_workspace_bytes(M, N, K) > 0, "shape was expected to be split"
+    g = torch.Generator(device="cuda").manual_seed(M + N)
+    a = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    b = (torch.randn((K, N) if b_mn else (N, K), device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    ref = a.float() @ (b.float() if b_mn else b.float().t())
+    c = ops.gemm(a, b, b_mn=b_mn)
+    torch.testing.assert_close(c.float(), ref, rtol=1.6e-2, atol=1e-2 * (K ** 0.5) * 0.05)
+    if not b_mn:
+        bias = (torch.randn(N, device="cuda", generator=g)).to(torch.bfloat16)
+        res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+        got = ops.linear(a, b, bias=bias, residual=res, act=ops.ACT_SILU)
+        y = (ref + bias.float()).to(torch.bfloat16).float()
+        y = torch.nn.functional.silu(y).to(torch.bfloat16).float()        # kernel rounds the activation output when a residual follows
+        want = (y + res.float())
+        torch.testing.assert_close(got.float(), want, rtol=2e-2, atol=3e-2)
+
+
+def test_split_k_conv_small_plane_matches_unsplit(monkeypatch=None):
+    """Implicit-GEMM conv on a small plane: split-K result == the unsplit kernel's up to fp32 summation order."""
+    from dreamllm_b200 import ops
+    from dreamllm_b200._lib import lib
+    N, H, W, Ci, Co = 4, 8, 8, 640, 320
+    assert lib().dllm_conv3x3_splitk_workspace_bytes(N, H, W, Ci, Co) > 0
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.randn(N, H, W, Ci, device="cuda", generator=g).to(torch.bfloat16)
+    w = (torch.randn(Co, 9 * Ci, device="cuda", generator=g) * 0.02).to(torch.bfloat16)
+    bias = torch.randn(Co, device="cuda", generator=g).to(torch.bfloat16)
+    rowb = torch.randn(N, Co, device="cuda", generator=g).to(torch.bfloat16)
+    res = torch.randn(N, H, W, Co, device="cuda", generator=g).to(torch.bfloat16)
+    got = ops.conv3x3(x, w, bias=bias, rowbias=rowb, residual=res)
+    # reference: torch conv2d in fp32 on the same bf16 values
+    w4 = w.float().view(Co, 3, 3, Ci).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w4, padding=1).permute(0, 2, 3, 1)
+    ref = (ref + bias.float() + rowb.float()[:, None, None, :]).to(torch.bfloat16).float() + res.float()
+    torch.testing.assert_close(got.float(), ref, rtol=2e-2, atol=3e-2)
