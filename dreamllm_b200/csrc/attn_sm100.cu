@@ -96,6 +96,15 @@ __device__ __forceinline__ void store_acc_tile(uint32_t tmem_acc, uint8_t* stage
   }
 }
 
+// DLLM_ATTN_TRACE (dev builds only, scripts/attn_trace.py): clock64 timestamps of one CTA's softmax warp 0 / MMA thread / TMA thread per KV
+// tile, to see which hand-off the iteration time is made of.  Slot layout: [tile j][16].
+#ifdef DLLM_ATTN_TRACE
+__device__ long long g_attn_trace[64 * 16 + 16];
+#define ATTN_TRACE(j, k) do { if (trace_on && (j) < 64) g_attn_trace[(j) * 16 + (k)] = clock64(); } while (0)
+#else
+#define ATTN_TRACE(j, k) do { } while (0)
+#endif
+
 // ================================================================================================ forward
 // kPT = true (default): P never touches shared memory.  The softmax warps write bf16 P back into the TMEM columns S occupied
 // (tcgen05.st) and the PV tile-GEMM reads its A operand from tensor memory (tcgen05.mma with [a_tmem]).  Because S is double-buffered, so
@@ -142,11 +151,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(pv_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  // causal: q tile i has i + 1 KV tiles of work; launch the heaviest first so the grid's tail is made of short CTAs (LPT order)
+  const int q0 = (kCausal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x) * 128, h = blockIdx.y, b = blockIdx.z;
   const int kv_len = seqlens ? min(seqlens[b], Skv) : Skv;   // Skv != S only for cross-attention (non-causal)
   const int q_len = seqlens ? kv_len : S;                    // right-padded self-attention: rows >= len are padding
   const int kv_end = kCausal ? min(kv_len, q0 + 128 + coff) : kv_len;
   const int n_kv = (kv_end + 63) / 64;
+#ifdef DLLM_ATTN_TRACE
+  const bool trace_on = (q0 == (gridDim.x - 1) * 128 && blockIdx.y == 1 && blockIdx.z == 0 && lane == 0);
+  if (trace_on && warp == 0) g_attn_trace[64 * 16] = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_fwd: smem misaligned\n"); __trap(); }
@@ -186,7 +200,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       const uint32_t ph = (j >> 1) & 1;
       while (jk < n_kv && jk < j + KS - 1) load_k(jk++);     // K(j) .. K(j + KS - 2) need no stage that V(j)'s consumer frees
       if (jk <= j) load_k(jk++);
+      ATTN_TRACE(j, 8);
       mbar_wait(&v_empty[st], ph ^ 1, 11);
+      ATTN_TRACE(j, 9);
       mbar_arrive_expect_tx(&v_full[st], 64 * D * 2);
       for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &v_full[st], h * D + c * 64, j * 64, b);
     }
@@ -200,6 +216,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     auto issue_qk = [&](int j) {
       const int ks = j % KS;
       mbar_wait(&k_full[ks], (j / KS) & 1, 12);
+      ATTN_TRACE(j, 5);
       tc_fence_after();
       mma_tile(tmem_S + (j & 1) * 64, sQ, false, 16384, sK + ks * L::kKV, false, 8192, D / 16, idesc_qk, false);
       umma_commit(&k_empty[ks]);
@@ -211,8 +228,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       if (j + 1 < n_kv) issue_qk(j + 1);
       const int st = j & 1;
       mbar_wait(&v_full[st], (j >> 1) & 1, 14);
+      ATTN_TRACE(j, 6);
       if constexpr (kPT) {
         mbar_wait(&p_full[j & 1], (j >> 1) & 1, 15);
+        ATTN_TRACE(j, 7);
         tc_fence_after();
         // O += P V_j with P read from TMEM: [128 lanes x 64 kv] bf16 = 32 columns at the base of S buffer j & 1, 8 columns per UMMA_K
 #pragma unroll
@@ -233,12 +252,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < n_kv; ++j) {
+      ATTN_TRACE(j, 10);
       mbar_wait(&s_full[j & 1], (j >> 1) & 1, 16);
+      if (warp == 0) ATTN_TRACE(j, 0);
       tc_fence_after();
       uint32_t sv[64];
       tmem_ld32(tmem_S + lane_off + (j & 1) * 64, sv);
       tmem_ld32(tmem_S + lane_off + (j & 1) * 64 + 32, sv + 32);
       tmem_ld_wait();
+      if (warp == 0) ATTN_TRACE(j, 1);
       const int kv0 = j * 64;
       const bool need_mask = (kCausal && kv0 + 63 > q0 + warp * 32 + coff) || (kv0 + 64 > kv_len) || (kv_mask != nullptr);
       float mx = -INFINITY;
@@ -278,6 +300,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       // lazy rescale: only move the reference max when it grew by more than 2^8 (keeps P <= 256, exact after 1/l)
       const bool need = (m_new - m_run) > 8.0f;
       const bool any = __any_sync(0xffffffffu, need);
+      if (warp == 0) ATTN_TRACE(j, 2);
       if constexpr (!kPT) {
         if (j > 0) mbar_wait(&pv_done[0], (j - 1) & 1, 17);  // P buffer free, O quiescent
       } else {
@@ -316,12 +339,14 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
           ls1 += p1;
           pw[c] = pack_bf16(p0, p1);          // K elements 2c, 2c+1 of this row share one 32-bit TMEM column
         }
+        if (warp == 0) ATTN_TRACE(j, 3);
         tmem_st32(tmem_S + lane_off + (j & 1) * 64, pw);
         tmem_st_wait();
         l_run += ls0 + ls1;
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[j & 1]);
+        if (warp == 0) ATTN_TRACE(j, 4);
       } else {
 #pragma unroll
         for (int jj = 0; jj < 8; ++jj) {
@@ -344,6 +369,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       else mbar_wait(&pv_done[0], (n_kv - 1) & 1, 18);
       tc_fence_after();
     }
+#ifdef DLLM_ATTN_TRACE
+    if (trace_on && warp == 0) g_attn_trace[64 * 16 + 1] = clock64();
+#endif
     const bool valid_row = (q_row < q_len) && n_kv > 0 && l_run > 0.f;
     const float inv = valid_row ? 1.f / l_run : 0.f;
     if (n_kv > 0) {
@@ -366,6 +394,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
     if (q_row < S)
       lse[(static_cast<size_t>(b) * nh + h) * S + q_row] = valid_row ? (m_run + log2f(l_run)) * kLn2 : INFINITY;
   }
+#ifdef DLLM_ATTN_TRACE
+  if (trace_on && warp == 0) g_attn_trace[64 * 16 + 2] = clock64();
+#endif
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<1>(tmem_base, 256);
@@ -651,7 +682,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  // causal: q tile i has i + 1 KV tiles of work; launch the heaviest first so the grid's tail is made of short CTAs (LPT order)
+  const int q0 = (kCausal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x) * 128, h = blockIdx.y, b = blockIdx.z;
   const int len = seqlens ? min(seqlens[b], S) : S;
   const int len_kv = seqlens ? len : Skv;
   const int kv_end = kCausal ? min(len_kv, q0 + 128) : len_kv;
@@ -1046,7 +1078,8 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_done + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
+  // causal: q tile i has i + 1 KV tiles of work; launch the heaviest first so the grid's tail is made of short CTAs (LPT order)
+  const int q0 = (kCausal ? (gridDim.x - 1 - blockIdx.x) : blockIdx.x) * 128, h = blockIdx.y, b = blockIdx.z;
   const int len = seqlens ? min(seqlens[b], S) : S;
   const int len_kv = seqlens ? len : Skv;
   const int kv_end = kCausal ? min(len_kv, q0 + 128) : len_kv;
@@ -1340,3 +1373,9 @@ int attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, c
 }
 
 }  // namespace dllm
+
+#ifdef DLLM_ATTN_TRACE
+extern "C" int dllm_attn_trace_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, dllm::g_attn_trace, sizeof(long long) * n);
+}
+#endif

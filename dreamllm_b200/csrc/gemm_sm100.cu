@@ -638,11 +638,16 @@ static SplitPlan plan_split(int M, int N, int K, int kcta_hint) {
   int ks = 1;
   static int disabled = -1;
   if (disabled < 0) { const char* e = getenv("DLLM_GEMM_NO_SPLITK"); disabled = (e && e[0] == '1') ? 1 : 0; }
-  if (!disabled && tiles * 2 <= slots && num_kb >= 8) {
+  static int min_ks = -1;   // DLLM_GEMM_SPLITK_MIN: smallest slice count worth the fp32 round trip + reduce launch (default 2)
+  if (min_ks < 0) { const char* e = getenv("DLLM_GEMM_SPLITK_MIN"); min_ks = (e && atoi(e) >= 2) ? atoi(e) : 2; }
+  if (!disabled && tiles * min_ks <= slots && num_kb >= 8) {
     ks = slots / tiles;
     if (ks > num_kb / 4) ks = num_kb / 4;    // at least 4 K blocks per slice
     if (ks > 16) ks = 16;
-    if (ks < 2) ks = 1;
+    if (ks < min_ks) ks = 1;
+    // no empty slice: the kernel gives every slice ceil(num_kb / ks) K blocks, so the last of e.g. 16 slices of 90 blocks would start
+    // past the end and store an accumulator no MMA ever initialised
+    if (ks > 1) { const int per = (num_kb + ks - 1) / ks; ks = (num_kb + per - 1) / per; }
   }
   p.ksplit = ks;
   p.mp = mt * tile_m;
