@@ -47,12 +47,34 @@ static int make_tmap_bsc(CUtensorMap* map, const void* ptr, int B, int S, int co
   return r == CUDA_SUCCESS ? 0 : DLLM_ERR_TMAP;
 }
 
-// one full MMA tile: D[tmem] (+)= A * B over `ksteps` UMMA_K steps
+// Descriptor of UMMA_K step `ks` of the tile whose step-0 descriptor is d0.  The start-address field counts 16-byte units and no tile
+// crosses the 256 KB its 14 bits span, so a plain add is exact; with the loops below fully unrolled every step's descriptor is the
+// tile's plus a compile-time constant.
+__device__ __forceinline__ uint64_t desc_step(uint64_t d0, bool mn, uint32_t chunk_stride, int ks) {
+  return d0 + ((mn ? ks * 2048u : (ks >> 2) * chunk_stride + (ks & 3) * 32u) >> 4);
+}
+// one full MMA tile: D[tmem] (+)= A * B over kSteps UMMA_K steps.
+// Issue cost matters here: the S / dP tile-GEMMs are N = 64 instructions (32-48 clk of tensor pipe each), and the r01 / early-r02 issue
+// loop — descriptor rebuilt per step, and ptxas wrapping each UTCHMMA in a per-active-thread ELECT/BRA loop because `lane == 0` does not
+// tell it the region is single-threaded — spent 13 dependent scalar instructions (~100 clk) per MMA: the issuing thread, not the tensor
+// pipe or the softmax warps, set the iteration time (profiles/r02j_attn_fwd_timeline.md).  The issuer is now chosen with elect.sync and
+// the descriptors are hoisted, which lets ptxas emit the kSteps UTCHMMAs back to back.
+template <int kSteps>
 __device__ __forceinline__ void mma_tile(uint32_t tmem_d, uint32_t a_base, bool a_mn, uint32_t a_cs, uint32_t b_base,
-                                         bool b_mn, uint32_t b_cs, int ksteps, uint32_t idesc, bool accumulate) {
-  for (int ks = 0; ks < ksteps; ++ks)
-    umma_ss<1>(tmem_d, op_desc(a_base, a_mn, a_cs, ks), op_desc(b_base, b_mn, b_cs, ks), idesc,
-               (accumulate || ks > 0) ? 1u : 0u);
+                                         bool b_mn, uint32_t b_cs, uint32_t idesc, bool accumulate) {
+  const uint64_t a0 = op_desc(a_base, a_mn, a_cs, 0), b0 = op_desc(b_base, b_mn, b_cs, 0);
+#pragma unroll
+  for (int ks = 0; ks < kSteps; ++ks)
+    umma_ss<1>(tmem_d, desc_step(a0, a_mn, a_cs, ks), desc_step(b0, b_mn, b_cs, ks), idesc, (accumulate || ks > 0) ? 1u : 0u);
+}
+// same with the A operand in tensor memory: step ks reads the 32-bit columns starting at tmem_a + ks * a_col_stride
+template <int kSteps>
+__device__ __forceinline__ void mma_tile_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t a_col_stride, uint32_t b_base, bool b_mn,
+                                            uint32_t b_cs, uint32_t idesc, bool accumulate) {
+  const uint64_t b0 = op_desc(b_base, b_mn, b_cs, 0);
+#pragma unroll
+  for (int ks = 0; ks < kSteps; ++ks)
+    umma_ts(tmem_d, tmem_a + ks * a_col_stride, desc_step(b0, b_mn, b_cs, ks), idesc, (accumulate || ks > 0) ? 1u : 0u);
 }
 
 // write 64 bf16 (one 128-byte swizzled line) for tile row `row`; vals come 8 at a time
@@ -182,7 +204,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   const uint32_t tmem_S = tmem_base;        // 2 x 64 columns
   const uint32_t tmem_O = tmem_base + 128;  // D columns
 
-  if (warp == 4 && lane == 0 && n_kv > 0) {
+  // producer / issuer: one lane picked with elect.sync — unlike `lane == 0` it lets ptxas treat the region as single-threaded, so the
+  // TMA / tcgen05.mma instructions are not wrapped in a per-active-thread loop
+  if (warp == 4) { if (elect_one_sync() && n_kv > 0) {
     // ---------------- TMA producer ----------------
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
     mbar_arrive_expect_tx(q_full, 128 * D * 2);
@@ -206,7 +230,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       mbar_arrive_expect_tx(&v_full[st], 64 * D * 2);
       for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &v_full[st], h * D + c * 64, j * 64, b);
     }
-  } else if (warp == 5 && lane == 0 && n_kv > 0) {
+  } } else if (warp == 5) { if (elect_one_sync() && n_kv > 0) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);
@@ -218,7 +242,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
       mbar_wait(&k_full[ks], (j / KS) & 1, 12);
       ATTN_TRACE(j, 5);
       tc_fence_after();
-      mma_tile(tmem_S + (j & 1) * 64, sQ, false, 16384, sK + ks * L::kKV, false, 8192, D / 16, idesc_qk, false);
+      mma_tile<D / 16>(tmem_S + (j & 1) * 64, sQ, false, 16384, sK + ks * L::kKV, false, 8192, idesc_qk, false);
       umma_commit(&k_empty[ks]);
       umma_commit(&s_full[j & 1]);
     };
@@ -234,18 +258,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
         ATTN_TRACE(j, 7);
         tc_fence_after();
         // O += P V_j with P read from TMEM: [128 lanes x 64 kv] bf16 = 32 columns at the base of S buffer j & 1, 8 columns per UMMA_K
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks)
-          umma_ts(tmem_O, tmem_S + (j & 1) * 64 + ks * 8, op_desc(sV + st * L::kKV, true, 8192, ks), idesc_pv, (j > 0 || ks > 0) ? 1u : 0u);
+        mma_tile_ts<4>(tmem_O, tmem_S + (j & 1) * 64, 8, sV + st * L::kKV, true, 8192, idesc_pv, j > 0);
       } else {
         mbar_wait(&p_full[0], j & 1, 15);
         tc_fence_after();
-        mma_tile(tmem_O, sP, false, 0, sV + st * L::kKV, true, 8192, 4, idesc_pv, j > 0);
+        mma_tile<4>(tmem_O, sP, false, 0, sV + st * L::kKV, true, 8192, idesc_pv, j > 0);
       }
       umma_commit(&v_empty[st]);
       umma_commit(&pv_done[kPT ? (j & 1) : 0]);
     }
-  } else if (warp < 4) {
+  } } else if (warp < 4) {
     // ---------------- softmax rows ----------------
     const int row = warp * 32 + lane;
     const int q_row = q0 + row;
@@ -513,7 +535,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
   const uint32_t tmem_dV = tmem_base + 256;   // D
   const uint32_t tmem_dK = tmem_base + 256 + D;
 
-  if (warp == 8 && lane == 0 && n_it > 0) {
+  // producer / issuer: one lane picked with elect.sync — unlike `lane == 0` it lets ptxas treat the region as single-threaded, so the
+  // TMA / tcgen05.mma instructions are not wrapped in a per-active-thread loop
+  if (warp == 8) { if (elect_one_sync() && n_it > 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
     mbar_arrive_expect_tx(kv_full, 2 * 128 * D * 2);
     for (int c = 0; c < NCH; ++c) {
@@ -530,7 +554,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
         tma_load_3d(smem + L::oDO + st * L::kQ + c * 8192, &tdo, &qdo_full[st], h * D + c * 64, qr0, b);
       }
     }
-  } else if (warp == 9 && lane == 0 && n_it > 0) {
+  } } else if (warp == 9) { if (elect_one_sync() && n_it > 0) {
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
     const uint32_t sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV), sQ = smem_u32(smem + L::oQ),
@@ -539,8 +563,8 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
       const int st = it & 1;
       mbar_wait(&qdo_full[st], (it >> 1) & 1, 21);
       tc_fence_after();
-      mma_tile(tmem_St + st * 64, sK, false, 16384, sQ + st * L::kQ, false, 8192, D / 16, idesc_s, false);
-      mma_tile(tmem_dPt + st * 64, sV, false, 16384, sDO + st * L::kQ, false, 8192, D / 16, idesc_s, false);
+      mma_tile<D / 16>(tmem_St + st * 64, sK, false, 16384, sQ + st * L::kQ, false, 8192, idesc_s, false);
+      mma_tile<D / 16>(tmem_dPt + st * 64, sV, false, 16384, sDO + st * L::kQ, false, 8192, idesc_s, false);
       umma_commit(&sdp_full[st]);
     };
     mbar_wait(kv_full, 0, 22);
@@ -550,12 +574,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tq, const __grid_consta
       const int st = it & 1;
       mbar_wait(&pds_full[st], (it >> 1) & 1, 23);
       tc_fence_after();
-      mma_tile(tmem_dV, sP + st * 16384, false, 0, sDO + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
-      mma_tile(tmem_dK, sDS + st * 16384, false, 0, sQ + st * L::kQ, true, 8192, 4, idesc_acc, it > 0);
+      mma_tile<4>(tmem_dV, sP + st * 16384, false, 0, sDO + st * L::kQ, true, 8192, idesc_acc, it > 0);
+      mma_tile<4>(tmem_dK, sDS + st * 16384, false, 0, sQ + st * L::kQ, true, 8192, idesc_acc, it > 0);
       umma_commit(&qdo_empty[st]);
       umma_commit(&acc_done[st]);
     }
-  } else if (warp < 8) {
+  } } else if (warp < 8) {
     const int wq = warp & 3, half = warp >> 2;
     const int row = wq * 32 + lane;  // kv row within tile
     const int kv_row = kv0 + row;
@@ -705,7 +729,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
 
-  if (warp == 8 && lane == 0 && n_kv > 0) {
+  // producer / issuer: one lane picked with elect.sync — unlike `lane == 0` it lets ptxas treat the region as single-threaded, so the
+  // TMA / tcgen05.mma instructions are not wrapped in a per-active-thread loop
+  if (warp == 8) { if (elect_one_sync() && n_kv > 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
     mbar_arrive_expect_tx(q_full, 2 * 128 * D * 2);
     for (int c = 0; c < NCH; ++c) {
@@ -721,7 +747,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
         tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &kv_full[st], h * D + c * 64, j * 64, b);
       }
     }
-  } else if (warp == 9 && lane == 0 && n_kv > 0) {
+  } } else if (warp == 9) { if (elect_one_sync() && n_kv > 0) {
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
     const uint32_t sQ = smem_u32(smem + L::oQ), sDO = smem_u32(smem + L::oDO), sK = smem_u32(smem + L::oK),
@@ -730,8 +756,8 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const int st = j & 1;
       mbar_wait(&kv_full[st], (j >> 1) & 1, 31);
       tc_fence_after();
-      mma_tile(tmem_S + st * 64, sQ, false, 16384, sK + st * L::kKV, false, 8192, D / 16, idesc_s, false);
-      mma_tile(tmem_dP + st * 64, sDO, false, 16384, sV + st * L::kKV, false, 8192, D / 16, idesc_s, false);
+      mma_tile<D / 16>(tmem_S + st * 64, sQ, false, 16384, sK + st * L::kKV, false, 8192, idesc_s, false);
+      mma_tile<D / 16>(tmem_dP + st * 64, sDO, false, 16384, sV + st * L::kKV, false, 8192, idesc_s, false);
       umma_commit(&sdp_full[st]);
     };
     mbar_wait(q_full, 0, 32);
@@ -741,11 +767,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant
       const int st = j & 1;
       mbar_wait(&ds_full[st], (j >> 1) & 1, 33);
       tc_fence_after();
-      mma_tile(tmem_dQ, sDS + st * 16384, false, 0, sK + st * L::kKV, true, 8192, 4, idesc_acc, j > 0);
+      mma_tile<4>(tmem_dQ, sDS + st * 16384, false, 0, sK + st * L::kKV, true, 8192, idesc_acc, j > 0);
       umma_commit(&kv_empty[st]);
       umma_commit(&acc_done[st]);
     }
-  } else if (warp < 8) {
+  } } else if (warp < 8) {
     const int wq = warp & 3, half = warp >> 2;
     const int row = wq * 32 + lane;
     const int q_row = q0 + row;
@@ -907,7 +933,9 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
   const uint32_t tmem_dV = tmem_base + 256;   // D
   const uint32_t tmem_dK = tmem_base + 256 + D;
 
-  if (warp == kBwdRowWarps && lane == 0 && n_it > 0) {
+  // producer / issuer: one lane picked with elect.sync — unlike `lane == 0` it lets ptxas treat the region as single-threaded, so the
+  // TMA / tcgen05.mma instructions are not wrapped in a per-active-thread loop
+  if (warp == kBwdRowWarps) { if (elect_one_sync() && n_it > 0) {
     // ---------------- TMA producer ----------------
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
     mbar_arrive_expect_tx(kv_full, 2 * 128 * D * 2);
@@ -929,7 +957,7 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
       bulk_load_1d(smem + L::oStat + rs * 512, lse_bh + qr0, 256, &qdo_full[rs]);          // S_pad is a multiple of 64: always in range
       bulk_load_1d(smem + L::oStat + rs * 512 + 256, del_bh + qr0, 256, &qdo_full[rs]);
     }
-  } else if (warp == kBwdRowWarps + 1 && lane == 0 && n_it > 0) {
+  } } else if (warp == kBwdRowWarps + 1) { if (elect_one_sync() && n_it > 0) {
     // ---------------- MMA issuer ----------------
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
@@ -939,8 +967,8 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
       const int st = it & 1, rs = it % kBwdRing;
       mbar_wait(&qdo_full[rs], (it / kBwdRing) & 1, 41);
       tc_fence_after();
-      mma_tile(tmem_St + st * 64, sK, false, 16384, sQ + rs * L::kQ, false, 8192, D / 16, idesc_s, false);
-      mma_tile(tmem_dPt + st * 64, sV, false, 16384, sDO + rs * L::kQ, false, 8192, D / 16, idesc_s, false);
+      mma_tile<D / 16>(tmem_St + st * 64, sK, false, 16384, sQ + rs * L::kQ, false, 8192, idesc_s, false);
+      mma_tile<D / 16>(tmem_dPt + st * 64, sV, false, 16384, sDO + rs * L::kQ, false, 8192, idesc_s, false);
       umma_commit(&sdp_full[st]);
     };
     mbar_wait(kv_full, 0, 42);
@@ -950,16 +978,13 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
       const int st = it & 1, rs = it % kBwdRing;
       mbar_wait(&pds_full[st], (it >> 1) & 1, 43);
       tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)   // dV += P^T dO_i : A = P^T from TMEM (k-step ks = q columns [16 ks, 16 ks + 16) at column 16 ks)
-        umma_ts(tmem_dV, tmem_St + st * 64 + 16 * ks, op_desc(sDO + rs * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)   // dK += dS^T Q_i
-        umma_ts(tmem_dK, tmem_dPt + st * 64 + 16 * ks, op_desc(sQ + rs * L::kQ, true, 8192, ks), idesc_acc, (it > 0 || ks > 0) ? 1u : 0u);
+      // dV += P^T dO_i : A = P^T from TMEM (k-step ks = q columns [16 ks, 16 ks + 16) at column 16 ks);  dK += dS^T Q_i
+      mma_tile_ts<4>(tmem_dV, tmem_St + st * 64, 16, sDO + rs * L::kQ, true, 8192, idesc_acc, it > 0);
+      mma_tile_ts<4>(tmem_dK, tmem_dPt + st * 64, 16, sQ + rs * L::kQ, true, 8192, idesc_acc, it > 0);
       umma_commit(&qdo_empty[rs]);
       umma_commit(&acc_done[st]);
     }
-  } else if (warp < kBwdRowWarps) {
+  } } else if (warp < kBwdRowWarps) {
     // ---------------- row warps ----------------
     const int wq = warp & 3, part = warp >> 2;
     const int row = wq * 32 + lane;  // kv row within tile
@@ -1102,7 +1127,9 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
 
-  if (warp == kBwdRowWarps && lane == 0 && n_kv > 0) {
+  // producer / issuer: one lane picked with elect.sync — unlike `lane == 0` it lets ptxas treat the region as single-threaded, so the
+  // TMA / tcgen05.mma instructions are not wrapped in a per-active-thread loop
+  if (warp == kBwdRowWarps) { if (elect_one_sync() && n_kv > 0) {
     tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
     mbar_arrive_expect_tx(q_full, 2 * 128 * D * 2);
     for (int c = 0; c < NCH; ++c) {
@@ -1118,7 +1145,7 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
         tma_load_3d(smem + L::oV + rs * L::kKV + c * 8192, &tv, &kv_full[rs], h * D + c * 64, j * 64, b);
       }
     }
-  } else if (warp == kBwdRowWarps + 1 && lane == 0 && n_kv > 0) {
+  } } else if (warp == kBwdRowWarps + 1) { if (elect_one_sync() && n_kv > 0) {
     constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
     const uint32_t sQ = smem_u32(smem + L::oQ), sDO = smem_u32(smem + L::oDO), sK = smem_u32(smem + L::oK),
@@ -1127,8 +1154,8 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       const int st = j & 1, rs = j % kBwdRing;
       mbar_wait(&kv_full[rs], (j / kBwdRing) & 1, 51);
       tc_fence_after();
-      mma_tile(tmem_S + st * 64, sQ, false, 16384, sK + rs * L::kKV, false, 8192, D / 16, idesc_s, false);
-      mma_tile(tmem_dP + st * 64, sDO, false, 16384, sV + rs * L::kKV, false, 8192, D / 16, idesc_s, false);
+      mma_tile<D / 16>(tmem_S + st * 64, sQ, false, 16384, sK + rs * L::kKV, false, 8192, idesc_s, false);
+      mma_tile<D / 16>(tmem_dP + st * 64, sDO, false, 16384, sV + rs * L::kKV, false, 8192, idesc_s, false);
       umma_commit(&sdp_full[st]);
     };
     mbar_wait(q_full, 0, 52);
@@ -1138,13 +1165,11 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
       const int st = j & 1, rs = j % kBwdRing;
       mbar_wait(&ds_full[st], (j >> 1) & 1, 53);
       tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)   // dQ += dS K_j : A = dS from TMEM
-        umma_ts(tmem_dQ, tmem_dP + st * 64 + 16 * ks, op_desc(sK + rs * L::kKV, true, 8192, ks), idesc_acc, (j > 0 || ks > 0) ? 1u : 0u);
+      mma_tile_ts<4>(tmem_dQ, tmem_dP + st * 64, 16, sK + rs * L::kKV, true, 8192, idesc_acc, j > 0);   // dQ += dS K_j : A = dS from TMEM
       umma_commit(&kv_empty[rs]);
       umma_commit(&acc_done[st]);
     }
-  } else if (warp < kBwdRowWarps) {
+  } } else if (warp < kBwdRowWarps) {
     const int wq = warp & 3, part = warp >> 2;
     const int row = wq * 32 + lane;
     const int q_row = q0 + row;

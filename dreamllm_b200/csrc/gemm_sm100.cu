@@ -177,7 +177,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     n_blk = r / gsize;
   };
 
-  if (warp_idx == 0 && lane == 0) {
+  // producer / issuer: one lane picked with elect.sync.  Unlike `lane == 0` it tells ptxas the region is single-threaded, so the TMA and
+  // tcgen05.mma instructions are emitted back to back instead of each inside a per-active-thread ELECT/BRA loop (21 scalar instructions
+  // between two UTCHMMAs before: at 64-128 clk of tensor pipe per instruction the issuing thread was the limit for BN = 128 tiles)
+  if (warp_idx == 0) { if (elect_one_sync()) {
     // ======================= TMA producer =======================
     int stage = 0;
     uint32_t phase = 0;
@@ -261,13 +264,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp_idx == 1 && lane == 0 && cta_rank == 0) {
+  } } else if (warp_idx == 1) { if (elect_one_sync() && cta_rank == 0) {
     // ======================= MMA issuer (leader CTA only) =======================
     constexpr uint32_t idesc = make_idesc_bf16(BM * kCta, kBN, kAMN, kBMN);
     constexpr uint32_t a_adv = kAMN ? 2048u : 32u;  // bytes per UMMA_K step
     constexpr uint32_t b_adv = kBMN ? 2048u : 32u;
     constexpr uint32_t a_lbo = kAMN ? 8192u : 16u;
     constexpr uint32_t b_lbo = kBMN ? 8192u : 16u;
+    const uint64_t adesc0 = make_smem_desc(smem_u32(smem), a_lbo, 1024);
+    const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + Cfg::kABytes, b_lbo, 1024);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -285,20 +290,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase, 3);
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t b_base = a_base + Cfg::kABytes;
+        // descriptors = stage-0 descriptor + constants (the start-address field counts 16-byte units; no tile crosses the 256 KB it spans)
+        const uint64_t adesc = adesc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
+        const uint64_t bdesc = bdesc0 + static_cast<uint64_t>(stage * (Cfg::kStageBytes >> 4));
 #pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t adesc = make_smem_desc(a_base + k * a_adv, a_lbo, 1024);
-          const uint64_t bdesc = make_smem_desc(b_base + k * b_adv, b_lbo, 1024);
-          umma_ss<kCta>(tmem_d, adesc, bdesc, idesc, (kb != kb0 || k != 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < BK / UMMA_K; ++k)
+          umma_ss<kCta>(tmem_d, adesc + ((k * a_adv) >> 4), bdesc + ((k * b_adv) >> 4), idesc, (kb != kb0 || k != 0) ? 1u : 0u);
         if constexpr (kCta == 1) umma_commit(&empty_bar[stage]); else umma_commit_2cta(&empty_bar[stage], 0b11);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if constexpr (kCta == 1) umma_commit(&tmem_full_bar[as]); else umma_commit_2cta(&tmem_full_bar[as], 0b11);
     }
-  } else if (warp_idx >= kEpiWarp0) {
+  } } else if (warp_idx >= kEpiWarp0) {
     // ======================= epilogue warps =======================
     const int ew = warp_idx - kEpiWarp0;  // 0..7
     const int wq = ew & 3;                // TMEM lane quarter: this warp may touch lanes [32*wq, 32*wq+32)
@@ -571,6 +574,10 @@ static inline int pick_bn(int N) {
     forced = e ? atoi(e) : 0;
   }
   if (forced == 128 || forced == 256) return forced;
+  if (forced == 1) {   // A/B: the width that pads N the least (N = 320: 384 vs 512 columns of MMA work; 640: 640 vs 768)
+    const int w256 = (N + 255) / 256 * 256, w128 = (N + 127) / 128 * 128;
+    return w128 < w256 ? 128 : 256;
+  }
   return N <= 128 ? 128 : 256;
 }
 
