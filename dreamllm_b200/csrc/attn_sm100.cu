@@ -122,6 +122,7 @@ __device__ __forceinline__ void store_acc_tile(uint32_t tmem_acc, uint8_t* stage
 // tile, to see which hand-off the iteration time is made of.  Slot layout: [tile j][16].
 #ifdef DLLM_ATTN_TRACE
 __device__ long long g_attn_trace[64 * 16 + 16];
+__device__ long long g_attn_cta_log[8192 * 4];   // per forward CTA: {clock64 at start, at end, smid, n_kv}
 #define ATTN_TRACE(j, k) do { if (trace_on && (j) < 64) g_attn_trace[(j) * 16 + (k)] = clock64(); } while (0)
 #else
 #define ATTN_TRACE(j, k) do { } while (0)
@@ -180,6 +181,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
   const int kv_end = kCausal ? min(kv_len, q0 + 128 + coff) : kv_len;
   const int n_kv = (kv_end + 63) / 64;
 #ifdef DLLM_ATTN_TRACE
+  const long long cta_t0 = clock64();
   const bool trace_on = (q0 == (gridDim.x - 1) * 128 && blockIdx.y == 1 && blockIdx.z == 0 && lane == 0);
   if (trace_on && warp == 0) g_attn_trace[64 * 16] = clock64();
 #endif
@@ -419,6 +421,363 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ 
 #ifdef DLLM_ATTN_TRACE
   if (trace_on && warp == 0) g_attn_trace[64 * 16 + 2] = clock64();
 #endif
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<1>(tmem_base, 256);
+#ifdef DLLM_ATTN_TRACE
+  if (threadIdx.x == 0) {
+    const int lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+    if (lin < 8192) {
+      uint32_t smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      g_attn_cta_log[lin * 4 + 0] = cta_t0;
+      g_attn_cta_log[lin * 4 + 1] = clock64();
+      g_attn_cta_log[lin * 4 + 2] = smid;
+      g_attn_cta_log[lin * 4 + 3] = n_kv;
+    }
+  }
+#endif
+}
+
+// ================================================================================================ forward, persistent
+// Same data path as attn_fwd_kernel<D, kCausal, true> (S / P in TMEM, TS-form PV, 3-stage K ring), but the grid is 2 CTAs per SM that
+// walk the (q tile, head, batch) items themselves.  Measured on the C2 shape with one CTA per item (profiles/r02n_attn_fwd_cta_log.json):
+// a CTA lives 9.7 k clk + 1.53 k clk per KV tile (17 tiles on average), and its SM slot then stays EMPTY for ~4 k clk until the next CTA
+// starts — 35 % of every slot went to launch gaps, TMEM alloc, barrier init, the exposed Q/K load latency and the O store.  Here a slot is
+// set up once; the producer starts the next item's Q / K loads as soon as the last QK^T of the current item retires (about two KV tiles
+// before its softmax / PV / O store finish), and the rings and barrier phases simply keep counting across items.
+//   * items come from a global atomic counter (the producer thread draws them and publishes them to the other roles through a 2-slot smem
+//     ring).  Their order is windows of ~2 items per CTA: all q tiles of W consecutive (head, batch) pairs, heaviest q tiles first.
+//     Heaviest-first balances the causal triangle; the window keeps the K / V of the heads in flight inside L2 — a plain heaviest-first
+//     order over ALL heads made every K / V tile an HBM read (2.2 GB per call, 6.1 TB/s: 355 us at B = 8 against 309 us non-persistent,
+//     while at B = 2-3, where K / V fit L2 anyway, the same kernel was already 12 % faster: profiles/r02r_attn_fwd_persist.md);
+//   * O is staged for its TMA store in the V ring (the Q buffer, which the one-shot kernel used, is already being refilled for the next
+//     item): the last PV of the item has retired by then, and the producer holds back the next item's first V loads until the four
+//     softmax warps report (o_stored) that their bulk stores have read the staging area;
+//   * the next item's first PV overwrites the O accumulator; it waits for P(0) of that item, which the softmax warps produce only after
+//     they have drained O — no extra barrier.
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kAttnThreads, 2)
+attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                        const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap to, bf16* __restrict__ out,
+                        long ld_o, float* __restrict__ lse, const int* __restrict__ seqlens, int B, int S, int Skv, int nh,
+                        float scale_log2, const uint8_t* __restrict__ kv_mask, int mask_ld, int* __restrict__ item_counter) {
+  const int coff = kCausal ? (Skv - S) : 0;
+  using L = FwdSmem<D, true>;
+  constexpr int NCH = L::NCH;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  constexpr int KS = L::kKStages;
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;       // the item's last QK^T has retired: the Q buffer may be refilled
+  uint64_t* k_full = bars + 2;        // [KS]  ring over ALL KV tiles this CTA processes: g % KS, phase (g / KS) & 1
+  uint64_t* k_empty = k_full + KS;    // [KS]
+  uint64_t* v_full = k_empty + KS;    // [2]
+  uint64_t* v_empty = v_full + 2;     // [2]
+  uint64_t* s_full = v_empty + 2;     // [2]
+  uint64_t* p_full = s_full + 2;      // [2]
+  uint64_t* pv_done = p_full + 2;     // [2]
+  uint64_t* o_stored = pv_done + 2;   // the item's O staging (V ring) has been read by the bulk stores
+  uint64_t* it_full = o_stored + 1;   // [2]  item ring
+  uint64_t* it_empty = it_full + 2;   // [2]
+  uint32_t* item_ring = reinterpret_cast<uint32_t*>(it_empty + 2);   // [2]
+  uint32_t* tmem_ptr = item_ring + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = (S + 127) / 128, n_hb = nh * B, n_items = nq * n_hb;
+#ifdef DLLM_ATTN_TRACE
+  const bool trace_on = (blockIdx.x == 0 && lane == 0);
+  int tr_item = 0;
+  if (trace_on && warp == 0) g_attn_trace[64 * 16] = clock64();
+#endif
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_fwd_persist: smem misaligned\n"); __trap(); }
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&it_full[i], 1);
+      mbar_init(&it_empty[i], 5);     // MMA thread + one lane of each softmax warp
+    }
+    mbar_init(o_stored, 4);
+    fence_mbar_init();
+  }
+  if (warp == 5) { tmem_alloc<1>(tmem_ptr, 256); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base;        // 2 x 64 columns
+  const uint32_t tmem_O = tmem_base + 128;  // D columns
+
+  // item w (heaviest first) -> q tile, head, batch, and its KV tile count; identical in every role
+  struct Item { int q0, h, b, kv_len, q_len, n_kv; };
+  const int win_heads = max(1, min(n_hb, (2 * static_cast<int>(gridDim.x) + nq - 1) / nq));   // ~2 items per CTA per window
+  const int full_items = (n_hb / win_heads) * win_heads * nq;
+  auto item = [&](int w) {
+    Item it;
+    const int win = (w < full_items) ? w / (win_heads * nq) : n_hb / win_heads;
+    const int idx = (w < full_items) ? w % (win_heads * nq) : w - full_items;
+    const int R = (w < full_items) ? win_heads : n_hb % win_heads;
+    const int qt = nq - 1 - idx / R, hb = win * win_heads + idx % R;
+    it.q0 = qt * 128; it.h = hb % nh; it.b = hb / nh;
+    it.kv_len = seqlens ? min(seqlens[it.b], Skv) : Skv;
+    it.q_len = seqlens ? it.kv_len : S;
+    const int kv_end = kCausal ? min(it.kv_len, it.q0 + 128 + coff) : it.kv_len;
+    it.n_kv = (kv_end + 63) / 64;
+    return it;
+  };
+
+  // consumer side of the item ring: slot n & 1, phase (n >> 1) & 1 for the n-th item this CTA sees (n_items = sentinel: no more work)
+  auto next_item = [&](uint32_t n, bool one_lane_arrives) {
+    mbar_wait(&it_full[n & 1], (n >> 1) & 1, 19);
+    const int w = static_cast<int>(item_ring[n & 1]);
+    if (one_lane_arrives) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&it_empty[n & 1]);
+    } else {
+      mbar_arrive(&it_empty[n & 1]);
+    }
+    return w;
+  };
+
+  if (warp == 4) { if (elect_one_sync()) {
+    // ---------------- TMA producer + item scheduler ----------------
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv);
+    uint32_t kg = 0, vg = 0, tc = 0;     // K tiles / V tiles requested so far, non-empty items started
+    for (uint32_t n = 0;; ++n) {
+      int w = atomicAdd(item_counter, 1);
+      if (w > n_items) w = n_items;
+      mbar_wait(&it_empty[n & 1], ((n >> 1) & 1) ^ 1, 19);
+      item_ring[n & 1] = static_cast<uint32_t>(w);
+      mbar_arrive(&it_full[n & 1]);    // release semantics: the ring write is visible to whoever observes the phase flip
+      if (w >= n_items) break;
+      const Item it = item(w);
+      if (it.n_kv == 0) continue;
+      ATTN_TRACE(tc, 6);
+      mbar_wait(q_empty, (tc & 1) ^ 1, 10);
+      ATTN_TRACE(tc, 7);
+      mbar_arrive_expect_tx(q_full, 128 * D * 2);
+      for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oQ + c * 16384, &tq, q_full, it.h * D + c * 64, it.q0, it.b);
+      int jk = 0;
+      auto load_k = [&](int jj) {
+        const uint32_t ks = kg % KS;
+        mbar_wait(&k_empty[ks], ((kg / KS) & 1) ^ 1, 10);
+        mbar_arrive_expect_tx(&k_full[ks], 64 * D * 2);
+        for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oK + ks * L::kKV + c * 8192, &tk, &k_full[ks], it.h * D + c * 64, jj * 64, it.b);
+        ++kg;
+      };
+      for (int j = 0; j < it.n_kv; ++j) {
+        while (jk < it.n_kv && jk < j + KS - 1) load_k(jk++);
+        if (jk <= j) load_k(jk++);
+        const uint32_t st = vg & 1;
+        if (j == 0 && tc > 0) mbar_wait(o_stored, (tc - 1) & 1, 11);   // the previous item's O staging lives in the V ring
+        mbar_wait(&v_empty[st], ((vg >> 1) & 1) ^ 1, 11);
+        mbar_arrive_expect_tx(&v_full[st], 64 * D * 2);
+        for (int c = 0; c < NCH; ++c) tma_load_3d(smem + L::oV + st * L::kKV + c * 8192, &tv, &v_full[st], it.h * D + c * 64, j * 64, it.b);
+        ++vg;
+      }
+      ATTN_TRACE(tc, 9);
+      ++tc;
+    }
+  } } else if (warp == 5) { if (elect_one_sync()) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_qk = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, D, false, true);
+    const uint32_t sQ = smem_u32(smem + L::oQ), sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV);
+    uint32_t g0 = 0, tc = 0;             // KV tiles of the finished items, non-empty items started
+    for (uint32_t n = 0;; ++n) {
+      const int w = next_item(n, false);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      if (it.n_kv == 0) continue;
+      auto issue_qk = [&](int j) {
+        const uint32_t g = g0 + j, ks = g % KS;
+        mbar_wait(&k_full[ks], (g / KS) & 1, 12);
+        tc_fence_after();
+        mma_tile<D / 16>(tmem_S + (g & 1) * 64, sQ, false, 16384, sK + ks * L::kKV, false, 8192, idesc_qk, false);
+        umma_commit(&k_empty[ks]);
+        umma_commit(&s_full[g & 1]);
+        if (j == it.n_kv - 1) umma_commit(q_empty);
+      };
+      ATTN_TRACE(tc, 10);
+      mbar_wait(q_full, tc & 1, 13);
+      ATTN_TRACE(tc, 5);
+      issue_qk(0);
+      for (int j = 0; j < it.n_kv; ++j) {
+        if (j + 1 < it.n_kv) issue_qk(j + 1);
+        const uint32_t g = g0 + j, st = g & 1, ph = (g >> 1) & 1;
+        mbar_wait(&v_full[st], ph, 14);
+        mbar_wait(&p_full[st], ph, 15);
+        tc_fence_after();
+        // O (+)= P V_j, P read from TMEM (32 columns at the base of S buffer g & 1); j == 0 overwrites the previous item's O, which its
+        // softmax warps drained before they produced this P
+        mma_tile_ts<4>(tmem_O, tmem_S + st * 64, 8, sV + st * L::kKV, true, 8192, idesc_pv, j > 0);
+        umma_commit(&v_empty[st]);
+        umma_commit(&pv_done[st]);
+      }
+      g0 += it.n_kv;
+      ++tc;
+    }
+  } } else if (warp < 4) {
+    // ---------------- softmax rows ----------------
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(warp * 32) << 16;
+    uint32_t g0 = 0;
+    for (uint32_t n = 0;; ++n) {
+      const int w = next_item(n, true);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      const int q_row = it.q0 + row;
+      bf16* orow = out + (static_cast<size_t>(it.b) * S + q_row) * ld_o + it.h * D;
+      if (it.n_kv == 0) {   // no keys at all: zeros
+        if (q_row < S) {
+#pragma unroll
+          for (int c = 0; c < D / 8; ++c) reinterpret_cast<uint4*>(orow)[c] = make_uint4(0u, 0u, 0u, 0u);
+          lse[(static_cast<size_t>(it.b) * nh + it.h) * S + q_row] = INFINITY;
+        }
+        continue;
+      }
+      float m_run = -INFINITY, l_run = 0.f;
+#ifdef DLLM_ATTN_TRACE
+      if (warp == 0) { ATTN_TRACE(tr_item, 0); if (trace_on && tr_item < 64) g_attn_trace[tr_item * 16 + 8] = it.n_kv; }
+#endif
+      for (int j = 0; j < it.n_kv; ++j) {
+        const uint32_t g = g0 + j, sb = g & 1, ph = (g >> 1) & 1;
+        mbar_wait(&s_full[sb], ph, 16);
+#ifdef DLLM_ATTN_TRACE
+        if (warp == 0 && j == 0) ATTN_TRACE(tr_item, 1);
+        if (warp == 0 && j == 4) ATTN_TRACE(tr_item, 11);
+        if (warp == 0 && j == 8) ATTN_TRACE(tr_item, 12);
+#endif
+        tc_fence_after();
+        uint32_t sv[64];
+        tmem_ld32(tmem_S + lane_off + sb * 64, sv);
+        tmem_ld32(tmem_S + lane_off + sb * 64 + 32, sv + 32);
+        tmem_ld_wait();
+        const int kv0 = j * 64;
+        const bool need_mask = (kCausal && kv0 + 63 > it.q0 + warp * 32 + coff) || (kv0 + 64 > it.kv_len) || (kv_mask != nullptr);
+        float mx = -INFINITY;
+        if (need_mask) {
+          uint32_t mw[16];
+          if (kv_mask != nullptr) {
+            const uint4* mp = reinterpret_cast<const uint4*>(kv_mask + static_cast<size_t>(it.b) * mask_ld + kv0);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const uint4 t = __ldg(mp + i);
+              mw[4 * i] = t.x; mw[4 * i + 1] = t.y; mw[4 * i + 2] = t.z; mw[4 * i + 3] = t.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) mw[i] = 0x01010101u;
+          }
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const int kvi = kv0 + c;
+            const bool ok = (kvi < it.kv_len) && (!kCausal || kvi <= q_row + coff) && (((mw[c >> 2] >> (8 * (c & 3))) & 0xffu) != 0u);
+            const float sc = ok ? __uint_as_float(sv[c]) : -INFINITY;
+            sv[c] = __float_as_uint(sc);
+            mx = fmaxf(mx, sc);
+          }
+        } else {
+          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 64; c += 4) {
+            m0 = fmaxf(m0, __uint_as_float(sv[c]));
+            m1 = fmaxf(m1, __uint_as_float(sv[c + 1]));
+            m2 = fmaxf(m2, __uint_as_float(sv[c + 2]));
+            m3 = fmaxf(m3, __uint_as_float(sv[c + 3]));
+          }
+          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        }
+        const float m_new = fmaxf(m_run, mx * scale_log2);
+        const bool need = (m_new - m_run) > 8.0f;     // lazy rescale (see attn_fwd_kernel)
+        const bool any = __any_sync(0xffffffffu, need);
+        if (any) {
+          const float m_tgt = (m_new == -INFINITY) ? m_run : m_new;
+          const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_tgt);
+          if (j > 0) {
+            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 17);   // O quiescent
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < D / 32; ++c) {
+              uint32_t o[32];
+              tmem_ld32(tmem_O + lane_off + c * 32, o);
+              tmem_ld_wait();
+#pragma unroll
+              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+              tmem_st32(tmem_O + lane_off + c * 32, o);
+            }
+            tmem_st_wait();
+          }
+          l_run *= alpha;
+          m_run = m_tgt;
+        }
+        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+        float ls0 = 0.f, ls1 = 0.f;
+        uint32_t pw[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - m_use);
+          const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - m_use);
+          ls0 += p0;
+          ls1 += p1;
+          pw[c] = pack_bf16(p0, p1);
+        }
+        tmem_st32(tmem_S + lane_off + sb * 64, pw);
+        tmem_st_wait();
+        l_run += ls0 + ls1;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[sb]);
+      }
+      const uint32_t gl = g0 + it.n_kv - 1;
+      if (warp == 0) ATTN_TRACE(tr_item, 2);
+      mbar_wait(&pv_done[gl & 1], (gl >> 1) & 1, 18);
+      if (warp == 0) ATTN_TRACE(tr_item, 3);
+      tc_fence_after();
+      const bool valid_row = (q_row < it.q_len) && l_run > 0.f;
+      const float inv = valid_row ? 1.f / l_run : 0.f;
+      // O -> bf16 -> swizzled staging in the (now idle) V ring -> per-warp TMA store of [32 rows x 64 cols] boxes; rows >= S are clipped
+      {
+        uint8_t* stage = smem + L::oV;
+#pragma unroll 1
+        for (int c = 0; c < D / 32; ++c) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_off + c * 32, o);
+          tmem_ld_wait();
+          uint8_t* tile = stage + (c >> 1) * 16384;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float f[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) f[x] = __uint_as_float(o[8 * e + x]) * inv;
+            store_row_chunk(tile, row, (c & 1) * 4 + e, f);
+          }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          for (int c = 0; c < NCH; ++c) tma_store_3d(&to, stage + c * 16384 + warp * 4096, it.h * D + c * 64, it.q0 + warp * 32, it.b);
+          tma_store_commit();
+          tma_store_wait_read<0>();
+          mbar_arrive(o_stored);
+        }
+      }
+      if (q_row < S)
+        lse[(static_cast<size_t>(it.b) * nh + it.h) * S + q_row] = valid_row ? (m_run + log2f(l_run)) * kLn2 : INFINITY;
+      tc_fence_before();   // the TMEM reads above are ordered before the arrive on p_full that releases the next item's first PV
+#ifdef DLLM_ATTN_TRACE
+      if (warp == 0) ATTN_TRACE(tr_item, 4);
+      ++tr_item;
+#endif
+      g0 += it.n_kv;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 5) tmem_dealloc<1>(tmem_base, 256);
@@ -912,6 +1271,10 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
   const int i_begin = kCausal ? (kv0 / 64) : 0;
   const int i_end = (len + 63) / 64;
   const int n_it = (kv0 < len_kv) ? max(i_end - i_begin, 0) : 0;
+#ifdef DLLM_ATTN_TRACE
+  const bool trace_on = (blockIdx.x == 0 && blockIdx.y == 1 && blockIdx.z == 0 && lane == 0);
+  if (trace_on && warp == 0) g_attn_trace[64 * 16 + 3] = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023) { printf("attn_bwd_dkdv_ts: smem misaligned\n"); __trap(); }
@@ -948,7 +1311,9 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
     for (int it = 0; it < n_it; ++it) {
       const int rs = it % kBwdRing;
       const int qr0 = (i_begin + it) * 64;
+      ATTN_TRACE(it, 8);
       mbar_wait(&qdo_empty[rs], ((it / kBwdRing) & 1) ^ 1, 40);
+      ATTN_TRACE(it, 9);
       mbar_arrive_expect_tx(&qdo_full[rs], 2 * 64 * D * 2 + 512);
       for (int c = 0; c < NCH; ++c) {
         tma_load_3d(smem + L::oQ + rs * L::kQ + c * 8192, &tq, &qdo_full[rs], h * D + c * 64, qr0, b);
@@ -965,7 +1330,9 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
                    sDO = smem_u32(smem + L::oDO);
     auto issue_s = [&](int it) {
       const int st = it & 1, rs = it % kBwdRing;
+      ATTN_TRACE(it, 11);
       mbar_wait(&qdo_full[rs], (it / kBwdRing) & 1, 41);
+      ATTN_TRACE(it, 5);
       tc_fence_after();
       mma_tile<D / 16>(tmem_St + st * 64, sK, false, 16384, sQ + rs * L::kQ, false, 8192, idesc_s, false);
       mma_tile<D / 16>(tmem_dPt + st * 64, sV, false, 16384, sDO + rs * L::kQ, false, 8192, idesc_s, false);
@@ -976,7 +1343,9 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
     for (int it = 0; it < n_it; ++it) {
       if (it + 1 < n_it) issue_s(it + 1);
       const int st = it & 1, rs = it % kBwdRing;
+      ATTN_TRACE(it, 6);
       mbar_wait(&pds_full[st], (it >> 1) & 1, 43);
+      ATTN_TRACE(it, 7);
       tc_fence_after();
       // dV += P^T dO_i : A = P^T from TMEM (k-step ks = q columns [16 ks, 16 ks + 16) at column 16 ks);  dK += dS^T Q_i
       mma_tile_ts<4>(tmem_dV, tmem_St + st * 64, 16, sDO + rs * L::kQ, true, 8192, idesc_acc, it > 0);
@@ -993,8 +1362,10 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1, rs = it % kBwdRing;
       const int qc0 = (i_begin + it) * 64 + part * 16;  // first q index of my 16 columns
+      if (warp == 0) ATTN_TRACE(it, 10);
       mbar_wait(&qdo_full[rs], (it / kBwdRing) & 1, 45);  // the bulk-copied lse / delta of this q tile are visible to this thread
       mbar_wait(&sdp_full[st], (it >> 1) & 1, 44);
+      if (warp == 0) ATTN_TRACE(it, 0);
       tc_fence_after();
       uint32_t sv[16], dv[16];
       tmem_ld16(tmem_St + lane_off + st * 64 + part * 16, sv);
@@ -1011,6 +1382,7 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
         }
       }
       tmem_ld_wait();
+      if (warp == 0) ATTN_TRACE(it, 1);
       uint32_t pw[8], dw[8];
       const bool full_tile = (qc0 + 15 < len) && (kv0 + 127 < len_kv) && (!kCausal || kv0 + 127 <= qc0);
       if (full_tile) {
@@ -1037,12 +1409,14 @@ attn_bwd_dkdv_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
           dw[c] = pack_bf16(de[0], de[1]);
         }
       }
+      if (warp == 0) ATTN_TRACE(it, 3);
       tmem_st8(tmem_St + lane_off + st * 64 + part * 16, pw);
       tmem_st8(tmem_dPt + lane_off + st * 64 + part * 16, dw);
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[st]);
+      if (warp == 0) ATTN_TRACE(it, 4);
     }
     // epilogue: 4 (D = 128) or 2 (D = 64) 64-column chunk jobs {dV, dK} x chunks, one per `part`
     constexpr int kJobs = 2 * NCH;
@@ -1240,6 +1614,539 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
   if (warp == kBwdRowWarps + 1) tmem_dealloc<1>(tmem_base, 512);
 }
 
+// ================================================================================================ backward, persistent
+// The TS-form backward kernels (above) with the same treatment as the forward: ONE CTA per SM walks (tile, head, batch) items drawn from
+// an atomic counter in windowed heaviest-first order, instead of one CTA per item.  With one 194 KB CTA per SM nothing hid a CTA's
+// fixed costs: the dK/dV trace (profiles/r02m_attn_bwd_timeline.md) shows 9.8 k clk from CTA start to the first S^T (K/V + first Q/dO
+// load latency on a cold SM), ~3 k clk of epilogue and ~4 k clk until the next CTA starts on the SM, against 17 iterations x 1.5 k clk of
+// work on average — 40 % of the SM's time.  Persistent:
+//   * the Q/dO (dK/dV kernel) resp. K/V (dQ kernel) operand ring and every barrier phase keep counting across items, so the producer
+//     prefetches the next item's first ring tiles while the current item's last iterations and epilogue run;
+//   * the stationary operands (K, V resp. Q, dO) are refilled as soon as the item's last S / dP tile-GEMMs retire (`stat_empty`);
+//   * the accumulators leave through the operand ring: the epilogue stages bf16 tiles in the ring stage(s) the item used last (free once
+//     its last accumulate-MMAs retire), and the producer refills those stages only after `o_stored` says the bulk stores have read them;
+//   * the next item's first accumulate-MMA (accumulate = 0) needs P^T/dS^T of that item from all 16 row warps, which produce it only
+//     after their part of the epilogue has drained the accumulators — no extra barrier.
+struct BwdOut {
+  bf16* dq; bf16* dk; bf16* dv;
+  long ld_dq, ld_dkv;
+};
+struct ItemId { int tile, hb; };
+// w-th item in windowed order: windows of `win_heads` (head, batch) pairs, inside a window tiles in heaviest-first order
+__device__ __forceinline__ ItemId decode_item(int w, int ntiles, int n_hb, int win_heads, bool descending) {
+  const int wsz = win_heads * ntiles, n_full = n_hb / win_heads, full_items = n_full * wsz;
+  int win, idx, R;
+  if (w < full_items) { win = w / wsz; idx = w - win * wsz; R = win_heads; }
+  else { win = n_full; idx = w - full_items; R = n_hb - n_full * win_heads; }
+  const int tpos = idx / R;
+  ItemId r;
+  r.tile = descending ? ntiles - 1 - tpos : tpos;
+  r.hb = win * win_heads + idx - tpos * R;
+  return r;
+}
+// this warp's 32 accumulator rows x 64 fp32 columns -> * mul -> bf16 -> 128B-swizzled 4 KB staging block -> one [32 x 64] TMA store box;
+// returns when the bulk store has read the staging block
+__device__ __forceinline__ void store_acc_rows64(uint32_t tmem_acc, uint8_t* stage_warp, float mul, const CUtensorMap* tm, int gcol,
+                                                 int grow, int b, int lane) {
+#pragma unroll 1
+  for (int hlf = 0; hlf < 2; ++hlf) {
+    uint32_t v[32];
+    tmem_ld32(tmem_acc + hlf * 32, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 q;
+      q.x = pack_bf16(__uint_as_float(v[8 * j + 0]) * mul, __uint_as_float(v[8 * j + 1]) * mul);
+      q.y = pack_bf16(__uint_as_float(v[8 * j + 2]) * mul, __uint_as_float(v[8 * j + 3]) * mul);
+      q.z = pack_bf16(__uint_as_float(v[8 * j + 4]) * mul, __uint_as_float(v[8 * j + 5]) * mul);
+      q.w = pack_bf16(__uint_as_float(v[8 * j + 6]) * mul, __uint_as_float(v[8 * j + 7]) * mul);
+      *reinterpret_cast<uint4*>(stage_warp + lane * 128 + (((hlf * 4 + j) ^ (lane & 7)) << 4)) = q;
+    }
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_3d(tm, stage_warp, gcol, grow, b);
+    tma_store_commit();
+    tma_store_wait_read<0>();
+  }
+}
+__device__ __forceinline__ void zero_row64(bf16* p) {
+#pragma unroll
+  for (int c = 0; c < 8; ++c) reinterpret_cast<uint4*>(p)[c] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kBwdTsThreads, 1)
+attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                             const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                             const __grid_constant__ CUtensorMap tdk, const __grid_constant__ CUtensorMap tdv,
+                             const float* __restrict__ lse2, const float* __restrict__ delta, const int* __restrict__ seqlens,
+                             BwdOut go, int B, int S, int Skv, int S_pad, int nh, float scale, float scale_log2,
+                             int* __restrict__ item_counter) {
+  using L = BwdKVTsSmem<D>;
+  constexpr int NCH = L::NCH;
+  constexpr int R4 = kBwdRing;
+  static_assert(R4 == 4, "stage arithmetic below assumes a 4-stage ring");
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* kv_full = bars + 0;
+  uint64_t* kv_empty = bars + 1;                  // the item's last S^T / dP^T tile-GEMMs have retired: K / V may be refilled
+  uint64_t* qdo_full = bars + 2;                  // [4]  ring over ALL q tiles this CTA processes: g % 4, phase (g / 4) & 1
+  uint64_t* qdo_empty = qdo_full + R4;            // [4]
+  uint64_t* sdp_full = qdo_empty + R4;            // [2]  TMEM double buffer: g & 1, phase (g >> 1) & 1
+  uint64_t* pds_full = sdp_full + 2;              // [2]
+  uint64_t* acc_done = pds_full + 2;              // [2]
+  uint64_t* o_stored = acc_done + 2;              // the item's dK / dV staging (two ring stages) has been read by the bulk stores
+  uint64_t* it_full = o_stored + 1;               // [2]  item ring
+  uint64_t* it_empty = it_full + 2;               // [2]
+  uint32_t* item_ring = reinterpret_cast<uint32_t*>(it_empty + 2);
+  uint32_t* tmem_ptr = item_ring + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kJobs = 2 * NCH;                  // 64-column chunk jobs {dV, dK} x chunks, one per `part`
+  const int nt = (Skv + 127) / 128, n_hb = nh * B, n_items = nt * n_hb;
+  const int win_heads = max(1, min(n_hb, (2 * static_cast<int>(gridDim.x) + nt - 1) / nt));
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_bwd_dkdv_persist: smem misaligned\n"); __trap(); }
+    mbar_init(kv_full, 1); mbar_init(kv_empty, 1);
+    for (int i = 0; i < R4; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&pds_full[i], kBwdRowWarps);
+      mbar_init(&it_full[i], 1);
+      mbar_init(&it_empty[i], kBwdRowWarps + 1);  // MMA thread + one lane of every row warp
+    }
+    mbar_init(o_stored, 4 * kJobs);
+    fence_mbar_init();
+  }
+  if (warp == kBwdRowWarps + 1) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_St = tmem_base, tmem_dPt = tmem_base + 128, tmem_dV = tmem_base + 256, tmem_dK = tmem_base + 256 + D;
+
+  struct Item { int kv0, h, b, len, len_kv, i_begin, n_it; };
+  auto item = [&](int w) {
+    const ItemId id = decode_item(w, nt, n_hb, win_heads, false);   // causal: kv tile 0 sees every q tile -> heaviest first
+    Item it;
+    it.kv0 = id.tile * 128; it.h = id.hb % nh; it.b = id.hb / nh;
+    it.len = seqlens ? min(seqlens[it.b], S) : S;
+    it.len_kv = seqlens ? it.len : Skv;
+    it.i_begin = kCausal ? (it.kv0 / 64) : 0;
+    const int i_end = (it.len + 63) / 64;
+    it.n_it = (it.kv0 < it.len_kv) ? max(i_end - it.i_begin, 0) : 0;
+    return it;
+  };
+  auto next_item = [&](uint32_t n, bool one_lane_arrives) {
+    mbar_wait(&it_full[n & 1], (n >> 1) & 1, 39);
+    const int w = static_cast<int>(item_ring[n & 1]);
+    if (one_lane_arrives) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&it_empty[n & 1]);
+    } else {
+      mbar_arrive(&it_empty[n & 1]);
+    }
+    return w;
+  };
+
+  if (warp == kBwdRowWarps) { if (elect_one_sync()) {
+    // ---------------- TMA producer + item scheduler ----------------
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    uint32_t qg = 0, ic = 0, hold = 0;   // q tiles requested, non-empty items started, ring stages holding un-stored dK / dV staging
+    for (uint32_t n = 0;; ++n) {
+      int w = atomicAdd(item_counter, 1);
+      if (w > n_items) w = n_items;
+      mbar_wait(&it_empty[n & 1], ((n >> 1) & 1) ^ 1, 39);
+      item_ring[n & 1] = static_cast<uint32_t>(w);
+      mbar_arrive(&it_full[n & 1]);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      if (it.n_it == 0) continue;
+      mbar_wait(kv_empty, (ic & 1) ^ 1, 40);
+      mbar_arrive_expect_tx(kv_full, 2 * 128 * D * 2);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smem + L::oK + c * 16384, &tk, kv_full, it.h * D + c * 64, it.kv0, it.b);
+        tma_load_3d(smem + L::oV + c * 16384, &tv, kv_full, it.h * D + c * 64, it.kv0, it.b);
+      }
+      const float* lse_bh = lse2 + (static_cast<size_t>(it.b) * nh + it.h) * S_pad;
+      const float* del_bh = delta + (static_cast<size_t>(it.b) * nh + it.h) * S_pad;
+      for (int t = 0; t < it.n_it; ++t) {
+        const uint32_t rs = qg & 3;
+        const int qr0 = (it.i_begin + t) * 64;
+        if ((hold >> rs) & 1u) { mbar_wait(o_stored, (ic - 1) & 1, 40); hold = 0; }   // (ic >= 1 whenever hold != 0)
+        mbar_wait(&qdo_empty[rs], ((qg >> 2) & 1) ^ 1, 40);
+        mbar_arrive_expect_tx(&qdo_full[rs], 2 * 64 * D * 2 + 512);
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_3d(smem + L::oQ + rs * L::kQ + c * 8192, &tq, &qdo_full[rs], it.h * D + c * 64, qr0, it.b);
+          tma_load_3d(smem + L::oDO + rs * L::kQ + c * 8192, &tdo, &qdo_full[rs], it.h * D + c * 64, qr0, it.b);
+        }
+        bulk_load_1d(smem + L::oStat + rs * 512, lse_bh + qr0, 256, &qdo_full[rs]);
+        bulk_load_1d(smem + L::oStat + rs * 512 + 256, del_bh + qr0, 256, &qdo_full[rs]);
+        ++qg;
+      }
+      hold |= (1u << ((qg + 3) & 3)) | (1u << ((qg + 2) & 3));   // the stages of the item's last two q tiles become its staging area
+      ++ic;
+    }
+  } } else if (warp == kBwdRowWarps + 1) { if (elect_one_sync()) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+    const uint32_t sK = smem_u32(smem + L::oK), sV = smem_u32(smem + L::oV), sQ = smem_u32(smem + L::oQ),
+                   sDO = smem_u32(smem + L::oDO);
+    uint32_t g0 = 0, ic = 0;
+    for (uint32_t n = 0;; ++n) {
+      const int w = next_item(n, false);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      if (it.n_it == 0) continue;
+      auto issue_s = [&](int t) {
+        const uint32_t g = g0 + t, st = g & 1, rs = g & 3;
+        mbar_wait(&qdo_full[rs], (g >> 2) & 1, 41);
+        tc_fence_after();
+        mma_tile<D / 16>(tmem_St + st * 64, sK, false, 16384, sQ + rs * L::kQ, false, 8192, idesc_s, false);
+        mma_tile<D / 16>(tmem_dPt + st * 64, sV, false, 16384, sDO + rs * L::kQ, false, 8192, idesc_s, false);
+        umma_commit(&sdp_full[st]);
+        if (t == it.n_it - 1) umma_commit(kv_empty);
+      };
+      mbar_wait(kv_full, ic & 1, 42);
+      issue_s(0);
+      for (int t = 0; t < it.n_it; ++t) {
+        if (t + 1 < it.n_it) issue_s(t + 1);
+        const uint32_t g = g0 + t, st = g & 1, rs = g & 3;
+        mbar_wait(&pds_full[st], (g >> 1) & 1, 43);
+        tc_fence_after();
+        // dV (+)= P^T dO_i, dK (+)= dS^T Q_i with P^T / dS^T read from TMEM; t == 0 overwrites the previous item's accumulators, which
+        // its row warps drained before they produced this P^T / dS^T
+        mma_tile_ts<4>(tmem_dV, tmem_St + st * 64, 16, sDO + rs * L::kQ, true, 8192, idesc_acc, t > 0);
+        mma_tile_ts<4>(tmem_dK, tmem_dPt + st * 64, 16, sQ + rs * L::kQ, true, 8192, idesc_acc, t > 0);
+        umma_commit(&qdo_empty[rs]);
+        umma_commit(&acc_done[st]);
+      }
+      g0 += it.n_it;
+      ++ic;
+    }
+  } } else if (warp < kBwdRowWarps) {
+    // ---------------- row warps ----------------
+    const int wq = warp & 3, part = warp >> 2;
+    const int row = wq * 32 + lane;  // kv row within tile
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const bool my_store = part < kJobs;
+    const int acc = part / NCH, ch = part % NCH;
+    uint32_t g0 = 0, ic = 0;
+    for (uint32_t n = 0;; ++n) {
+      const int w = next_item(n, true);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      const int kv_row = it.kv0 + row;
+      if (it.n_it == 0) {   // no query attends to this kv tile: zeros
+        if (my_store && kv_row < Skv)
+          zero_row64((acc == 0 ? go.dv : go.dk) + (static_cast<size_t>(it.b) * Skv + kv_row) * go.ld_dkv + it.h * D + ch * 64);
+        continue;
+      }
+      for (int t = 0; t < it.n_it; ++t) {
+        const uint32_t g = g0 + t, st = g & 1, rs = g & 3;
+        const int qc0 = (it.i_begin + t) * 64 + part * 16;  // first q index of my 16 columns
+        mbar_wait(&qdo_full[rs], (g >> 2) & 1, 45);  // the bulk-copied lse / delta of this q tile are visible to this thread
+        mbar_wait(&sdp_full[st], (g >> 1) & 1, 44);
+        tc_fence_after();
+        uint32_t sv[16], dv[16];
+        tmem_ld16(tmem_St + lane_off + st * 64 + part * 16, sv);
+        tmem_ld16(tmem_dPt + lane_off + st * 64 + part * 16, dv);
+        float lq[16], dq_[16];
+        {
+          const float4* ls = reinterpret_cast<const float4*>(smem + L::oStat + rs * 512) + part * 4;
+          const float4* ds4 = reinterpret_cast<const float4*>(smem + L::oStat + rs * 512 + 256) + part * 4;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 a = ls[i], c = ds4[i];
+            lq[4 * i] = a.x; lq[4 * i + 1] = a.y; lq[4 * i + 2] = a.z; lq[4 * i + 3] = a.w;
+            dq_[4 * i] = c.x; dq_[4 * i + 1] = c.y; dq_[4 * i + 2] = c.z; dq_[4 * i + 3] = c.w;
+          }
+        }
+        tmem_ld_wait();
+        uint32_t pw[8], dw[8];
+        const bool full_tile = (qc0 + 15 < it.len) && (it.kv0 + 127 < it.len_kv) && (!kCausal || it.kv0 + 127 <= qc0);
+        if (full_tile) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - lq[2 * c]);
+            const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - lq[2 * c + 1]);
+            pw[c] = pack_bf16(p0, p1);
+            dw[c] = pack_bf16(p0 * (__uint_as_float(dv[2 * c]) - dq_[2 * c]), p1 * (__uint_as_float(dv[2 * c + 1]) - dq_[2 * c + 1]));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float pe[2], de[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int cc = 2 * c + e;
+              const int qi = qc0 + cc;
+              const bool ok = (qi < it.len) && (kv_row < it.len_kv) && (!kCausal || kv_row <= qi);
+              pe[e] = ok ? exp2f(__uint_as_float(sv[cc]) * scale_log2 - lq[cc]) : 0.f;
+              de[e] = ok ? pe[e] * (__uint_as_float(dv[cc]) - dq_[cc]) : 0.f;
+            }
+            pw[c] = pack_bf16(pe[0], pe[1]);
+            dw[c] = pack_bf16(de[0], de[1]);
+          }
+        }
+        tmem_st8(tmem_St + lane_off + st * 64 + part * 16, pw);
+        tmem_st8(tmem_dPt + lane_off + st * 64 + part * 16, dw);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pds_full[st]);
+      }
+      // epilogue: job `part` = one 64-column chunk of dV or dK, staged in the ring stages of the item's last two q tiles
+      const uint32_t gl = g0 + it.n_it - 1;
+      mbar_wait(&acc_done[gl & 1], (gl >> 1) & 1, 46);
+      tc_fence_after();
+      if (my_store) {
+        if (ic > 0) mbar_wait(o_stored, (ic - 1) & 1, 47);   // every warp's bulk store of the previous item has read its staging
+        const uint32_t sA = gl & 3, sB = (gl + 3) & 3;
+        uint8_t* stage;
+        if constexpr (NCH == 2) {   // four 16 KB chunks: {Q part, dO part} of stage sA, then of stage sB
+          stage = smem + ((part & 1) ? L::oDO : L::oQ) + ((part >> 1) ? sB : sA) * L::kQ + wq * 4096;
+        } else {                    // two 16 KB chunks, each = the 8 KB Q part + 8 KB dO part of one stage
+          stage = smem + ((wq >> 1) ? L::oDO : L::oQ) + (part ? sB : sA) * L::kQ + (wq & 1) * 4096;
+        }
+        store_acc_rows64((acc == 0 ? tmem_dV : tmem_dK) + lane_off + ch * 64, stage, acc == 0 ? 1.f : scale, acc == 0 ? &tdv : &tdk,
+                         it.h * D + ch * 64, it.kv0 + wq * 32, it.b, lane);
+        if (lane == 0) mbar_arrive(o_stored);
+      }
+      tc_fence_before();
+      g0 += it.n_it;
+      ++ic;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBwdRowWarps + 1) tmem_dealloc<1>(tmem_base, 512);
+}
+
+template <int D, bool kCausal>
+__global__ void __launch_bounds__(kBwdTsThreads, 1)
+attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_constant__ CUtensorMap tk,
+                           const __grid_constant__ CUtensorMap tv, const __grid_constant__ CUtensorMap tdo,
+                           const __grid_constant__ CUtensorMap tdq, const float* __restrict__ lse2, const float* __restrict__ delta,
+                           const int* __restrict__ seqlens, BwdOut go, int B, int S, int Skv, int S_pad, int nh, float scale,
+                           float scale_log2, int* __restrict__ item_counter) {
+  using L = BwdQTsSmem<D>;
+  constexpr int NCH = L::NCH;
+  constexpr int R4 = kBwdRing;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::oBar);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;                 // the item's last S / dP tile-GEMMs have retired: Q / dO may be refilled
+  uint64_t* kv_full = bars + 2;                 // [4]  ring over ALL kv tiles this CTA processes
+  uint64_t* kv_empty = kv_full + R4;            // [4]
+  uint64_t* sdp_full = kv_empty + R4;           // [2]
+  uint64_t* ds_full = sdp_full + 2;             // [2]
+  uint64_t* acc_done = ds_full + 2;             // [2]
+  uint64_t* o_stored = acc_done + 2;            // the item's dQ staging (one ring stage) has been read by the bulk stores
+  uint64_t* it_full = o_stored + 1;             // [2]
+  uint64_t* it_empty = it_full + 2;             // [2]
+  uint32_t* item_ring = reinterpret_cast<uint32_t*>(it_empty + 2);
+  uint32_t* tmem_ptr = item_ring + 2;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nq = (S + 127) / 128, n_hb = nh * B, n_items = nq * n_hb;
+  const int win_heads = max(1, min(n_hb, (2 * static_cast<int>(gridDim.x) + nq - 1) / nq));
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023) { printf("attn_bwd_dq_persist: smem misaligned\n"); __trap(); }
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < R4; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sdp_full[i], 1); mbar_init(&acc_done[i], 1);
+      mbar_init(&ds_full[i], kBwdRowWarps);
+      mbar_init(&it_full[i], 1);
+      mbar_init(&it_empty[i], kBwdRowWarps + 1);
+    }
+    mbar_init(o_stored, 4 * NCH);
+    fence_mbar_init();
+  }
+  if (warp == kBwdRowWarps + 1) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const uint32_t tmem_S = tmem_base, tmem_dP = tmem_base + 128, tmem_dQ = tmem_base + 256;
+
+  struct Item { int q0, h, b, len, len_kv, n_kv; };
+  auto item = [&](int w) {
+    const ItemId id = decode_item(w, nq, n_hb, win_heads, kCausal);   // causal: the last q tile sees every kv tile -> heaviest first
+    Item it;
+    it.q0 = id.tile * 128; it.h = id.hb % nh; it.b = id.hb / nh;
+    it.len = seqlens ? min(seqlens[it.b], S) : S;
+    it.len_kv = seqlens ? it.len : Skv;
+    const int kv_end = kCausal ? min(it.len_kv, it.q0 + 128) : it.len_kv;
+    it.n_kv = (it.q0 < it.len) ? (kv_end + 63) / 64 : 0;
+    return it;
+  };
+  auto next_item = [&](uint32_t n, bool one_lane_arrives) {
+    mbar_wait(&it_full[n & 1], (n >> 1) & 1, 59);
+    const int w = static_cast<int>(item_ring[n & 1]);
+    if (one_lane_arrives) {
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&it_empty[n & 1]);
+    } else {
+      mbar_arrive(&it_empty[n & 1]);
+    }
+    return w;
+  };
+
+  if (warp == kBwdRowWarps) { if (elect_one_sync()) {
+    // ---------------- TMA producer + item scheduler ----------------
+    tma_prefetch_desc(&tq); tma_prefetch_desc(&tk); tma_prefetch_desc(&tv); tma_prefetch_desc(&tdo);
+    uint32_t kg = 0, ic = 0, hold = 0;
+    for (uint32_t n = 0;; ++n) {
+      int w = atomicAdd(item_counter, 1);
+      if (w > n_items) w = n_items;
+      mbar_wait(&it_empty[n & 1], ((n >> 1) & 1) ^ 1, 59);
+      item_ring[n & 1] = static_cast<uint32_t>(w);
+      mbar_arrive(&it_full[n & 1]);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      if (it.n_kv == 0) continue;
+      mbar_wait(q_empty, (ic & 1) ^ 1, 50);
+      mbar_arrive_expect_tx(q_full, 2 * 128 * D * 2);
+      for (int c = 0; c < NCH; ++c) {
+        tma_load_3d(smem + L::oQ + c * 16384, &tq, q_full, it.h * D + c * 64, it.q0, it.b);
+        tma_load_3d(smem + L::oDO + c * 16384, &tdo, q_full, it.h * D + c * 64, it.q0, it.b);
+      }
+      for (int j = 0; j < it.n_kv; ++j) {
+        const uint32_t rs = kg & 3;
+        if ((hold >> rs) & 1u) { mbar_wait(o_stored, (ic - 1) & 1, 50); hold = 0; }
+        mbar_wait(&kv_empty[rs], ((kg >> 2) & 1) ^ 1, 50);
+        mbar_arrive_expect_tx(&kv_full[rs], 2 * 64 * D * 2);
+        for (int c = 0; c < NCH; ++c) {
+          tma_load_3d(smem + L::oK + rs * L::kKV + c * 8192, &tk, &kv_full[rs], it.h * D + c * 64, j * 64, it.b);
+          tma_load_3d(smem + L::oV + rs * L::kKV + c * 8192, &tv, &kv_full[rs], it.h * D + c * 64, j * 64, it.b);
+        }
+        ++kg;
+      }
+      hold |= 1u << ((kg + 3) & 3);   // the stage of the item's last kv tile becomes its dQ staging area
+      ++ic;
+    }
+  } } else if (warp == kBwdRowWarps + 1) { if (elect_one_sync()) {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idesc_acc = make_idesc_bf16(128, D, false, true);
+    const uint32_t sQ = smem_u32(smem + L::oQ), sDO = smem_u32(smem + L::oDO), sK = smem_u32(smem + L::oK),
+                   sV = smem_u32(smem + L::oV);
+    uint32_t g0 = 0, ic = 0;
+    for (uint32_t n = 0;; ++n) {
+      const int w = next_item(n, false);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      if (it.n_kv == 0) continue;
+      auto issue_s = [&](int j) {
+        const uint32_t g = g0 + j, st = g & 1, rs = g & 3;
+        mbar_wait(&kv_full[rs], (g >> 2) & 1, 51);
+        tc_fence_after();
+        mma_tile<D / 16>(tmem_S + st * 64, sQ, false, 16384, sK + rs * L::kKV, false, 8192, idesc_s, false);
+        mma_tile<D / 16>(tmem_dP + st * 64, sDO, false, 16384, sV + rs * L::kKV, false, 8192, idesc_s, false);
+        umma_commit(&sdp_full[st]);
+        if (j == it.n_kv - 1) umma_commit(q_empty);
+      };
+      mbar_wait(q_full, ic & 1, 52);
+      issue_s(0);
+      for (int j = 0; j < it.n_kv; ++j) {
+        if (j + 1 < it.n_kv) issue_s(j + 1);
+        const uint32_t g = g0 + j, st = g & 1, rs = g & 3;
+        mbar_wait(&ds_full[st], (g >> 1) & 1, 53);
+        tc_fence_after();
+        mma_tile_ts<4>(tmem_dQ, tmem_dP + st * 64, 16, sK + rs * L::kKV, true, 8192, idesc_acc, j > 0);   // dQ (+)= dS K_j, dS from TMEM
+        umma_commit(&kv_empty[rs]);
+        umma_commit(&acc_done[st]);
+      }
+      g0 += it.n_kv;
+      ++ic;
+    }
+  } } else if (warp < kBwdRowWarps) {
+    const int wq = warp & 3, part = warp >> 2;
+    const int row = wq * 32 + lane;
+    const uint32_t lane_off = static_cast<uint32_t>(wq * 32) << 16;
+    const bool my_store = part < NCH;
+    uint32_t g0 = 0, ic = 0;
+    for (uint32_t n = 0;; ++n) {
+      const int w = next_item(n, true);
+      if (w >= n_items) break;
+      const Item it = item(w);
+      const int q_row = it.q0 + row;
+      if (it.n_kv == 0) {   // padding rows of a right-padded batch: zeros
+        if (my_store && q_row < S) zero_row64(go.dq + (static_cast<size_t>(it.b) * S + q_row) * go.ld_dq + it.h * D + part * 64);
+        continue;
+      }
+      const size_t sidx = (static_cast<size_t>(it.b) * nh + it.h) * S_pad + min(q_row, S_pad - 1);
+      const float my_lse = lse2[sidx], my_delta = delta[sidx];
+      const bool row_ok = q_row < it.len;
+      for (int j = 0; j < it.n_kv; ++j) {
+        const uint32_t g = g0 + j, st = g & 1;
+        const int kc0 = j * 64 + part * 16;
+        mbar_wait(&sdp_full[st], (g >> 1) & 1, 54);
+        tc_fence_after();
+        uint32_t sv[16], dv[16];
+        tmem_ld16(tmem_S + lane_off + st * 64 + part * 16, sv);
+        tmem_ld16(tmem_dP + lane_off + st * 64 + part * 16, dv);
+        tmem_ld_wait();
+        uint32_t dw[8];
+        const bool full_tile = (it.q0 + 127 < it.len) && (kc0 + 15 < it.len_kv) && (!kCausal || kc0 + 15 <= it.q0);
+        if (full_tile) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - my_lse);
+            const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - my_lse);
+            dw[c] = pack_bf16(p0 * (__uint_as_float(dv[2 * c]) - my_delta), p1 * (__uint_as_float(dv[2 * c + 1]) - my_delta));
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            float de[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int cc = 2 * c + e;
+              const int kvi = kc0 + cc;
+              const bool ok = row_ok && (kvi < it.len_kv) && (!kCausal || kvi <= q_row);
+              const float pe = ok ? exp2f(__uint_as_float(sv[cc]) * scale_log2 - my_lse) : 0.f;
+              de[e] = ok ? pe * (__uint_as_float(dv[cc]) - my_delta) : 0.f;
+            }
+            dw[c] = pack_bf16(de[0], de[1]);
+          }
+        }
+        tmem_st8(tmem_dP + lane_off + st * 64 + part * 16, dw);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ds_full[st]);
+      }
+      // epilogue: chunk `part` of dQ, staged in the ring stage of the item's last kv tile
+      const uint32_t gl = g0 + it.n_kv - 1;
+      mbar_wait(&acc_done[gl & 1], (gl >> 1) & 1, 56);
+      tc_fence_after();
+      if (my_store) {
+        if (ic > 0) mbar_wait(o_stored, (ic - 1) & 1, 57);
+        const uint32_t sA = gl & 3;
+        uint8_t* stage;
+        if constexpr (NCH == 2) stage = smem + (part ? L::oV : L::oK) + sA * L::kKV + wq * 4096;         // 16 KB chunk = one K or V stage
+        else stage = smem + ((wq >> 1) ? L::oV : L::oK) + sA * L::kKV + (wq & 1) * 4096;                 // 16 KB chunk = 8 KB K + 8 KB V stage
+        store_acc_rows64(tmem_dQ + lane_off + part * 64, stage, scale, &tdq, it.h * D + part * 64, it.q0 + wq * 32, it.b, lane);
+        if (lane == 0) mbar_arrive(o_stored);
+      }
+      tc_fence_before();
+      g0 += it.n_kv;
+      ++ic;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kBwdRowWarps + 1) tmem_dealloc<1>(tmem_base, 512);
+}
+
 // ================================================================================================ host
 template <typename K>
 static int set_smem(K kern, int bytes) {
@@ -1271,12 +2178,43 @@ static int launch_fwd_pt(const CUtensorMap& tq, const CUtensorMap& tk, const CUt
   kern<<<grid, kAttnThreads, FwdSmem<D, PT>::kBytes, st>>>(tq, tk, tv, to, lse, seqlens, S, Skv, nh, scale_log2, kv_mask, mask_ld);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
 }
+// DLLM_ATTN_NONPERSIST=1: one CTA per (q tile, head, batch) item (the r02 kernel before persistence) for same-box A/B runs
+static bool attn_nonpersist() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DLLM_ATTN_NONPERSIST");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 template <int D, bool C>
-static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, float* lse,
-                      const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st,
+static int launch_fwd_persist(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, void* out,
+                              long ld_o, float* lse,
+                              const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st,
+                              const uint8_t* kv_mask, int mask_ld) {
+  auto kern = attn_fwd_persist_kernel<D, C>;
+  static bool once = false;
+  if (!once) {
+    if (set_smem(kern, FwdSmem<D, true>::kBytes)) return DLLM_ERR_LAUNCH;
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    once = true;
+  }
+  const long items = static_cast<long>((S + 127) / 128) * nh * B;
+  const long slots = 2L * num_sms();
+  const unsigned grid = static_cast<unsigned>(items < slots ? items : slots);
+  int* counter = tile_counter_slot(st);
+  if (!counter) return DLLM_ERR_LAUNCH;
+  kern<<<grid, kAttnThreads, FwdSmem<D, true>::kBytes, st>>>(tq, tk, tv, to, static_cast<bf16*>(out), ld_o, lse, seqlens, B, S, Skv, nh,
+                                                              scale_log2, kv_mask, mask_ld, counter);
+  return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
+}
+template <int D, bool C>
+static int launch_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& to, void* out, long ld_o,
+                      float* lse, const int* seqlens, int B, int S, int Skv, int nh, float scale_log2, cudaStream_t st,
                       const uint8_t* kv_mask = nullptr, int mask_ld = 0) {
-  return attn_legacy() ? launch_fwd_pt<D, C, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, scale_log2, st, kv_mask, mask_ld)
-                       : launch_fwd_pt<D, C, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, scale_log2, st, kv_mask, mask_ld);
+  if (attn_legacy()) return launch_fwd_pt<D, C, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, scale_log2, st, kv_mask, mask_ld);
+  if (attn_nonpersist()) return launch_fwd_pt<D, C, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, scale_log2, st, kv_mask, mask_ld);
+  return launch_fwd_persist<D, C>(tq, tk, tv, to, out, ld_o, lse, seqlens, B, S, Skv, nh, scale_log2, st, kv_mask, mask_ld);
 }
 
 int attn_fwd(const void* q, const void* k, const void* v, void* out, float* lse, const int* seqlens, int B, int S, int nh,
@@ -1315,10 +2253,10 @@ int attn_fwd_cache_mask(const void* q, const void* k, const void* v, void* out, 
   if ((rc = make_tmap_bsc(&tv, v, B, kv_rows, nh * d, ld_kv, 64))) return rc;
   if ((rc = make_tmap_bsc(&to, out, B, S, nh * d, ld_o, 32))) return rc;
   const float sl2 = scale * kLog2e;
-  if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld)
-                              : launch_fwd<128, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld);
-  return causal ? launch_fwd<64, true>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld)
-                : launch_fwd<64, false>(tq, tk, tv, to, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld);
+  if (d == 128) return causal ? launch_fwd<128, true>(tq, tk, tv, to, out, ld_o, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld)
+                              : launch_fwd<128, false>(tq, tk, tv, to, out, ld_o, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld);
+  return causal ? launch_fwd<64, true>(tq, tk, tv, to, out, ld_o, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld)
+                : launch_fwd<64, false>(tq, tk, tv, to, out, ld_o, lse, seqlens, B, S, Skv, nh, sl2, st, km, mask_ld);
 }
 
 static inline int s_pad(int S) { return (S + 63) / 64 * 64; }
@@ -1329,15 +2267,18 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
                       const CUtensorMap& tv64, const CUtensorMap& tv128, const CUtensorMap& tdo64,
                       const CUtensorMap& tdo128, const CUtensorMap& tdq, const CUtensorMap& tdk, const CUtensorMap& tdv,
                       const bf16* dout, const bf16* out, const float* lse, float* delta, float* lse2, const int* seqlens,
-                      int B, int S, int Skv, int nh, long ld_o, float scale, cudaStream_t st) {
+                      int B, int S, int Skv, int nh, long ld_o, float scale, cudaStream_t st, const BwdOut& go) {
   auto k1 = attn_bwd_dkdv_kernel<D, C>;
   auto k2 = attn_bwd_dq_kernel<D, C>;
   auto k1t = attn_bwd_dkdv_ts_kernel<D, C>;
   auto k2t = attn_bwd_dq_ts_kernel<D, C>;
+  auto k1p = attn_bwd_dkdv_persist_kernel<D, C>;
+  auto k2p = attn_bwd_dq_persist_kernel<D, C>;
   static bool once = false;
   if (!once) {
     if (set_smem(k1, BwdKVSmem<D>::kBytes) || set_smem(k2, BwdQSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
     if (set_smem(k1t, BwdKVTsSmem<D>::kBytes) || set_smem(k2t, BwdQTsSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
+    if (set_smem(k1p, BwdKVTsSmem<D>::kBytes) || set_smem(k2p, BwdQTsSmem<D>::kBytes)) return DLLM_ERR_LAUNCH;
     once = true;
   }
   const int Sp = s_pad(S);
@@ -1350,6 +2291,16 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
                                                             scale, scale * kLog2e);
     k2<<<grid_q, kBwdThreads, BwdQSmem<D>::kBytes, st>>>(tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, S, Skv, Sp, nh, scale,
                                                           scale * kLog2e);
+  } else if (!attn_nonpersist()) {
+    const long items_kv = static_cast<long>(grid_kv.x) * nh * B, items_q = static_cast<long>(grid_q.x) * nh * B;
+    const long sms = num_sms();
+    int* c1 = tile_counter_slot(st);
+    int* c2 = tile_counter_slot(st);
+    if (!c1 || !c2) return DLLM_ERR_LAUNCH;
+    k1p<<<static_cast<unsigned>(items_kv < sms ? items_kv : sms), kBwdTsThreads, BwdKVTsSmem<D>::kBytes, st>>>(
+        tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, go, B, S, Skv, Sp, nh, scale, scale * kLog2e, c1);
+    k2p<<<static_cast<unsigned>(items_q < sms ? items_q : sms), kBwdTsThreads, BwdQTsSmem<D>::kBytes, st>>>(
+        tq128, tk64, tv64, tdo128, tdq, lse2, delta, seqlens, go, B, S, Skv, Sp, nh, scale, scale * kLog2e, c2);
   } else {
     k1t<<<grid_kv, kBwdTsThreads, BwdKVTsSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Skv, Sp,
                                                                  nh, scale, scale * kLog2e);
@@ -1389,9 +2340,10 @@ int attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, c
   if ((rc = make_tmap_bsc(&tdq, dq, B, S, C, ld_dq, 32))) return rc;
   if ((rc = make_tmap_bsc(&tdk, dk, B, Skv, C, ld_dkv, 32))) return rc;
   if ((rc = make_tmap_bsc(&tdv, dv, B, Skv, C, ld_dkv, 32))) return rc;
+  const BwdOut go{static_cast<bf16*>(dq), static_cast<bf16*>(dk), static_cast<bf16*>(dv), ld_dq, ld_dkv};
 #define DLLM_BWD(DD, CC)                                                                                             \
   return launch_bwd<DD, CC>(tq64, tq128, tk64, tk128, tv64, tv128, tdo64, tdo128, tdq, tdk, tdv, (const bf16*)dout,     \
-                            (const bf16*)out, lse, delta, lse2, seqlens, B, S, Skv, nh, ld_o, scale, st)
+                            (const bf16*)out, lse, delta, lse2, seqlens, B, S, Skv, nh, ld_o, scale, st, go)
   if (d == 128) { if (causal) DLLM_BWD(128, true); else DLLM_BWD(128, false); }
   if (causal) DLLM_BWD(64, true); else DLLM_BWD(64, false);
 #undef DLLM_BWD
@@ -1402,5 +2354,8 @@ int attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, c
 #ifdef DLLM_ATTN_TRACE
 extern "C" int dllm_attn_trace_read(long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, dllm::g_attn_trace, sizeof(long long) * n);
+}
+extern "C" int dllm_attn_cta_log_read(long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, dllm::g_attn_cta_log, sizeof(long long) * n);
 }
 #endif

@@ -547,7 +547,7 @@ int num_sms() {
 }
 
 // per-device ring of tile counters for the dynamic scheduler (one-time 4 KiB scratch; each launch zeroes its slot in stream order)
-static int* tile_counter_slot(cudaStream_t stream) {
+int* tile_counter_slot(cudaStream_t stream) {
   constexpr int kSlots = 1024, kMaxDev = 16;
   static int* base[kMaxDev] = {nullptr};
   static unsigned next[kMaxDev] = {0};

@@ -15,6 +15,8 @@
 namespace dllm {
 
 int num_sms();
+// a zeroed int in device memory for one launch's dynamic work scheduler (zeroed in stream order; ring of 1024 slots per device)
+int* tile_counter_slot(cudaStream_t stream);
 void set_reserved_sms(int n);
 int reserved_sms();
 int make_tmap_2d(CUtensorMap* map, const void* ptr, int elem_bytes, uint64_t rows, uint64_t cols, uint64_t ld,

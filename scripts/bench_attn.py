@@ -2,7 +2,8 @@ import sys, torch
 sys.path.insert(0, ".")
 from dreamllm_b200 import ops
 BF = torch.bfloat16
-B, S, nh, d = 8, 2048, 32, 128
+import os
+B, S, nh, d = int(os.environ.get("ATTN_B", 8)), 2048, 32, 128
 g = torch.Generator(device="cuda").manual_seed(0)
 qkv = torch.randn(B, S, 3, nh, d, device="cuda", generator=g).to(BF)
 q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
