@@ -661,79 +661,116 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
         tmem_ld_wait();
         const int kv0 = j * 64;
         const bool need_mask = (kCausal && kv0 + 63 > it.q0 + warp * 32 + coff) || (kv0 + 64 > it.kv_len) || (kv_mask != nullptr);
-        float mx = -INFINITY;
-        if (need_mask) {
-          uint32_t mw[16];
-          if (kv_mask != nullptr) {
-            const uint4* mp = reinterpret_cast<const uint4*>(kv_mask + static_cast<size_t>(it.b) * mask_ld + kv0);
+        // Fast path (no masking, not the item's first tile): the exponentials do not wait for this tile's row max.  They are taken against
+        // the running reference m_run — exactly what the lazy rescale below would use unless the max grew by more than 2^8 — while the
+        // same pass tracks the max; only if some row's max did grow that much is the tile redone on the slow path (S is still in TMEM:
+        // P has not been stored yet).  Removes the separate max pass (~240 clk of dependent FMNMX per tile) from every warp's chain.
+        bool redo = need_mask || j == 0;
+        if (!redo) {
+          const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+          float ls0 = 0.f, ls1 = 0.f, mq[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          uint32_t pw[32];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const uint4 t = __ldg(mp + i);
-              mw[4 * i] = t.x; mw[4 * i + 1] = t.y; mw[4 * i + 2] = t.z; mw[4 * i + 3] = t.w;
+          for (int c = 0; c < 32; ++c) {
+            const float s0 = __uint_as_float(sv[2 * c]), s1 = __uint_as_float(sv[2 * c + 1]);
+            const float p0 = exp2f(s0 * scale_log2 - m_use);
+            const float p1 = exp2f(s1 * scale_log2 - m_use);
+            mq[c & 3] = fmaxf(mq[c & 3], fmaxf(s0, s1));
+            ls0 += p0;
+            ls1 += p1;
+            pw[c] = pack_bf16(p0, p1);
+          }
+          const float mxf = fmaxf(fmaxf(mq[0], mq[1]), fmaxf(mq[2], mq[3]));
+          const bool grew = (fmaxf(m_run, mxf * scale_log2) - m_run) > 8.0f;
+          redo = __any_sync(0xffffffffu, grew);
+          if (!redo) {
+            tmem_st32(tmem_S + lane_off + sb * 64, pw);
+            tmem_st_wait();
+            l_run += ls0 + ls1;
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[sb]);
+          } else {
+            tmem_ld32(tmem_S + lane_off + sb * 64, sv);
+            tmem_ld32(tmem_S + lane_off + sb * 64 + 32, sv + 32);
+            tmem_ld_wait();
+          }
+        }
+        if (redo) {
+          float mx = -INFINITY;
+          if (need_mask) {
+            uint32_t mw[16];
+            if (kv_mask != nullptr) {
+              const uint4* mp = reinterpret_cast<const uint4*>(kv_mask + static_cast<size_t>(it.b) * mask_ld + kv0);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const uint4 t = __ldg(mp + i);
+                mw[4 * i] = t.x; mw[4 * i + 1] = t.y; mw[4 * i + 2] = t.z; mw[4 * i + 3] = t.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) mw[i] = 0x01010101u;
+            }
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+              const int kvi = kv0 + c;
+              const bool ok = (kvi < it.kv_len) && (!kCausal || kvi <= q_row + coff) && (((mw[c >> 2] >> (8 * (c & 3))) & 0xffu) != 0u);
+              const float sc = ok ? __uint_as_float(sv[c]) : -INFINITY;
+              sv[c] = __float_as_uint(sc);
+              mx = fmaxf(mx, sc);
             }
           } else {
+            float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) mw[i] = 0x01010101u;
-          }
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const int kvi = kv0 + c;
-            const bool ok = (kvi < it.kv_len) && (!kCausal || kvi <= q_row + coff) && (((mw[c >> 2] >> (8 * (c & 3))) & 0xffu) != 0u);
-            const float sc = ok ? __uint_as_float(sv[c]) : -INFINITY;
-            sv[c] = __float_as_uint(sc);
-            mx = fmaxf(mx, sc);
-          }
-        } else {
-          float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
-#pragma unroll
-          for (int c = 0; c < 64; c += 4) {
-            m0 = fmaxf(m0, __uint_as_float(sv[c]));
-            m1 = fmaxf(m1, __uint_as_float(sv[c + 1]));
-            m2 = fmaxf(m2, __uint_as_float(sv[c + 2]));
-            m3 = fmaxf(m3, __uint_as_float(sv[c + 3]));
-          }
-          mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        }
-        const float m_new = fmaxf(m_run, mx * scale_log2);
-        const bool need = (m_new - m_run) > 8.0f;     // lazy rescale (see attn_fwd_kernel)
-        const bool any = __any_sync(0xffffffffu, need);
-        if (any) {
-          const float m_tgt = (m_new == -INFINITY) ? m_run : m_new;
-          const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_tgt);
-          if (j > 0) {
-            mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 17);   // O quiescent
-            tc_fence_after();
-#pragma unroll 1
-            for (int c = 0; c < D / 32; ++c) {
-              uint32_t o[32];
-              tmem_ld32(tmem_O + lane_off + c * 32, o);
-              tmem_ld_wait();
-#pragma unroll
-              for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
-              tmem_st32(tmem_O + lane_off + c * 32, o);
+            for (int c = 0; c < 64; c += 4) {
+              m0 = fmaxf(m0, __uint_as_float(sv[c]));
+              m1 = fmaxf(m1, __uint_as_float(sv[c + 1]));
+              m2 = fmaxf(m2, __uint_as_float(sv[c + 2]));
+              m3 = fmaxf(m3, __uint_as_float(sv[c + 3]));
             }
-            tmem_st_wait();
+            mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           }
-          l_run *= alpha;
-          m_run = m_tgt;
-        }
-        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-        float ls0 = 0.f, ls1 = 0.f;
-        uint32_t pw[32];
+          const float m_new = fmaxf(m_run, mx * scale_log2);
+          const bool need = (m_new - m_run) > 8.0f;     // lazy rescale (see attn_fwd_kernel)
+          const bool any = __any_sync(0xffffffffu, need);
+          if (any) {
+            const float m_tgt = (m_new == -INFINITY) ? m_run : m_new;
+            const float alpha = (m_run == -INFINITY) ? 0.f : exp2f(m_run - m_tgt);
+            if (j > 0) {
+              mbar_wait(&pv_done[(g - 1) & 1], ((g - 1) >> 1) & 1, 17);   // O quiescent
+              tc_fence_after();
+#pragma unroll 1
+              for (int c = 0; c < D / 32; ++c) {
+                uint32_t o[32];
+                tmem_ld32(tmem_O + lane_off + c * 32, o);
+                tmem_ld_wait();
 #pragma unroll
-        for (int c = 0; c < 32; ++c) {
-          const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - m_use);
-          const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - m_use);
-          ls0 += p0;
-          ls1 += p1;
-          pw[c] = pack_bf16(p0, p1);
+                for (int e = 0; e < 32; ++e) o[e] = __float_as_uint(__uint_as_float(o[e]) * alpha);
+                tmem_st32(tmem_O + lane_off + c * 32, o);
+              }
+              tmem_st_wait();
+            }
+            l_run *= alpha;
+            m_run = m_tgt;
+          }
+          const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+          float ls0 = 0.f, ls1 = 0.f;
+          uint32_t pw[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float p0 = exp2f(__uint_as_float(sv[2 * c]) * scale_log2 - m_use);
+            const float p1 = exp2f(__uint_as_float(sv[2 * c + 1]) * scale_log2 - m_use);
+            ls0 += p0;
+            ls1 += p1;
+            pw[c] = pack_bf16(p0, p1);
+          }
+          tmem_st32(tmem_S + lane_off + sb * 64, pw);
+          tmem_st_wait();
+          l_run += ls0 + ls1;
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[sb]);
         }
-        tmem_st32(tmem_S + lane_off + sb * 64, pw);
-        tmem_st_wait();
-        l_run += ls0 + ls1;
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[sb]);
       }
       const uint32_t gl = g0 + it.n_kv - 1;
       if (warp == 0) ATTN_TRACE(tr_item, 2);
@@ -784,46 +821,69 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
 }
 
 // ================================================================================================ backward prep
-// delta[b,h,s] = sum_d dO*O ; lse2 = lse*log2(e).  One warp per (token, head).
+// delta[b,h,s] = sum_d dO*O ; lse2 = lse*log2(e).
 // Output layout is padded to [B, nh, S_pad] (S_pad = S rounded up to 64, pad entries = 0) so the backward kernels can
-// fetch a q tile's 64 values with aligned float4 loads.
+// fetch a q tile's 64 values with aligned float4 loads / one 256-byte bulk copy.
+// One 16-byte load of O and of dO per thread and row: a (token, head) row is D / 8 lanes, four rows per lane group are in flight before
+// the first dot product.  (r01 / early r02: one warp per row, 8 bytes per lane and a 5-step shuffle per 512 bytes — 107 us = 2.5 TB/s
+// on the C2 shape, 10 % of the whole backward; profiles/r02u_attn_bwd_kernels.md.)
 template <int D>
-__global__ void attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out, const float* __restrict__ lse,
-                                     float* __restrict__ delta, float* __restrict__ lse2, int B, int S, int S_pad, int nh,
-                                     long ld_o) {
-  const long gw = (static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const long total = static_cast<long>(B) * S_pad * nh;
-  if (gw >= total) return;
-  const int h = static_cast<int>(gw % nh);
-  const long tokp = gw / nh;
-  const int s = static_cast<int>(tokp % S_pad);
-  const int b = static_cast<int>(tokp / S_pad);
-  if (s >= S) {
-    if (lane == 0) {
-      const size_t idxp = (static_cast<size_t>(b) * nh + h) * S_pad + s;
+__global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
+                                                            const float* __restrict__ lse, float* __restrict__ delta,
+                                                            float* __restrict__ lse2, int B, int S, int S_pad, int nh, long ld_o) {
+  constexpr int GS = D / 8;        // lanes per row
+  constexpr int PPW = 32 / GS;     // rows per warp pass
+  constexpr int U = 4;             // passes in flight
+  const int lane = threadIdx.x & 31, sub = lane / GS, li = lane % GS;
+  const long gtid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long total = static_cast<long>(B) * S * nh;
+  const long base = (gtid >> 5) * (PPW * U);
+  uint4 a[U], g[U];
+  long row[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    row[u] = base + u * PPW + sub;
+    a[u] = g[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (row[u] < total) {
+      const long tok = row[u] / nh;
+      const int h = static_cast<int>(row[u] - tok * nh);
+      const size_t off = static_cast<size_t>(tok) * ld_o + h * D + li * 8;
+      a[u] = __ldg(reinterpret_cast<const uint4*>(out + off));
+      g[u] = __ldg(reinterpret_cast<const uint4*>(dout + off));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a[u]);
+    const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g[u]);
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 x = __bfloat1622float2(pa[e]), y = __bfloat1622float2(pg[e]);
+      acc += x.x * y.x + x.y * y.y;
+    }
+#pragma unroll
+    for (int o = GS / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (li == 0 && row[u] < total) {
+      const long tok = row[u] / nh;
+      const int h = static_cast<int>(row[u] - tok * nh);
+      const int b = static_cast<int>(tok / S), sq = static_cast<int>(tok - static_cast<long>(b) * S);
+      const size_t idx = (static_cast<size_t>(b) * nh + h) * S + sq;
+      const size_t idxp = (static_cast<size_t>(b) * nh + h) * S_pad + sq;
+      delta[idxp] = acc;
+      lse2[idxp] = lse[idx] * kLog2e;
+    }
+  }
+  // pad entries s in [S, S_pad)
+  const int padw = S_pad - S;
+  if (padw > 0) {
+    const long npad = static_cast<long>(B) * nh * padw;
+    for (long i = gtid; i < npad; i += static_cast<long>(gridDim.x) * blockDim.x) {
+      const long bh = i / padw;
+      const size_t idxp = static_cast<size_t>(bh) * S_pad + S + (i - bh * padw);
       delta[idxp] = 0.f;
       lse2[idxp] = 0.f;
     }
-    return;
-  }
-  const long tok = static_cast<long>(b) * S + s;
-  const bf16* po = out + tok * ld_o + h * D;
-  const bf16* pd = dout + tok * ld_o + h * D;
-  float acc = 0.f;
-  constexpr int EPL = D / 32;  // elements per lane (4 or 2)
-#pragma unroll
-  for (int e = 0; e < EPL; e += 2) {
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(po + lane * EPL + e));
-    const float2 g = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(pd + lane * EPL + e));
-    acc += a.x * g.x + a.y * g.y;
-  }
-  acc = warp_sum(acc);
-  if (lane == 0) {
-    const size_t idx = (static_cast<size_t>(b) * nh + h) * S + s;
-    const size_t idxp = (static_cast<size_t>(b) * nh + h) * S_pad + s;
-    delta[idxp] = acc;
-    lse2[idxp] = lse[idx] * kLog2e;
   }
 }
 
@@ -1624,9 +1684,22 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
 //     prefetches the next item's first ring tiles while the current item's last iterations and epilogue run;
 //   * the stationary operands (K, V resp. Q, dO) are refilled as soon as the item's last S / dP tile-GEMMs retire (`stat_empty`);
 //   * the accumulators leave through the operand ring: the epilogue stages bf16 tiles in the ring stage(s) the item used last (free once
-//     its last accumulate-MMAs retire), and the producer refills those stages only after `o_stored` says the bulk stores have read them;
+//     its last accumulate-MMAs retire), and the producer refills those stages only after the `stored_cnt` counter says the bulk stores have read them;
 //   * the next item's first accumulate-MMA (accumulate = 0) needs P^T/dS^T of that item from all 16 row warps, which produce it only
 //     after their part of the epilogue has drained the accumulators — no extra barrier.
+// Monotonic "stores done" counter in shared memory (release add by the storing warps, acquire poll by the waiters).  An mbarrier would
+// do for a waiter that observes every phase, but the producer only looks when it is about to refill a staging stage, and with short items
+// (two q tiles: the whole item fits the ring) it runs two or more items ahead of the epilogues — a parity wait then aliases and lets it
+// overwrite staging that has not been stored yet (seen as wrong dK / dV tiles at window boundaries; profiles/r02x_attn_bwd_race.md).
+__device__ __forceinline__ void smem_count_add_release(uint32_t* cnt) {
+  asm volatile("red.release.cta.shared::cta.add.u32 [%0], 1;" ::"r"(smem_u32(cnt)) : "memory");
+}
+__device__ __forceinline__ void smem_count_wait_acquire(const uint32_t* cnt, uint32_t target) {
+  uint32_t v;
+  do {
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(cnt)) : "memory");
+  } while (static_cast<int32_t>(v - target) < 0);
+}
 struct BwdOut {
   bf16* dq; bf16* dk; bf16* dv;
   long ld_dq, ld_dkv;
@@ -1697,11 +1770,11 @@ attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __gri
   uint64_t* sdp_full = qdo_empty + R4;            // [2]  TMEM double buffer: g & 1, phase (g >> 1) & 1
   uint64_t* pds_full = sdp_full + 2;              // [2]
   uint64_t* acc_done = pds_full + 2;              // [2]
-  uint64_t* o_stored = acc_done + 2;              // the item's dK / dV staging (two ring stages) has been read by the bulk stores
-  uint64_t* it_full = o_stored + 1;               // [2]  item ring
+  uint64_t* it_full = acc_done + 2;               // [2]  item ring
   uint64_t* it_empty = it_full + 2;               // [2]
   uint32_t* item_ring = reinterpret_cast<uint32_t*>(it_empty + 2);
   uint32_t* tmem_ptr = item_ring + 2;
+  uint32_t* stored_cnt = tmem_ptr + 1;            // storing warps whose bulk stores have read their staging (4 * kJobs per non-empty item)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kJobs = 2 * NCH;                  // 64-column chunk jobs {dV, dK} x chunks, one per `part`
@@ -1718,7 +1791,7 @@ attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __gri
       mbar_init(&it_full[i], 1);
       mbar_init(&it_empty[i], kBwdRowWarps + 1);  // MMA thread + one lane of every row warp
     }
-    mbar_init(o_stored, 4 * kJobs);
+    *stored_cnt = 0;
     fence_mbar_init();
   }
   if (warp == kBwdRowWarps + 1) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
@@ -1776,7 +1849,7 @@ attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __gri
       for (int t = 0; t < it.n_it; ++t) {
         const uint32_t rs = qg & 3;
         const int qr0 = (it.i_begin + t) * 64;
-        if ((hold >> rs) & 1u) { mbar_wait(o_stored, (ic - 1) & 1, 40); hold = 0; }   // (ic >= 1 whenever hold != 0)
+        if ((hold >> rs) & 1u) { smem_count_wait_acquire(stored_cnt, 4u * kJobs * ic); hold = 0; }   // every earlier item is stored
         mbar_wait(&qdo_empty[rs], ((qg >> 2) & 1) ^ 1, 40);
         mbar_arrive_expect_tx(&qdo_full[rs], 2 * 64 * D * 2 + 512);
         for (int c = 0; c < NCH; ++c) {
@@ -1905,7 +1978,7 @@ attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __gri
       mbar_wait(&acc_done[gl & 1], (gl >> 1) & 1, 46);
       tc_fence_after();
       if (my_store) {
-        if (ic > 0) mbar_wait(o_stored, (ic - 1) & 1, 47);   // every warp's bulk store of the previous item has read its staging
+        smem_count_wait_acquire(stored_cnt, 4u * kJobs * ic);   // every warp's bulk stores of the earlier items have read their staging
         const uint32_t sA = gl & 3, sB = (gl + 3) & 3;
         uint8_t* stage;
         if constexpr (NCH == 2) {   // four 16 KB chunks: {Q part, dO part} of stage sA, then of stage sB
@@ -1915,7 +1988,7 @@ attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __gri
         }
         store_acc_rows64((acc == 0 ? tmem_dV : tmem_dK) + lane_off + ch * 64, stage, acc == 0 ? 1.f : scale, acc == 0 ? &tdv : &tdk,
                          it.h * D + ch * 64, it.kv0 + wq * 32, it.b, lane);
-        if (lane == 0) mbar_arrive(o_stored);
+        if (lane == 0) smem_count_add_release(stored_cnt);
       }
       tc_fence_before();
       g0 += it.n_it;
@@ -1946,11 +2019,11 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_
   uint64_t* sdp_full = kv_empty + R4;           // [2]
   uint64_t* ds_full = sdp_full + 2;             // [2]
   uint64_t* acc_done = ds_full + 2;             // [2]
-  uint64_t* o_stored = acc_done + 2;            // the item's dQ staging (one ring stage) has been read by the bulk stores
-  uint64_t* it_full = o_stored + 1;             // [2]
+  uint64_t* it_full = acc_done + 2;             // [2]
   uint64_t* it_empty = it_full + 2;             // [2]
   uint32_t* item_ring = reinterpret_cast<uint32_t*>(it_empty + 2);
   uint32_t* tmem_ptr = item_ring + 2;
+  uint32_t* stored_cnt = tmem_ptr + 1;          // storing warps whose bulk store has read its staging (4 * NCH per non-empty item)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = (S + 127) / 128, n_hb = nh * B, n_items = nq * n_hb;
@@ -1966,7 +2039,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_
       mbar_init(&it_full[i], 1);
       mbar_init(&it_empty[i], kBwdRowWarps + 1);
     }
-    mbar_init(o_stored, 4 * NCH);
+    *stored_cnt = 0;
     fence_mbar_init();
   }
   if (warp == kBwdRowWarps + 1) { tmem_alloc<1>(tmem_ptr, 512); tmem_relinquish<1>(); }
@@ -2020,7 +2093,7 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_
       }
       for (int j = 0; j < it.n_kv; ++j) {
         const uint32_t rs = kg & 3;
-        if ((hold >> rs) & 1u) { mbar_wait(o_stored, (ic - 1) & 1, 50); hold = 0; }
+        if ((hold >> rs) & 1u) { smem_count_wait_acquire(stored_cnt, 4u * NCH * ic); hold = 0; }
         mbar_wait(&kv_empty[rs], ((kg >> 2) & 1) ^ 1, 50);
         mbar_arrive_expect_tx(&kv_full[rs], 2 * 64 * D * 2);
         for (int c = 0; c < NCH; ++c) {
@@ -2129,13 +2202,13 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_
       mbar_wait(&acc_done[gl & 1], (gl >> 1) & 1, 56);
       tc_fence_after();
       if (my_store) {
-        if (ic > 0) mbar_wait(o_stored, (ic - 1) & 1, 57);
+        smem_count_wait_acquire(stored_cnt, 4u * NCH * ic);
         const uint32_t sA = gl & 3;
         uint8_t* stage;
         if constexpr (NCH == 2) stage = smem + (part ? L::oV : L::oK) + sA * L::kKV + wq * 4096;         // 16 KB chunk = one K or V stage
         else stage = smem + ((wq >> 1) ? L::oV : L::oK) + sA * L::kKV + (wq & 1) * 4096;                 // 16 KB chunk = 8 KB K + 8 KB V stage
         store_acc_rows64(tmem_dQ + lane_off + part * 64, stage, scale, &tdq, it.h * D + part * 64, it.q0 + wq * 32, it.b, lane);
-        if (lane == 0) mbar_arrive(o_stored);
+        if (lane == 0) smem_count_add_release(stored_cnt);
       }
       tc_fence_before();
       g0 += it.n_kv;
@@ -2282,9 +2355,10 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
     once = true;
   }
   const int Sp = s_pad(S);
-  const long warps = static_cast<long>(B) * Sp * nh;
-  attn_bwd_prep_kernel<D><<<static_cast<unsigned>((warps * 32 + 255) / 256), 256, 0, st>>>(dout, out, lse, delta, lse2, B, S,
-                                                                                           Sp, nh, ld_o);
+  const long rows_per_block = 8L * (32 / (D / 8)) * 4;   // 8 warps x rows per warp pass x passes in flight (attn_bwd_prep_kernel)
+  const long prep_rows = static_cast<long>(B) * S * nh;
+  attn_bwd_prep_kernel<D><<<static_cast<unsigned>((prep_rows + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(
+      dout, out, lse, delta, lse2, B, S, Sp, nh, ld_o);
   dim3 grid_kv((Skv + 127) / 128, nh, B), grid_q((S + 127) / 128, nh, B);
   if (attn_legacy()) {
     k1<<<grid_kv, kBwdThreads, BwdKVSmem<D>::kBytes, st>>>(tq64, tk128, tv128, tdo64, tdk, tdv, lse2, delta, seqlens, S, Skv, Sp, nh,
