@@ -6,7 +6,8 @@ sanitizer pass; VERDICT r1 item 8 asks for racecheck + memcheck over the pipelin
 
 Shapes are tiny (the tools slow kernels down 10-100x) but cover: 1-CTA and 2-CTA GEMM in all four operand layouts, both N-tile widths,
 fused epilogues, the implicit-GEMM conv, attention forward / backward (causal d=128 with padding, non-causal d=64, cross-attention,
-kv-cache with a key mask), and the GroupNorm / LayerNorm / GEGLU kernels."""
+kv-cache with a key mask; the persistent kernels with several items per CTA), split-K GEMM / conv, and the GroupNorm / LayerNorm /
+GEGLU kernels."""
 import sys
 
 import torch
@@ -31,6 +32,9 @@ ops.linear(x, r(256, 192), bias=r(256), act=ops.ACT_QUICK_GELU)
 xi = r(2, 16, 16, 64)
 ops.conv3x3(xi, r(128, 9 * 64), bias=r(128), rowbias=r(2, 128), residual=r(2, 16, 16, 128))
 ops.conv3x3(xi, r(320, 9 * 64))
+xs = r(4, 8, 8, 640)                      # split-K paths (small M: fp32 K-slice partials + reduce)
+ops.conv3x3(xs, r(320, 9 * 640), bias=r(320), rowbias=r(4, 320), residual=r(4, 8, 8, 320))
+ops.linear(r(256, 2048), r(1280, 2048), bias=r(1280), act=ops.ACT_GELU)
 
 # attention: causal d=128, right-padded batch, fwd + bwd
 B, S, nh, d = 2, 200, 2, 128
@@ -56,6 +60,19 @@ mask = torch.ones(2, 128, device="cuda", dtype=torch.uint8)
 mask[1, :9] = 0
 ops.attn_fwd_cache(r(2, 1, nh, d), kc, vc, 70, causal=True, kv_mask=mask)
 ops.attn_fwd_cache(r(2, 40, nh, d), kc, vc, 70, causal=True, kv_mask=mask)
+
+# persistent attention kernels with several items per CTA (cross-item prefetch, accumulator staging in the operand ring, item scheduler):
+# more (q tile, head, batch) items than resident CTAs
+B, S, nh, d = 3, 320, 128, 64
+qkv = r(B, S, 3, nh, d)
+o, lse = ops.attn_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=False)
+dqkv = torch.empty_like(qkv)
+ops.attn_bwd(r(B, S, nh * d), qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, lse, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], causal=False)
+B, S, nh, d = 2, 384, 80, 128
+qkv = r(B, S, 3, nh, d)
+o, lse = ops.attn_fwd(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], causal=True)
+dqkv = torch.empty_like(qkv)
+ops.attn_bwd(r(B, S, nh * d), qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], o, lse, dqkv[:, :, 0], dqkv[:, :, 1], dqkv[:, :, 2], causal=True)
 
 # HBM-bound kernels with reductions
 xg = r(2, 16 * 16, 320)
