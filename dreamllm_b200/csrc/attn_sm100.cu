@@ -824,66 +824,65 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
 // delta[b,h,s] = sum_d dO*O ; lse2 = lse*log2(e).
 // Output layout is padded to [B, nh, S_pad] (S_pad = S rounded up to 64, pad entries = 0) so the backward kernels can
 // fetch a q tile's 64 values with aligned float4 loads / one 256-byte bulk copy.
-// One 16-byte load of O and of dO per thread and row: a (token, head) row is D / 8 lanes, four rows per lane group are in flight before
-// the first dot product.  (r01 / early r02: one warp per row, 8 bytes per lane and a 5-step shuffle per 512 bytes — 107 us = 2.5 TB/s
-// on the C2 shape, 10 % of the whole backward; profiles/r02u_attn_bwd_kernels.md.)
+// A block owns 32 consecutive tokens of one batch entry and all heads: rows (token, head) are read 16 bytes per thread with four row
+// groups in flight (contiguous: heads are adjacent in memory), the dot products are parked in shared memory as [head][token], and the
+// outputs leave as 128-byte runs along the token axis.  (First version: one warp per row, 8 bytes per lane, and every result written /
+// every lse read as a lone 4-byte access 8 KB from its neighbour's — three 32-byte sectors per 256-byte row, as much sector traffic as
+// the payload: 107-117 us under ncu on the C2 shape = 2.4 TB/s, 10 % of the whole backward; profiles/r02u_attn_bwd_kernels.md.)
 template <int D>
 __global__ void __launch_bounds__(256) attn_bwd_prep_kernel(const bf16* __restrict__ dout, const bf16* __restrict__ out,
                                                             const float* __restrict__ lse, float* __restrict__ delta,
                                                             float* __restrict__ lse2, int B, int S, int S_pad, int nh, long ld_o) {
-  constexpr int GS = D / 8;        // lanes per row
-  constexpr int PPW = 32 / GS;     // rows per warp pass
-  constexpr int U = 4;             // passes in flight
-  const int lane = threadIdx.x & 31, sub = lane / GS, li = lane % GS;
-  const long gtid = static_cast<long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  const long total = static_cast<long>(B) * S * nh;
-  const long base = (gtid >> 5) * (PPW * U);
-  uint4 a[U], g[U];
-  long row[U];
+  constexpr int GS = D / 8;          // lanes per row
+  constexpr int RPP = 256 / GS;      // rows per block pass
+  constexpr int U = 4;               // passes in flight
+  constexpr int TOK = 32;
+  extern __shared__ float sacc[];    // [nh][TOK]
+  const int tiles_per_b = S_pad / TOK;
+  const int b = blockIdx.x / tiles_per_b, s0 = (blockIdx.x - b * tiles_per_b) * TOK;
+  const int ntok = max(0, min(TOK, S - s0));
+  const int nrows = ntok * nh;
+  const int sub = threadIdx.x / GS, li = threadIdx.x % GS;
+  const size_t base = (static_cast<size_t>(b) * S + s0) * ld_o;
+  for (int r0 = 0; r0 < nrows; r0 += RPP * U) {
+    uint4 a[U], g[U];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    row[u] = base + u * PPW + sub;
-    a[u] = g[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (row[u] < total) {
-      const long tok = row[u] / nh;
-      const int h = static_cast<int>(row[u] - tok * nh);
-      const size_t off = static_cast<size_t>(tok) * ld_o + h * D + li * 8;
-      a[u] = __ldg(reinterpret_cast<const uint4*>(out + off));
-      g[u] = __ldg(reinterpret_cast<const uint4*>(dout + off));
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u * RPP + sub;
+      a[u] = g[u] = make_uint4(0u, 0u, 0u, 0u);
+      if (r < nrows) {
+        const int tok = r / nh, h = r - tok * nh;
+        const size_t off = base + static_cast<size_t>(tok) * ld_o + h * D + li * 8;
+        a[u] = __ldg(reinterpret_cast<const uint4*>(out + off));
+        g[u] = __ldg(reinterpret_cast<const uint4*>(dout + off));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int r = r0 + u * RPP + sub;
+      const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a[u]);
+      const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g[u]);
+      float acc = 0.f;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 x = __bfloat1622float2(pa[e]), y = __bfloat1622float2(pg[e]);
+        acc += x.x * y.x + x.y * y.y;
+      }
+#pragma unroll
+      for (int o = GS / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (li == 0 && r < nrows) {
+        const int tok = r / nh, h = r - tok * nh;
+        sacc[h * TOK + tok] = acc;
+      }
     }
   }
-#pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const __nv_bfloat162* pa = reinterpret_cast<const __nv_bfloat162*>(&a[u]);
-    const __nv_bfloat162* pg = reinterpret_cast<const __nv_bfloat162*>(&g[u]);
-    float acc = 0.f;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 x = __bfloat1622float2(pa[e]), y = __bfloat1622float2(pg[e]);
-      acc += x.x * y.x + x.y * y.y;
-    }
-#pragma unroll
-    for (int o = GS / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (li == 0 && row[u] < total) {
-      const long tok = row[u] / nh;
-      const int h = static_cast<int>(row[u] - tok * nh);
-      const int b = static_cast<int>(tok / S), sq = static_cast<int>(tok - static_cast<long>(b) * S);
-      const size_t idx = (static_cast<size_t>(b) * nh + h) * S + sq;
-      const size_t idxp = (static_cast<size_t>(b) * nh + h) * S_pad + sq;
-      delta[idxp] = acc;
-      lse2[idxp] = lse[idx] * kLog2e;
-    }
-  }
-  // pad entries s in [S, S_pad)
-  const int padw = S_pad - S;
-  if (padw > 0) {
-    const long npad = static_cast<long>(B) * nh * padw;
-    for (long i = gtid; i < npad; i += static_cast<long>(gridDim.x) * blockDim.x) {
-      const long bh = i / padw;
-      const size_t idxp = static_cast<size_t>(bh) * S_pad + S + (i - bh * padw);
-      delta[idxp] = 0.f;
-      lse2[idxp] = 0.f;
-    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nh * TOK; i += 256) {
+    const int h = i / TOK, tk = i - h * TOK, sq = s0 + tk;
+    const size_t idxp = (static_cast<size_t>(b) * nh + h) * S_pad + sq;
+    const bool real = sq < S;
+    delta[idxp] = real ? sacc[i] : 0.f;
+    lse2[idxp] = real ? lse[(static_cast<size_t>(b) * nh + h) * S + sq] * kLog2e : 0.f;
   }
 }
 
@@ -2355,9 +2354,8 @@ static int launch_bwd(const CUtensorMap& tq64, const CUtensorMap& tq128, const C
     once = true;
   }
   const int Sp = s_pad(S);
-  const long rows_per_block = 8L * (32 / (D / 8)) * 4;   // 8 warps x rows per warp pass x passes in flight (attn_bwd_prep_kernel)
-  const long prep_rows = static_cast<long>(B) * S * nh;
-  attn_bwd_prep_kernel<D><<<static_cast<unsigned>((prep_rows + rows_per_block - 1) / rows_per_block), 256, 0, st>>>(
+  if (nh > 384) return DLLM_ERR_SHAPE;   // prep kernel parks nh x 32 floats in (default-limit) shared memory
+  attn_bwd_prep_kernel<D><<<static_cast<unsigned>(static_cast<long>(B) * (Sp / 32)), 256, static_cast<size_t>(nh) * 32 * sizeof(float), st>>>(
       dout, out, lse, delta, lse2, B, S, Sp, nh, ld_o);
   dim3 grid_kv((Skv + 127) / 128, nh, B), grid_q((S + 127) / 128, nh, B);
   if (attn_legacy()) {
