@@ -54,7 +54,7 @@ def _worker(rank, world, port, q):
     red.zero_grad()
     m(input_ids=mine, labels=mine).loss.backward()
     red.finalize()
-    grads = {k: p.grad.detach().float().cpu() for k, p in m.named_parameters()}
+    grads = {k: p.grad.detach().float().cpu().numpy() for k, p in m.named_parameters()}   # numpy: pickled by value (the worker exits early)
     copies, nb = red.copies, len(red.buckets)
     red.remove()
     # ---- sharded optimizer: 3 steps
@@ -65,7 +65,7 @@ def _worker(rank, world, port, q):
         opt.zero_grad()
         m2(input_ids=mine, labels=mine).loss.backward()
         norms.append(float(opt.step()))
-    params = {k: p.detach().float().cpu() for k, p in m2.named_parameters()}
+    params = {k: p.detach().float().cpu().numpy() for k, p in m2.named_parameters()}
     q.put((rank, grads, copies, nb, params, norms, opt.launched))
     dist.destroy_process_group()
 
@@ -83,6 +83,7 @@ def test_sharded_adamw_and_reducer_over_nccl():
         p.join(timeout=120)
     assert all(p.exitcode == 0 for p in procs)
     (_, g0, copies0, nb, p0, n0, l0), (_, g1, copies1, _, p1, n1, l1) = res
+    g0, g1, p0, p1 = ({k: torch.from_numpy(v) for k, v in d.items()} for d in (g0, g1, p0, p1))
     # ranks agree
     for k in p0:
         assert torch.equal(p0[k], p1[k]), f"sharded parameters diverged on {k}"
