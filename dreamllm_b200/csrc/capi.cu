@@ -240,11 +240,6 @@ int dllm_attn_bwd_ex(const void* dout, const void* q, const void* k, const void*
   return attn_bwd_ex(dout, q, k, v, out, lse, dq, dk, dv, seqlens, workspace, workspace_bytes, B, Sq, Skv, nh, d, ld_q, ld_kv, ld_o,
                      ld_dq, ld_dkv, causal, scale, S(stream));
 }
-int dllm_groupnorm_nhwc_stats(const void* x, const void* w, const void* b, void* y, float* stats, void* workspace, size_t ws_bytes, int N,
-                              int HW, int C, int G, float eps, int silu, void* stream) {
-  ensure_context(x);
-  return groupnorm_nhwc_stats(x, w, b, y, stats, workspace, ws_bytes, N, HW, C, G, eps, silu, S(stream));
-}
 int dllm_groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, void* stream) {
   ensure_context(x);
   return groupnorm_stats(x, stats, workspace, ws_bytes, N, HW, C, G, eps, S(stream));

@@ -2,9 +2,6 @@
 // Reference call sites: StableDiffusionHead.pipeline, modeling_plugins.py:809-833 (unet(...) -> CFG combine ->
 // scheduler.step), whose arithmetic is diffusers 0.24 (ResnetBlock2D GroupNorm+SiLU, GEGLU, Upsample2D, Downsample2D,
 // Timesteps, DDIM/DDPM step) — restated in oracle/unet_oracle.py.
-#include <cooperative_groups.h>
-#include <stdlib.h>
-
 #include "common.cuh"
 #include "gemm_sm100.h"
 #include "ops.h"
@@ -288,128 +285,6 @@ __global__ void __launch_bounds__(kGnMaxThreads) gn_apply_kernel(const bf16* __r
   }
 }
 
-// One-launch forward GroupNorm for tensors whose partial-sum grid fits the GPU at once (cooperative launch):
-//   phase 1 = gn_partial_kernel<false> (same chunking, same order) -> grid barrier -> phase 2 = every CTA redoes gn_finalize_kernel's
-//   reduction for the G groups of its image (same lane-strided order + shuffle tree; the chunk-0 CTA also publishes {mean, rstd} for the
-//   backward) -> phase 3 = gn_apply_kernel<false> over the rows the CTA has just summed (L1 / L2 hits).
-// Bit-identical to the three-launch sequence.  Why: at the stage-1 training shape (4 samples) a GroupNorm moves 21 MB and its three
-// dependent launches took 12 + 4 + 21 us plus two launch gaps — ~1 TB/s, 13.5 % of the step (profiles/r03b_c5_launch_list_partial.md).
-__global__ void __launch_bounds__(kGnMaxThreads) gn_fused_fwd_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w,
-                                                                     const bf16* __restrict__ b, float* __restrict__ partial,
-                                                                     float* __restrict__ stats, bf16* __restrict__ y, int HW, int C, int G,
-                                                                     int rows_per_cta, int RL, float count, float eps, int silu) {
-  extern __shared__ float sm[];  // phase 1: [RL][2][C]; phase 2/3: [G][2] {mean, rstd}
-  const int n = blockIdx.y, chunk = blockIdx.x, nchunks = gridDim.x;
-  const int nvec = C >> 3, cpg = C / G;
-  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
-  const int r0 = chunk * rows_per_cta, r1 = min(HW, r0 + rows_per_cta);
-  const size_t base = static_cast<size_t>(n) * HW * C;
-  const V8* xb = reinterpret_cast<const V8*>(x + base) + v;
-  constexpr int kU = GnUnroll<false>::v;
-  {
-    float s[8], q[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-    for (int r = r0 + rl; r < r1; r += RL * kU) {
-      V8 xv[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int rr = r + u * RL;
-        if (rr < r1) xv[u] = xb[static_cast<size_t>(rr) * nvec];
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int rr = r + u * RL;
-        if (rr < r1) {
-          float f[8];
-          up8(xv[u], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] += f[j] * f[j]; }
-        }
-      }
-    }
-    float* sm_s = sm + (static_cast<size_t>(rl) * 2) * C + v * 8;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { sm_s[j] = s[j]; sm_s[C + j] = q[j]; }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
-      float a = 0.f;
-      for (int l = 0; l < RL; ++l) a += sm[static_cast<size_t>(l) * 2 * C + i];
-      sm[i] = a;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
-      const int g = i >> 1, which = i & 1;
-      const float* p0 = sm + which * C + g * cpg;
-      float a = 0.f;
-      for (int c = 0; c < cpg; ++c) a += p0[c];
-      partial[((static_cast<size_t>(n) * nchunks + chunk) * G + g) * 2 + which] = a;
-    }
-  }
-  __threadfence();
-  cooperative_groups::this_grid().sync();
-  {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int g = warp; g < G; g += nwarps) {
-      float a = 0.f, bsum = 0.f;
-      for (int c = lane; c < nchunks; c += 32) {
-        const float2 p = *reinterpret_cast<const float2*>(partial + ((static_cast<size_t>(n) * nchunks + c) * G + g) * 2);
-        a += p.x;
-        bsum += p.y;
-      }
-      a = warp_sum(a);
-      bsum = warp_sum(bsum);
-      if (lane == 0) {
-        const float mean = a / count;
-        const float var = fmaxf(bsum / count - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
-        sm[2 * g] = mean;
-        sm[2 * g + 1] = rstd;
-        if (chunk == 0) {
-          stats[(static_cast<size_t>(n) * G + g) * 2] = mean;
-          stats[(static_cast<size_t>(n) * G + g) * 2 + 1] = rstd;
-        }
-      }
-    }
-  }
-  __syncthreads();
-  {
-    float wf[8], bf_[8], mean[8], rstd[8];
-    up8(reinterpret_cast<const V8*>(w)[v], wf);
-    up8(reinterpret_cast<const V8*>(b)[v], bf_);
-    const GnVecGroups gg = gn_vec_groups(v, cpg, G);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mean[j] = sm[2 * gg.gidx[j]];
-      rstd[j] = sm[2 * gg.gidx[j] + 1];
-    }
-    V8* ob = reinterpret_cast<V8*>(y + base) + v;
-    for (int r = r0 + rl; r < r1; r += RL * kU) {
-      V8 xv[kU];
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int rr = r + u * RL;
-        if (rr < r1) xv[u] = xb[static_cast<size_t>(rr) * nvec];
-      }
-#pragma unroll
-      for (int u = 0; u < kU; ++u) {
-        const int rr = r + u * RL;
-        if (rr < r1) {
-          float f[8], o[8];
-          up8(xv[u], f);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float t = r16((f[j] - mean[j]) * rstd[j] * wf[j] + bf_[j]);
-            if (silu) t = t / (1.f + expf(-t));
-            o[j] = t;
-          }
-          ob[static_cast<size_t>(rr) * nvec] = pk8(o);
-        }
-      }
-    }
-  }
-}
-
 // pixel rows per partial-sum CTA: 64 for the big UNet planes, more for the VAE's 512x512 planes so that the finalize pass never walks
 // more than 128 partials, fewer for small planes so that the grid still covers the 148 SMs
 static inline int gn_rows(int HW, int N) {
@@ -445,44 +320,16 @@ static void gn_launch_apply(const bf16* x, const bf16* w, const bf16* b, const f
   gn_apply_kernel<false><<<dim3((HW + rows - 1) / rows, N), m.threads, 0, s>>>(x, nullptr, w, b, stats, nullptr, nullptr, y, HW, C, G, rows,
                                                                                 m.RL, silu);
 }
-// one cooperative launch when the partial-sum grid is co-resident (DLLM_GN_NO_FUSE=1: always the three-launch path, for A/B runs)
-static bool gn_try_fused(const bf16* x, const bf16* w, const bf16* b, float* partial, float* stats, bf16* y, int N, int HW, int C, int G,
-                         float eps, int silu, cudaStream_t s) {
-  static int off = -1;
-  if (off < 0) { const char* e = getenv("DLLM_GN_NO_FUSE"); off = (e && e[0] == '1') ? 1 : 0; }
-  if (off) return false;
-  const GnMap m = gn_map(C);
-  if (m.threads % 32 || 2 * G > m.RL * 2 * C) return false;
-  const int rows = gn_rows(HW, N);
-  const int nchunks = (HW + rows - 1) / rows;
-  const size_t smem = static_cast<size_t>(m.RL) * 2 * C * sizeof(float);
-  if (smem > 48 * 1024) return false;
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_fwd_kernel, m.threads, smem) != cudaSuccess) return false;
-  if (static_cast<long>(N) * nchunks > static_cast<long>(per_sm) * num_sms()) return false;
-  int rl = m.RL;
-  float count = static_cast<float>(HW) * (C / G);
-  void* args[] = {(void*)&x, (void*)&w, (void*)&b, (void*)&partial, (void*)&stats, (void*)&y, (void*)&HW, (void*)&C, (void*)&G,
-                  (void*)&rows, (void*)&rl, (void*)&count, (void*)&eps, (void*)&silu};
-  return cudaLaunchCooperativeKernel((const void*)gn_fused_fwd_kernel, dim3(nchunks, N), dim3(m.threads), args, smem, s) == cudaSuccess;
-}
-// y = groupnorm(x) (+SiLU); stats_out (nullable) receives {mean, rstd} per (n, group) for the backward
-int groupnorm_nhwc_stats(const void* x, const void* w, const void* b, void* y, float* stats_out, void* workspace, size_t ws_bytes, int N,
-                         int HW, int C, int G, float eps, int silu, cudaStream_t s) {
+int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW, int C,
+                   int G, float eps, int silu, cudaStream_t s) {
   DLLM_REQUIRE_ALIGN16(x, w, b, y);
   if (int rc = gn_check(N, HW, C, G, ws_bytes)) return rc;
   float* partial = static_cast<float*>(workspace);
   const int rows = gn_rows(HW, N);
-  float* stats = stats_out ? stats_out : partial + static_cast<size_t>(N) * ((HW + rows - 1) / rows) * G * 2;
-  if (gn_try_fused((const bf16*)x, (const bf16*)w, (const bf16*)b, partial, stats, (bf16*)y, N, HW, C, G, eps, silu, s)) return 0;
-  (void)cudaGetLastError();   // a refused cooperative launch leaves no work behind; fall through to the three-launch path
+  float* stats = partial + static_cast<size_t>(N) * ((HW + rows - 1) / rows) * G * 2;
   gn_launch_stats((const bf16*)x, stats, partial, N, HW, C, G, eps, s);
   gn_launch_apply((const bf16*)x, (const bf16*)w, (const bf16*)b, stats, (bf16*)y, N, HW, C, G, silu, s);
   return cudaGetLastError() == cudaSuccess ? 0 : DLLM_ERR_LAUNCH;
-}
-int groupnorm_nhwc(const void* x, const void* w, const void* b, void* y, void* workspace, size_t ws_bytes, int N, int HW, int C,
-                   int G, float eps, int silu, cudaStream_t s) {
-  return groupnorm_nhwc_stats(x, w, b, y, nullptr, workspace, ws_bytes, N, HW, C, G, eps, silu, s);
 }
 
 // ------------------------------------------------------------------------------------------------ GEGLU

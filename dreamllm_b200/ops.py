@@ -438,12 +438,13 @@ def groupnorm(x_nhwc, weight, bias, groups, eps, silu, return_stats=False):
     if not return_stats:
         check(lib().dllm_groupnorm_nhwc(_p(x_nhwc), _p(weight), _p(bias), _p(y), _p(ws), wsb, N, HW, C, groups, float(eps), int(silu),
                                         _stream()), "dllm_groupnorm_nhwc")
-        LAUNCHES.add(1)
+        LAUNCHES.add(3)
         return y
     stats = torch.empty((N, groups, 2), device=x_nhwc.device, dtype=torch.float32)
-    check(lib().dllm_groupnorm_nhwc_stats(_p(x_nhwc), _p(weight), _p(bias), _p(y), _p(stats), _p(ws), wsb, N, HW, C, groups, float(eps),
-                                          int(silu), _stream()), "dllm_groupnorm_nhwc_stats")
-    LAUNCHES.add(1)      # one cooperative launch at small batch; three launches (stats / finalize / apply) when the grid does not fit the GPU
+    check(lib().dllm_groupnorm_stats(_p(x_nhwc), _p(stats), _p(ws), wsb, N, HW, C, groups, float(eps), _stream()), "dllm_groupnorm_stats")
+    check(lib().dllm_groupnorm_apply(_p(x_nhwc), _p(weight), _p(bias), _p(stats), _p(y), N, HW, C, groups, int(silu), _stream()),
+          "dllm_groupnorm_apply")
+    LAUNCHES.add(3)
     return y, stats
 
 

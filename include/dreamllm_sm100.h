@@ -172,11 +172,6 @@ int dllm_sampler_step(const float* eps, float* latents, const float* noise, cons
 int dllm_attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
                      void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int Sq, int Skv, int nh,
                      int d, long ld_q, long ld_kv, long ld_o, long ld_dq, long ld_dkv, int causal, float scale, void* stream);
-/* GroupNorm(+SiLU) forward that also returns {mean, rstd} per (n, group) for the backward (stats may be NULL): diffusers ResnetBlock2D
- * norm1 / norm2 under training (modeling_plugins.py:556 unet(...)).  One cooperative launch when the tensor's partial-sum grid fits the
- * GPU (small batches), otherwise the stats / finalize / apply sequence of dllm_groupnorm_stats + dllm_groupnorm_apply; identical results. */
-int dllm_groupnorm_nhwc_stats(const void* x, const void* w, const void* b, void* y, float* stats, void* workspace, size_t ws_bytes, int N,
-                              int HW, int C, int G, float eps, int silu, void* stream);
 int dllm_groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, void* stream);
 int dllm_groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
                          void* stream);
