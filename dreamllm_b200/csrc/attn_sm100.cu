@@ -665,6 +665,19 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
         // the running reference m_run — exactly what the lazy rescale below would use unless the max grew by more than 2^8 — while the
         // same pass tracks the max; only if some row's max did grow that much is the tile redone on the slow path (S is still in TMEM:
         // P has not been stored yet).  Removes the separate max pass (~240 clk of dependent FMNMX per tile) from every warp's chain.
+        // causal: the second diagonal tile lies entirely above the diagonal for the upper half of the q tile — no key of it is visible to
+        // any row of this warp.  P = 0 without touching the exponential unit; the running max / sum do not move.
+        if (kCausal && kv_mask == nullptr && kv0 > it.q0 + warp * 32 + 31 + coff) {
+          uint32_t pz[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) pz[c] = 0u;
+          tmem_st32(tmem_S + lane_off + sb * 64, pz);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[sb]);
+          continue;
+        }
         bool redo = need_mask || j == 0;
         if (!redo) {
           const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
@@ -699,25 +712,30 @@ attn_fwd_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_con
         if (redo) {
           float mx = -INFINITY;
           if (need_mask) {
-            uint32_t mw[16];
-            if (kv_mask != nullptr) {
+            // keys [kv0, kv0 + hi) of this tile are visible to this row: sequence end and the causal diagonal fold into one bound
+            const int hi = min(it.kv_len - kv0, kCausal ? q_row + coff - kv0 + 1 : 64);
+            if (kv_mask != nullptr) {   // + key-padding mask bytes (padded prompt batch inside a kv-cache)
+              uint32_t mw[16];
               const uint4* mp = reinterpret_cast<const uint4*>(kv_mask + static_cast<size_t>(it.b) * mask_ld + kv0);
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const uint4 t = __ldg(mp + i);
                 mw[4 * i] = t.x; mw[4 * i + 1] = t.y; mw[4 * i + 2] = t.z; mw[4 * i + 3] = t.w;
               }
+#pragma unroll
+              for (int c = 0; c < 64; ++c) {
+                const bool ok = (c < hi) && (((mw[c >> 2] >> (8 * (c & 3))) & 0xffu) != 0u);
+                const float sc = ok ? __uint_as_float(sv[c]) : -INFINITY;
+                sv[c] = __float_as_uint(sc);
+                mx = fmaxf(mx, sc);
+              }
             } else {
 #pragma unroll
-              for (int i = 0; i < 16; ++i) mw[i] = 0x01010101u;
-            }
-#pragma unroll
-            for (int c = 0; c < 64; ++c) {
-              const int kvi = kv0 + c;
-              const bool ok = (kvi < it.kv_len) && (!kCausal || kvi <= q_row + coff) && (((mw[c >> 2] >> (8 * (c & 3))) & 0xffu) != 0u);
-              const float sc = ok ? __uint_as_float(sv[c]) : -INFINITY;
-              sv[c] = __float_as_uint(sc);
-              mx = fmaxf(mx, sc);
+              for (int c = 0; c < 64; ++c) {
+                const float sc = (c < hi) ? __uint_as_float(sv[c]) : -INFINITY;
+                sv[c] = __float_as_uint(sc);
+                mx = fmaxf(mx, sc);
+              }
             }
           } else {
             float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
