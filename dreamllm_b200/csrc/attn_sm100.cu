@@ -1942,6 +1942,20 @@ attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __gri
         mbar_wait(&qdo_full[rs], (g >> 2) & 1, 45);  // the bulk-copied lse / delta of this q tile are visible to this thread
         mbar_wait(&sdp_full[st], (g >> 1) & 1, 44);
         tc_fence_after();
+        // causal diagonal, per warp rather than per tile: every kv row of this warp lies below every q column of its 16 -> P^T = dS^T = 0
+        // without loads or exponentials (the upper half of the kv tile against the first q tile of the item)
+        if (kCausal && it.kv0 + wq * 32 > qc0 + 15) {
+          uint32_t z[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) z[c] = 0u;
+          tmem_st8(tmem_St + lane_off + st * 64 + part * 16, z);
+          tmem_st8(tmem_dPt + lane_off + st * 64 + part * 16, z);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&pds_full[st]);
+          continue;
+        }
         uint32_t sv[16], dv[16];
         tmem_ld16(tmem_St + lane_off + st * 64 + part * 16, sv);
         tmem_ld16(tmem_dPt + lane_off + st * 64 + part * 16, dv);
@@ -1958,7 +1972,9 @@ attn_bwd_dkdv_persist_kernel(const __grid_constant__ CUtensorMap tq, const __gri
         }
         tmem_ld_wait();
         uint32_t pw[8], dw[8];
-        const bool full_tile = (qc0 + 15 < it.len) && (it.kv0 + 127 < it.len_kv) && (!kCausal || it.kv0 + 127 <= qc0);
+        // no masking needed for THIS WARP's 32 kv rows x 16 q columns (the tile-level test sent the lower half of the kv tile down the
+        // masked path on the second diagonal q tile although all of it is visible)
+        const bool full_tile = (qc0 + 15 < it.len) && (it.kv0 + wq * 32 + 31 < it.len_kv) && (!kCausal || it.kv0 + wq * 32 + 31 <= qc0);
         if (full_tile) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
@@ -2180,12 +2196,24 @@ attn_bwd_dq_persist_kernel(const __grid_constant__ CUtensorMap tq, const __grid_
         const int kc0 = j * 64 + part * 16;
         mbar_wait(&sdp_full[st], (g >> 1) & 1, 54);
         tc_fence_after();
+        // causal diagonal per warp: all 16 kv columns lie beyond the last q row of this warp -> dS = 0 without loads or exponentials
+        if (kCausal && kc0 > it.q0 + wq * 32 + 31) {
+          uint32_t z[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) z[c] = 0u;
+          tmem_st8(tmem_dP + lane_off + st * 64 + part * 16, z);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ds_full[st]);
+          continue;
+        }
         uint32_t sv[16], dv[16];
         tmem_ld16(tmem_S + lane_off + st * 64 + part * 16, sv);
         tmem_ld16(tmem_dP + lane_off + st * 64 + part * 16, dv);
         tmem_ld_wait();
         uint32_t dw[8];
-        const bool full_tile = (it.q0 + 127 < it.len) && (kc0 + 15 < it.len_kv) && (!kCausal || kc0 + 15 <= it.q0);
+        const bool full_tile = (it.q0 + wq * 32 + 31 < it.len) && (kc0 + 15 < it.len_kv) && (!kCausal || kc0 + 15 <= it.q0 + wq * 32);   // per warp
         if (full_tile) {
 #pragma unroll
           for (int c = 0; c < 8; ++c) {
