@@ -6,6 +6,8 @@ fallback: a CPU tensor is an error.
 """
 from __future__ import annotations
 
+import weakref
+
 import torch
 
 from ._lib import check, lib
@@ -621,12 +623,17 @@ _WCACHE = {}
 
 
 def _cached_weight(key, w, build):
-    """Derived weight layouts of frozen towers (built once; rebuilt if the parameter is written to or moved)."""
+    """Derived weight layouts of frozen towers (built once; rebuilt if the parameter is written to, moved or replaced).
+
+    The entry remembers WHICH tensor object it was built from (weak reference): `id(weight)` in the key, the data pointer and the version
+    counter can all coincide for a new model's parameter once the old model has been freed (CPython reuses object slots, the caching
+    allocator reuses blocks, and two freshly loaded parameters have the same version) — the cache then served the previous model's
+    conv_in / conv_out matrices (seen as a rare, order-dependent failure of the UNet gradient test with an always identical error)."""
     ent = _WCACHE.get(key)
     tag = (w.data_ptr(), w._version, w.device, w.dtype)
-    if ent is None or ent[0] != tag:
+    if ent is None or ent[0] != tag or ent[2]() is not w:
         with torch.no_grad():
-            ent = (tag, build(w.detach()))
+            ent = (tag, build(w.detach()), weakref.ref(w, lambda _r, _k=key: _WCACHE.pop(_k, None)))
         _WCACHE[key] = ent
     return ent[1]
 
