@@ -16,6 +16,8 @@
 //   warps 4-7 epilogue: tcgen05.ld -> convert -> swizzled smem -> per-warp TMA store (overlaps next tile's MMAs)
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "common.cuh"
 #include "gemm_sm100.h"
 
@@ -551,14 +553,19 @@ int* tile_counter_slot(cudaStream_t stream) {
   constexpr int kSlots = 1024, kMaxDev = 16;
   static int* base[kMaxDev] = {nullptr};
   static unsigned next[kMaxDev] = {0};
+  static std::mutex mu;   // callers may be autograd worker threads of several devices
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 0 || dev >= kMaxDev) return nullptr;
-  if (!base[dev]) {
-    if (cudaMalloc(&base[dev], kSlots * sizeof(int)) != cudaSuccess) return nullptr;
-    cudaMemset(base[dev], 0, kSlots * sizeof(int));
+  int* slot;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!base[dev]) {
+      if (cudaMalloc(&base[dev], kSlots * sizeof(int)) != cudaSuccess) return nullptr;
+      cudaMemset(base[dev], 0, kSlots * sizeof(int));
+    }
+    slot = base[dev] + (next[dev]++ % kSlots);
   }
-  int* slot = base[dev] + (next[dev]++ % kSlots);
   if (cudaMemsetAsync(slot, 0, sizeof(int), stream) != cudaSuccess) return nullptr;
   return slot;
 }

@@ -40,6 +40,45 @@ def test_sass_contains_tcgen05_and_tma():
     assert "HMMA.16816" not in sass      # no legacy mma.sync path
 
 
+def test_tile_gemm_mma_instructions_are_issued_back_to_back():
+    """Regression guard for the round-2 issue-path fix (profiles/r02j_attn_fwd_timeline.md): inside a tile-GEMM the UTCHMMAs must follow each
+    other directly.  With the issuer chosen by `lane == 0` ptxas wrapped every UTCHMMA in an ELECT / BRA.U.ANY loop and rebuilt the
+    operand descriptors per K step: 13 (attention) to 21 (GEMM) dependent scalar instructions ~ 100 clk between two MMAs that occupy the
+    tensor pipe for 32-128 clk.  Checked per kernel: most consecutive-UTCHMMA gaps are <= 4 instructions and none of the *typical* ones
+    (the median) exceeds 3."""
+    import re
+    import statistics
+    import subprocess
+    from dreamllm_b200 import _lib
+    _lib.build()
+    bdir = os.path.join(os.path.dirname(_lib.LIB_PATH), "build")
+    checked = 0
+    for obj in ("gemm_sm100.o", "attn_sm100.o"):
+        sass = subprocess.run(["cuobjdump", "-sass", os.path.join(bdir, obj)], capture_output=True, text=True).stdout
+        cur, idx, n = None, [], 0
+        funcs = {}
+        for line in sass.splitlines():
+            m = re.search(r"Function : (\S+)", line)
+            if m:
+                cur, n = m.group(1), 0
+                funcs[cur] = []
+                continue
+            if cur and re.match(r"\s+/\*[0-9a-f]{4}\*/", line):
+                n += 1
+                if "UTCHMMA" in line:
+                    funcs[cur].append(n)
+        for name, pos in funcs.items():
+            if len(pos) < 4:
+                continue
+            if "attn_" in name and "persist" not in name and "_ts_" not in name and "attn_fwd_kernel" not in name:
+                continue                                   # round-1 data-path kernels kept only for DLLM_ATTN_LEGACY A/B runs
+            gaps = [b - a for a, b in zip(pos, pos[1:])]
+            assert statistics.median(gaps) <= 3, (name[:80], gaps)
+            assert sum(g <= 4 for g in gaps) >= 0.6 * len(gaps), (name[:80], gaps)
+            checked += 1
+    assert checked >= 20, checked
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_no_cpu_fallback():
     from dreamllm_b200 import ops
