@@ -1699,7 +1699,7 @@ attn_bwd_dq_ts_kernel(const __grid_constant__ CUtensorMap tq, const __grid_const
 // work on average — 40 % of the SM's time.  Persistent:
 //   * the Q/dO (dK/dV kernel) resp. K/V (dQ kernel) operand ring and every barrier phase keep counting across items, so the producer
 //     prefetches the next item's first ring tiles while the current item's last iterations and epilogue run;
-//   * the stationary operands (K, V resp. Q, dO) are refilled as soon as the item's last S / dP tile-GEMMs retire (`stat_empty`);
+//   * the stationary operands (K, V resp. Q, dO) are refilled as soon as the item's last S / dP tile-GEMMs retire (`kv_empty` in the dK/dV kernel, `q_empty` in the dQ kernel);
 //   * the accumulators leave through the operand ring: the epilogue stages bf16 tiles in the ring stage(s) the item used last (free once
 //     its last accumulate-MMAs retire), and the producer refills those stages only after the `stored_cnt` counter says the bulk stores have read them;
 //   * the next item's first accumulate-MMA (accumulate = 0) needs P^T/dS^T of that item from all 16 row warps, which produce it only
