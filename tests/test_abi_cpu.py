@@ -114,6 +114,40 @@ def test_host_only_entry_points_answer_without_a_gpu():
     assert L.dllm_get_reserved_sms() == 0
 
 
+def test_split_k_plan_never_has_an_empty_slice():
+    """`dllm_gemm_splitk_workspace_bytes` / `dllm_conv3x3_splitk_workspace_bytes` are host code (148 SMs assumed without a device): the
+    slice count they imply must divide the K blocks without an empty last slice.  The kernel gives every slice ceil(num_kb / ks) blocks, so
+    ks = 16 over 90 blocks made slice 15 start past the end and store an accumulator no MMA had initialised (round 2, caught by the conv
+    parity test on the GPU); small outputs must be split, full waves must not."""
+    from dreamllm_b200 import _lib
+    L = _lib.lib()
+    if os.environ.get("DLLM_GEMM_NO_SPLITK") == "1":
+        pytest.skip("split-K disabled by environment")
+
+    def check(ws, M, N, K):
+        tile_m = 256 if M > 128 else 128
+        mp = (M + tile_m - 1) // tile_m * tile_m
+        assert ws % (mp * N * 4) == 0, (M, N, K, ws)
+        ks = ws // (mp * N * 4)
+        num_kb = (K + 63) // 64
+        per = (num_kb + ks - 1) // ks
+        assert ks >= 2 and (num_kb + per - 1) // per == ks and per >= 4, (M, N, K, ks, num_kb)
+        return ks
+
+    split = 0
+    for M in (64, 128, 256, 400, 512, 1024, 4096):
+        for N in (320, 640, 1280, 4096, 11008):
+            for K in (320, 1152, 2880, 4096, 5760, 11520, 22016):
+                ws = L.dllm_gemm_splitk_workspace_bytes(M, N, K)
+                if ws:
+                    check(ws, M, N, K)
+                    split += 1
+    assert split > 20
+    assert L.dllm_gemm_splitk_workspace_bytes(16384, 4096, 4096) == 0                     # 1024 tiles: nothing to gain
+    assert check(L.dllm_conv3x3_splitk_workspace_bytes(4, 8, 8, 640, 320), 256, 320, 9 * 640) == 15   # the shape that exposed the bug (90 K blocks)
+    assert L.dllm_conv3x3_splitk_workspace_bytes(32, 64, 64, 320, 320) == 0
+
+
 def test_optimizer_kernels_use_128_bit_accesses():
     """The HBM-bound optimizer-shard kernels stream through 128-bit vector loads / stores (LDG.E.128 / STG.E.128), no 32-bit bulk traffic."""
     import subprocess
