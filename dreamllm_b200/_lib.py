@@ -109,6 +109,7 @@ SIGNATURES = {
     "dllm_timestep_embedding_batch": (_i, [_vp, _vp, _i, _i, _vp]),
     "dllm_sampler_step": (_i, [_vp, _vp, _vp, _vp, _vp, _f, _i, _i, _l, _vp]),
     "dllm_attn_bwd_ex": (_i, [_vp] * 11 + [_sz, _i, _i, _i, _i, _i, _l, _l, _l, _l, _l, _i, _f, _vp]),
+    "dllm_attn_item_order": (None, [_i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "dllm_groupnorm_stats": (_i, [_vp, _vp, _vp, _sz, _i, _i, _i, _i, _f, _vp]),
     "dllm_groupnorm_apply": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "dllm_groupnorm_bwd_nhwc": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _vp]),

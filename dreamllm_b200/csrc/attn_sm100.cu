@@ -1723,7 +1723,7 @@ struct BwdOut {
 };
 struct ItemId { int tile, hb; };
 // w-th item in windowed order: windows of `win_heads` (head, batch) pairs, inside a window tiles in heaviest-first order
-__device__ __forceinline__ ItemId decode_item(int w, int ntiles, int n_hb, int win_heads, bool descending) {
+__host__ __device__ __forceinline__ ItemId decode_item(int w, int ntiles, int n_hb, int win_heads, bool descending) {
   const int wsz = win_heads * ntiles, n_full = n_hb / win_heads, full_items = n_full * wsz;
   int win, idx, R;
   if (w < full_items) { win = w / wsz; idx = w - win * wsz; R = win_heads; }
@@ -2465,6 +2465,17 @@ int attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, c
   if (d == 128) { if (causal) DLLM_BWD(128, true); else DLLM_BWD(128, false); }
   if (causal) DLLM_BWD(64, true); else DLLM_BWD(64, false);
 #undef DLLM_BWD
+}
+
+// host-side view of the persistent kernels' item order (tests / tooling): item w of a grid of `grid` CTAs -> (tile, head*batch index)
+void attn_item_order(int w, int ntiles, int n_hb, int grid, int descending, int* tile, int* hb, int* win_heads_out) {
+  int win_heads = (2 * grid + ntiles - 1) / ntiles;
+  if (win_heads > n_hb) win_heads = n_hb;
+  if (win_heads < 1) win_heads = 1;
+  const ItemId id = decode_item(w, ntiles, n_hb, win_heads, descending != 0);
+  *tile = id.tile;
+  *hb = id.hb;
+  if (win_heads_out) *win_heads_out = win_heads;
 }
 
 }  // namespace dllm

@@ -240,6 +240,9 @@ int dllm_attn_bwd_ex(const void* dout, const void* q, const void* k, const void*
   return attn_bwd_ex(dout, q, k, v, out, lse, dq, dk, dv, seqlens, workspace, workspace_bytes, B, Sq, Skv, nh, d, ld_q, ld_kv, ld_o,
                      ld_dq, ld_dkv, causal, scale, S(stream));
 }
+void dllm_attn_item_order(int w, int ntiles, int n_hb, int grid, int descending, int* tile, int* hb, int* win_heads) {
+  attn_item_order(w, ntiles, n_hb, grid, descending, tile, hb, win_heads);
+}
 int dllm_groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, void* stream) {
   ensure_context(x);
   return groupnorm_stats(x, stats, workspace, ws_bytes, N, HW, C, G, eps, S(stream));

@@ -172,6 +172,11 @@ int dllm_sampler_step(const float* eps, float* latents, const float* noise, cons
 int dllm_attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, const void* out, const float* lse, void* dq,
                      void* dk, void* dv, const int* seqlens, void* workspace, size_t workspace_bytes, int B, int Sq, int Skv, int nh,
                      int d, long ld_q, long ld_kv, long ld_o, long ld_dq, long ld_dkv, int causal, float scale, void* stream);
+/* Host-only: the order in which the persistent attention kernels (flash attention replacing flash_attn_func / flash_attn_varlen_func,
+ * modeling_dreamllm.py:532-551) hand out their (tile, head x batch) work items — item w of a launch with `grid` resident CTAs.  Windows of
+ * win_heads = ceil(2 * grid / ntiles) consecutive (head, batch) pairs; inside a window heaviest tiles first (descending != 0: highest
+ * tile index first — forward / dQ under a causal mask; 0: lowest first — dK/dV).  For tests and tooling; no device work. */
+void dllm_attn_item_order(int w, int ntiles, int n_hb, int grid, int descending, int* tile, int* hb, int* win_heads);
 int dllm_groupnorm_stats(const void* x, float* stats, void* workspace, size_t ws_bytes, int N, int HW, int C, int G, float eps, void* stream);
 int dllm_groupnorm_apply(const void* x, const void* w, const void* b, const float* stats, void* y, int N, int HW, int C, int G, int silu,
                          void* stream);
