@@ -1723,7 +1723,7 @@ struct BwdOut {
 };
 struct ItemId { int tile, hb; };
 // w-th item in windowed order: windows of `win_heads` (head, batch) pairs, inside a window tiles in heaviest-first order
-__host__ __device__ __forceinline__ ItemId decode_item(int w, int ntiles, int n_hb, int win_heads, bool descending) {
+__device__ __forceinline__ ItemId decode_item(int w, int ntiles, int n_hb, int win_heads, bool descending) {
   const int wsz = win_heads * ntiles, n_full = n_hb / win_heads, full_items = n_full * wsz;
   int win, idx, R;
   if (w < full_items) { win = w / wsz; idx = w - win * wsz; R = win_heads; }
@@ -2467,14 +2467,19 @@ int attn_bwd_ex(const void* dout, const void* q, const void* k, const void* v, c
 #undef DLLM_BWD
 }
 
-// host-side view of the persistent kernels' item order (tests / tooling): item w of a grid of `grid` CTAs -> (tile, head*batch index)
+// host-side mirror of decode_item (tests / tooling): item w of a grid of `grid` CTAs -> (tile, head*batch index).  Kept as a separate
+// host function with the same arithmetic so that the device translation unit is exactly the one validated on hardware.
 void attn_item_order(int w, int ntiles, int n_hb, int grid, int descending, int* tile, int* hb, int* win_heads_out) {
   int win_heads = (2 * grid + ntiles - 1) / ntiles;
   if (win_heads > n_hb) win_heads = n_hb;
   if (win_heads < 1) win_heads = 1;
-  const ItemId id = decode_item(w, ntiles, n_hb, win_heads, descending != 0);
-  *tile = id.tile;
-  *hb = id.hb;
+  const int wsz = win_heads * ntiles, n_full = n_hb / win_heads, full_items = n_full * wsz;
+  int win, idx, R;
+  if (w < full_items) { win = w / wsz; idx = w - win * wsz; R = win_heads; }
+  else { win = n_full; idx = w - full_items; R = n_hb - n_full * win_heads; }
+  const int tpos = idx / R;
+  *tile = descending ? ntiles - 1 - tpos : tpos;
+  *hb = win * win_heads + idx - tpos * R;
   if (win_heads_out) *win_heads_out = win_heads;
 }
 
